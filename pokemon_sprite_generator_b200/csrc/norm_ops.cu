@@ -1,0 +1,308 @@
+// GroupNorm (+ optional SiLU) forward / backward over token-major (NHWC) activations.  SURVEY.md §2.1 K4/K5.
+//
+// Reference ops replaced: nn.GroupNorm + F.silu in ResBlock (src/models/unet.py:79,89,115,127), the eps=1e-6
+// norms of CrossAttentionBlock (:156-157,214,231) and final_conv.0 (:397-398), forward and autograd backward.
+//
+// Layout: x[b, pix, c] with pixel pitch ld (so channel slices of concat buffers work), c contiguous.
+// Each thread owns 8 consecutive channels (one 16-byte vector for bf16) for all pixels of its slice, so
+// global accesses are coalesced 16B vectors.  Statistics are fp32, reduced in a fixed order:
+//   forward : partial (sum, sumsq) per (b, slice, group)          -> apply (normalise, affine, SiLU)
+//   backward: partial (sum dn, sum dn*xhat) per (b, slice, chan)  -> apply (dx) + reduce (dgamma, dbeta)
+// Bandwidth-bound: forward reads x twice (second pass from L2 when the sample fits) and writes y once.
+#include "psg_common.cuh"
+
+namespace {
+
+constexpr int kMaxThreads = 512;
+
+struct GNShape {
+  int B, HW, C, G, cpg;
+  int vpp;          // vectors (8 ch) per pixel
+  int rows;         // pixel rows handled concurrently by a block = blockDim / vpp
+  int S;            // slices per sample
+  int pix_per_slice;
+};
+
+__device__ __forceinline__ float act_fwd(float n, int act) { return act == 1 ? psg_silu(n) : n; }
+__device__ __forceinline__ float act_bwd(float n, int act) { return act == 1 ? psg_silu_grad(n) : 1.f; }
+
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x, long long ld, GNShape s, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [G][2]
+  const int b = blockIdx.y, sl = blockIdx.x;
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % s.vpp, row = threadIdx.x / s.vpp;
+  const int p0 = sl * s.pix_per_slice, p1 = min(s.HW, p0 + s.pix_per_slice);
+  float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (row < s.rows) {
+    const T* base = x + ((long long)b * s.HW) * ld + v * 8;
+    for (int p = p0 + row; p < p1; p += s.rows) {
+      Vec8<T> t;
+      t.load(base + (long long)p * ld);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sum[j] += t.v[2 * j] + t.v[2 * j + 1];
+        sq[j] += t.v[2 * j] * t.v[2 * j] + t.v[2 * j + 1] * t.v[2 * j + 1];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (v * 8 + 2 * j) / s.cpg;
+      atomicAdd(&sm[2 * g], sum[j]);
+      atomicAdd(&sm[2 * g + 1], sq[j]);
+    }
+  }
+  __syncthreads();
+  float* out = partial + ((long long)(b * s.S + sl) * s.G) * 2;
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) out[i] = sm[i];
+}
+
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ x, long long ld, T* __restrict__ y, long long ldy,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, GNShape s,
+                                const float* __restrict__ partial, float* __restrict__ stats, float eps, int act) {
+  extern __shared__ float sm[];  // [G][2] mean, rstd
+  const int b = blockIdx.y, sl = blockIdx.x;
+  for (int g = threadIdx.x; g < s.G; g += blockDim.x) {
+    float su = 0.f, sq = 0.f;
+    for (int k = 0; k < s.S; ++k) {
+      const float* pp = partial + ((long long)(b * s.S + k) * s.G + g) * 2;
+      su += pp[0];
+      sq += pp[1];
+    }
+    const float m = (float)s.cpg * (float)s.HW;
+    const float mean = su / m;
+    const float var = fmaxf(sq / m - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    sm[2 * g] = mean;
+    sm[2 * g + 1] = rstd;
+    if (sl == 0) { stats[((long long)b * s.G + g) * 2] = mean; stats[((long long)b * s.G + g) * 2 + 1] = rstd; }
+  }
+  __syncthreads();
+  const int v = threadIdx.x % s.vpp, row = threadIdx.x / s.vpp;
+  if (row >= s.rows) return;
+  float ga[8], be[8], mu[8], rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = v * 8 + j, g = c / s.cpg;
+    ga[j] = gamma[c]; be[j] = beta[c]; mu[j] = sm[2 * g]; rs[j] = sm[2 * g + 1];
+  }
+  const int p0 = sl * s.pix_per_slice, p1 = min(s.HW, p0 + s.pix_per_slice);
+  const T* xb = x + ((long long)b * s.HW) * ld + v * 8;
+  T* yb = y + ((long long)b * s.HW) * ldy + v * 8;
+  for (int p = p0 + row; p < p1; p += s.rows) {
+    Vec8<T> t;
+    t.load(xb + (long long)p * ld);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t.v[j] = act_fwd((t.v[j] - mu[j]) * rs[j] * ga[j] + be[j], act);
+    t.store(yb + (long long)p * ldy);
+  }
+}
+
+// backward pass 1: per-channel partial sums of dn and dn*xhat, dn = dy * act'(n)
+template <typename T>
+__global__ void gn_bwd_partial_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ld,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ stats, GNShape s, float* __restrict__ partial, int act) {
+  extern __shared__ float sm[];  // [C][2]
+  const int b = blockIdx.y, sl = blockIdx.x;
+  for (int i = threadIdx.x; i < 2 * s.C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % s.vpp, row = threadIdx.x / s.vpp;
+  if (row < s.rows) {
+    float ga[8], be[8], mu[8], rs[8], a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j, g = c / s.cpg;
+      ga[j] = gamma[c]; be[j] = beta[c];
+      mu[j] = stats[((long long)b * s.G + g) * 2]; rs[j] = stats[((long long)b * s.G + g) * 2 + 1];
+      a1[j] = 0.f; a2[j] = 0.f;
+    }
+    const int p0 = sl * s.pix_per_slice, p1 = min(s.HW, p0 + s.pix_per_slice);
+    const T* xb = x + ((long long)b * s.HW) * ld + v * 8;
+    const T* db = dy + ((long long)b * s.HW) * lddy + v * 8;
+    for (int p = p0 + row; p < p1; p += s.rows) {
+      Vec8<T> tx, td;
+      tx.load(xb + (long long)p * ld);
+      td.load(db + (long long)p * lddy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (tx.v[j] - mu[j]) * rs[j];
+        const float dn = td.v[j] * act_bwd(xh * ga[j] + be[j], act);
+        a1[j] += dn;
+        a2[j] += dn * xh;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[2 * (v * 8 + j)], a1[j]);
+      atomicAdd(&sm[2 * (v * 8 + j) + 1], a2[j]);
+    }
+  }
+  __syncthreads();
+  float* out = partial + ((long long)(b * s.S + sl) * s.C) * 2;
+  for (int i = threadIdx.x; i < 2 * s.C; i += blockDim.x) out[i] = sm[i];
+}
+
+// backward pass 2: dx = rstd * (dn*gamma - (A + xhat*Bs)/m), A = sum_g dn*gamma, Bs = sum_g dn*gamma*xhat
+template <typename T>
+__global__ void gn_bwd_apply_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ld,
+                                    T* __restrict__ dx, long long lddx, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ stats, GNShape s,
+                                    const float* __restrict__ partial, int act, int accumulate) {
+  extern __shared__ float sm[];  // [G][2] : A, Bs
+  const int b = blockIdx.y, sl = blockIdx.x;
+  for (int i = threadIdx.x; i < 2 * s.G; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < s.C; c += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < s.S; ++k) {
+      const float* pp = partial + ((long long)(b * s.S + k) * s.C + c) * 2;
+      s1 += pp[0];
+      s2 += pp[1];
+    }
+    const float g = gamma[c];
+    atomicAdd(&sm[2 * (c / s.cpg)], g * s1);
+    atomicAdd(&sm[2 * (c / s.cpg) + 1], g * s2);
+  }
+  __syncthreads();
+  const int v = threadIdx.x % s.vpp, row = threadIdx.x / s.vpp;
+  if (row >= s.rows) return;
+  const float inv_m = 1.f / ((float)s.cpg * (float)s.HW);
+  float ga[8], be[8], mu[8], rs[8], A[8], Bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = v * 8 + j, g = c / s.cpg;
+    ga[j] = gamma[c]; be[j] = beta[c];
+    mu[j] = stats[((long long)b * s.G + g) * 2]; rs[j] = stats[((long long)b * s.G + g) * 2 + 1];
+    A[j] = sm[2 * g] * inv_m; Bs[j] = sm[2 * g + 1] * inv_m;
+  }
+  const int p0 = sl * s.pix_per_slice, p1 = min(s.HW, p0 + s.pix_per_slice);
+  const T* xb = x + ((long long)b * s.HW) * ld + v * 8;
+  const T* db = dy + ((long long)b * s.HW) * lddy + v * 8;
+  T* ob = dx + ((long long)b * s.HW) * lddx + v * 8;
+  for (int p = p0 + row; p < p1; p += s.rows) {
+    Vec8<T> tx, td, to;
+    tx.load(xb + (long long)p * ld);
+    td.load(db + (long long)p * lddy);
+    if (accumulate) to.load(ob + (long long)p * lddx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (tx.v[j] - mu[j]) * rs[j];
+      const float dn = td.v[j] * act_bwd(xh * ga[j] + be[j], act);
+      const float d = rs[j] * (dn * ga[j] - A[j] - xh * Bs[j]);
+      to.v[j] = accumulate ? to.v[j] + d : d;
+    }
+    to.store(ob + (long long)p * lddx);
+  }
+}
+
+// dgamma[c] += sum over rows of partial[row][c][1]; dbeta[c] += ... [0]   (rows = B*S)
+__global__ void gn_param_grad_kernel(const float* __restrict__ partial, int rows, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float2 p = *reinterpret_cast<const float2*>(partial + ((long long)r * C + c) * 2);
+    s1 += p.x;
+    s2 += p.y;
+  }
+  dbeta[c] = accumulate ? dbeta[c] + s1 : s1;
+  dgamma[c] = accumulate ? dgamma[c] + s2 : s2;
+}
+
+int make_shape(GNShape& s, int B, int HW, int C, int G, int slices, int* threads) {
+  if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G != 0 || C % 8 != 0) return -1;
+  s.B = B; s.HW = HW; s.C = C; s.G = G; s.cpg = C / G;
+  if (s.cpg % 2 != 0) return -1;
+  s.vpp = C / 8;
+  if (s.vpp > kMaxThreads) return -1;
+  s.rows = kMaxThreads / s.vpp;
+  if (s.rows > HW) s.rows = HW;
+  *threads = ((s.rows * s.vpp + 31) / 32) * 32;
+  s.S = slices < 1 ? 1 : slices;
+  if (s.S > HW) s.S = HW;
+  s.pix_per_slice = (HW + s.S - 1) / s.S;
+  s.S = (HW + s.pix_per_slice - 1) / s.pix_per_slice;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Number of slices per sample psg_groupnorm_* will use for (B, HW); workspace sizes derive from it:
+//   forward  workspace floats >= B * S * G * 2 ; backward workspace floats >= B * S * C * 2
+int psg_groupnorm_slices(int B, int HW) {
+  int target = 2 * psg_num_sms();
+  int S = (target + B - 1) / (B > 0 ? B : 1);
+  int max_s = HW / 16 > 0 ? HW / 16 : 1;   // keep >= 16 pixels per slice
+  if (S > max_s) S = max_s;
+  if (S < 1) S = 1;
+  int pps = (HW + S - 1) / S;
+  return (HW + pps - 1) / pps;
+}
+
+// y = act(GroupNorm(x)); stats[b][g] = (mean, rstd) saved for backward.  act: 0 none, 1 SiLU.
+int psg_groupnorm_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
+                      float* stats, float* workspace, int B, int HW, int C, int G, float eps, int act, int dtype,
+                      void* stream) {
+  PSG_CHECK_ARG(x && y && gamma && beta && stats && workspace, "psg_groupnorm_fwd: null pointer");
+  GNShape s;
+  int threads;
+  PSG_CHECK_ARG(make_shape(s, B, HW, C, G, psg_groupnorm_slices(B, HW), &threads) == 0,
+                "psg_groupnorm_fwd: unsupported shape B=%d HW=%d C=%d G=%d (need C%%8==0, even channels/group)", B, HW, C, G);
+  PSG_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0),
+                "psg_groupnorm_fwd: pitches/pointers must be 16B aligned");
+  PSG_CHECK_ARG(B <= 65535, "psg_groupnorm_fwd: B too large");
+  dim3 grid(s.S, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = 2 * G * sizeof(float);
+  if (dtype == PSG_DTYPE_BF16) {
+    gn_stats_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)x, ld_x, s, workspace);
+    gn_apply_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)x, ld_x, (__nv_bfloat16*)y, ld_y, gamma, beta,
+                                                                s, workspace, stats, eps, act);
+  } else {
+    gn_stats_kernel<float><<<grid, threads, smem, st>>>((const float*)x, ld_x, s, workspace);
+    gn_apply_kernel<float><<<grid, threads, smem, st>>>((const float*)x, ld_x, (float*)y, ld_y, gamma, beta, s, workspace, stats,
+                                                        eps, act);
+  }
+  PSG_CHECK_LAUNCH("psg_groupnorm_fwd");
+  return PSG_OK;
+}
+
+// dx (+)= dL/dx; dgamma/dbeta (+)= parameter grads (fp32).  workspace floats >= B*S*C*2.
+int psg_groupnorm_bwd(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,
+                      const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta,
+                      float* workspace, int B, int HW, int C, int G, int act, int dtype, int accumulate_dx,
+                      int accumulate_params, void* stream) {
+  PSG_CHECK_ARG(dy && x && dx && gamma && beta && stats && dgamma && dbeta && workspace, "psg_groupnorm_bwd: null pointer");
+  GNShape s;
+  int threads;
+  PSG_CHECK_ARG(make_shape(s, B, HW, C, G, psg_groupnorm_slices(B, HW), &threads) == 0,
+                "psg_groupnorm_bwd: unsupported shape B=%d HW=%d C=%d G=%d", B, HW, C, G);
+  PSG_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0, "psg_groupnorm_bwd: pitches must be multiples of 8");
+  PSG_CHECK_ARG(B <= 65535, "psg_groupnorm_bwd: B too large");
+  dim3 grid(s.S, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem1 = 2 * (size_t)C * sizeof(float), smem2 = 2 * G * sizeof(float);
+  if (dtype == PSG_DTYPE_BF16) {
+    gn_bwd_partial_kernel<__nv_bfloat16><<<grid, threads, smem1, st>>>((const __nv_bfloat16*)dy, ld_dy, (const __nv_bfloat16*)x, ld_x,
+                                                                      gamma, beta, stats, s, workspace, act);
+    gn_bwd_apply_kernel<__nv_bfloat16><<<grid, threads, smem2, st>>>((const __nv_bfloat16*)dy, ld_dy, (const __nv_bfloat16*)x, ld_x,
+                                                                    (__nv_bfloat16*)dx, ld_dx, gamma, beta, stats, s, workspace, act,
+                                                                    accumulate_dx);
+  } else {
+    gn_bwd_partial_kernel<float><<<grid, threads, smem1, st>>>((const float*)dy, ld_dy, (const float*)x, ld_x, gamma, beta, stats, s,
+                                                              workspace, act);
+    gn_bwd_apply_kernel<float><<<grid, threads, smem2, st>>>((const float*)dy, ld_dy, (const float*)x, ld_x, (float*)dx, ld_dx, gamma,
+                                                            beta, stats, s, workspace, act, accumulate_dx);
+  }
+  gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, B * s.S, C, dgamma, dbeta, accumulate_params);
+  PSG_CHECK_LAUNCH("psg_groupnorm_bwd");
+  return PSG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,623 @@
+// tcgen05 / TMEM / TMA GEMM + implicit-GEMM convolution engine for sm_100a (bf16 in, fp32 accumulate).
+//
+// One warp-specialised kernel, three roles (192 threads):
+//   warp 0      TMA producer  : cp.async.bulk.tensor (tiled 2D, or im2col 4D over NHWC) -> 128B-swizzled smem ring
+//   warp 1      MMA issuer    : one thread issues tcgen05.mma (M=128, N=kBlockN, K=16) into a TMEM accumulator
+//   warps 2..5  epilogue      : tcgen05.ld TMEM -> registers -> fused epilogue (gemm_epilogue.cuh) -> global
+//
+// kMode 0 ("TN"):  A K-major (tiled matrix or im2col pixels), B K-major matrix.   fprop / dgrad / linears.
+// kMode 1 ("NT"):  A MN-major matrix, B MN-major (tiled matrix or im2col pixels). wgrad (reduction over rows).
+//
+// Replaces the ATen calls behind nn.Conv2d / nn.Linear / MHA projections on the reference hot path
+// (src/models/unet.py:80,90,96,160-187,325-399); SURVEY.md §2.1 K1-K3, K6-K9.
+#include "gemm_desc.h"
+#include <cuda.h>
+#include <string.h>
+
+namespace umma {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 192;
+constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+
+struct alignas(64) KernelParams {
+  CUtensorMap tm_a;
+  CUtensorMap tm_b;
+  int M, N;
+  int num_kb, kb_per_split;
+  // mode 0, A im2col
+  int a_im2col, cblks, ksize, conv_stride, pad, flip, P, Q;
+  // mode 1, B im2col (wgrad): columns are (tap, cin)
+  int b_im2col, cin, tiles_per_tap;
+  long long split_stride;
+  PsgEpilogue epi;
+};
+
+__device__ int g_timeout_flag = 0;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU (a hung box is a strike); on timeout raise a flag
+// the host can read (psg_umma_timeout_flag) and fall through.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 24); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  atomicExch(&g_timeout_flag, 1);
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp bit layout), SWIZZLE_128B.
+//  K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1).
+//  MN-major: K-rows of 128 B (64 MN elements), 8-row groups 1024 B apart (SBO), 64-element MN groups `lbo` apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
+  return (1u << 4)                      // D = f32
+         | (1u << 7) | (1u << 10)       // A, B = bf16
+         | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue for one thread's 32 consecutive columns of one row
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint32_t (&acc)[32], long long m, long long n0,
+                                               int nvalid, long long N, float* out_override) {
+  // fast path: whole chunk valid and 16B-aligned everywhere
+  const bool vec = (nvalid == 32) && ((n0 & 7) == 0) && ((e.ldc & 7) == 0) && ((e.ldr & 7) == 0) && ((e.ld_aux & 7) == 0) &&
+                   ((e.ld_rowbias & 3) == 0);
+  if (!vec) {
+    PsgEpilogue t = e;
+    if (out_override) t.out = out_override;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) psg_epilogue_scalar(t, __uint_as_float(acc[j]), m, n0 + j, N);
+    return;
+  }
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (e.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float4 b = __ldg(b4 + j); v[4*j] += b.x; v[4*j+1] += b.y; v[4*j+2] += b.z; v[4*j+3] += b.w; }
+  }
+  if (e.rowbias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.rowbias + (m / e.rows_per_group) * e.ld_rowbias + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float4 b = __ldg(b4 + j); v[4*j] += b.x; v[4*j+1] += b.y; v[4*j+2] += b.z; v[4*j+3] += b.w; }
+  }
+  if (e.aux_out) {
+    if (e.act_dtype == PSG_DTYPE_BF16) {
+      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(e.aux_out) + m * e.ld_aux + n0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { Vec8<__nv_bfloat16> t;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t.v[i] = v[8*j+i];
+        t.store(p + 8*j); }
+    } else {
+      float* p = reinterpret_cast<float*>(e.aux_out) + m * e.ld_aux + n0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(p + 4*j) = make_float4(v[4*j], v[4*j+1], v[4*j+2], v[4*j+3]);
+    }
+  }
+  if (e.act == PSG_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = psg_gelu(v[j]);
+  } else if (e.act == PSG_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = psg_silu(v[j]);
+  }
+  if (e.aux_in) {
+    float a[32];
+    if (e.act_dtype == PSG_DTYPE_BF16) {
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + m * e.ld_aux + n0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { Vec8<__nv_bfloat16> t; t.load(p + 8*j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[8*j+i] = t.v[i]; }
+    } else {
+      const float* p = reinterpret_cast<const float*>(e.aux_in) + m * e.ld_aux + n0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = p[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      v[j] *= (e.aux_act == PSG_ACT_GELU) ? psg_gelu_grad(a[j]) : (e.aux_act == PSG_ACT_SILU ? psg_silu_grad(a[j]) : 1.f);
+  }
+  if (e.drop_threshold) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      uint32_t h = psg_hash32(e.drop_seed, (uint64_t)(m * N + n0 + j));
+      v[j] = (h >= e.drop_threshold) ? v[j] * e.drop_scale : 0.f;
+    }
+  }
+  if (e.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+  }
+  if (e.residual) {
+    if (e.act_dtype == PSG_DTYPE_BF16) {
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(e.residual) + m * e.ldr + n0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { Vec8<__nv_bfloat16> t; t.load(p + 8*j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8*j+i] += t.v[i]; }
+    } else {
+      const float* p = reinterpret_cast<const float*>(e.residual) + m * e.ldr + n0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float4 r = *reinterpret_cast<const float4*>(p + 4*j); v[4*j] += r.x; v[4*j+1] += r.y; v[4*j+2] += r.z; v[4*j+3] += r.w; }
+    }
+  }
+  if (e.out_dtype == PSG_DTYPE_BF16) {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(e.out) + m * e.ldc + n0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { Vec8<__nv_bfloat16> t;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t.v[i] = v[8*j+i];
+      t.store(p + 8*j); }
+  } else {
+    float* p = (out_override ? out_override : reinterpret_cast<float*>(e.out)) + m * e.ldc + n0;
+    if (e.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float4 o = *reinterpret_cast<float4*>(p + 4*j);
+        *reinterpret_cast<float4*>(p + 4*j) = make_float4(o.x + v[4*j], o.y + v[4*j+1], o.z + v[4*j+2], o.w + v[4*j+3]); }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(p + 4*j) = make_float4(v[4*j], v[4*j+1], v[4*j+2], v[4*j+3]);
+    }
+  }
+}
+
+__host__ __device__ constexpr uint32_t tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+template <int kBlockN, int kStages>
+struct SmemLayout {
+  static constexpr uint32_t B_BYTES = kBlockN * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t BAR_OFFSET = STAGE_BYTES * kStages;
+  static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * kStages + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int kBlockN, int kStages, int kMode>
+__global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_constant__ KernelParams p) {
+  using L = SmemLayout<kBlockN, kStages>;
+  static_assert(kBlockN % 32 == 0 && kBlockN <= 256, "BLOCK_N must be a multiple of 32 (epilogue chunk) and <= 256");
+  static_assert(kMode == 0 || kBlockN % 64 == 0, "MN-major B tiles are built from 64-wide TMA boxes");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem + L::BAR_OFFSET;
+  const uint32_t bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_tmem = bar_empty + 8 * kStages;
+  const uint32_t tmem_slot = bar_tmem + 8;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y, split = blockIdx.z;
+  const int m0 = tile_m * BLOCK_M;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tm_a);
+    prefetch_tmap(&p.tm_b);
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols_for(kBlockN));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int w0 = 0, h0 = 0, img0 = 0;
+      if (kMode == 0 && p.a_im2col) {
+        const int pq = p.P * p.Q;
+        img0 = m0 / pq;
+        const int rem = m0 - img0 * pq;
+        const int pp = rem / p.Q, qq = rem - pp * p.Q;
+        w0 = qq * p.conv_stride - p.pad;
+        h0 = pp * p.conv_stride - p.pad;
+      }
+      int b_tap = 0, b_c0 = tile_n * kBlockN;
+      if (kMode == 1 && p.b_im2col) {
+        b_tap = tile_n / p.tiles_per_tap;
+        b_c0 = (tile_n - b_tap * p.tiles_per_tap) * kBlockN;
+      }
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb0 + it;
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t full = bar_full + 8 * s;
+        mbar_expect_tx(full, L::STAGE_BYTES);
+        const uint32_t sa = smem + s * L::STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        if (kMode == 0) {
+          if (p.a_im2col) {
+            const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
+            int r = tap / p.ksize, ss = tap - r * p.ksize;
+            if (p.flip) { r = p.ksize - 1 - r; ss = p.ksize - 1 - ss; }
+            tma_load_im2col_4d(sa, &p.tm_a, full, cb * BLOCK_K, w0, h0, img0, (uint16_t)ss, (uint16_t)r);
+          } else {
+            tma_load_2d(sa, &p.tm_a, full, kb * BLOCK_K, m0);
+          }
+          tma_load_2d(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * 8192, &p.tm_a, full, m0 + 64 * j, kb * BLOCK_K);
+          if (p.b_im2col) {
+            const int pix = kb * BLOCK_K;
+            const int pq = p.P * p.Q;
+            const int img = pix / pq;
+            const int rem = pix - img * pq;
+            const int pp = rem / p.Q, qq = rem - pp * p.Q;
+            const int r = b_tap / p.ksize, ss = b_tap - r * p.ksize;
+#pragma unroll
+            for (int j = 0; j < kBlockN / 64; ++j)
+              tma_load_im2col_4d(sb + j * 8192, &p.tm_b, full, b_c0 + 64 * j, qq * p.conv_stride - p.pad,
+                                 pp * p.conv_stride - p.pad, img, (uint16_t)ss, (uint16_t)r);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockN / 64; ++j)
+              tma_load_2d(sb + j * 8192, &p.tm_b, full, tile_n * kBlockN + 64 * j, kb * BLOCK_K);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(kBlockN, kMode, kMode);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem + s * L::STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          uint64_t ad, bd;
+          if (kMode == 0) {
+            ad = make_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            bd = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+          } else {
+            ad = make_desc(sa + k * (UMMA_K * 128), 8192, 1024);
+            bd = make_desc(sb + k * (UMMA_K * 128), 8192, 1024);
+          }
+          umma_bf16(tmem_acc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(bar_tmem);             // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after();
+    const long long m = (long long)m0 + q * 32 + lane;
+    float* out_override = nullptr;
+    if (p.kb_per_split < p.num_kb) out_override = reinterpret_cast<float*>(p.epi.out) + (long long)split * p.split_stride;
+    long long col_base;
+    int col_limit;
+    if (kMode == 1 && p.b_im2col) {
+      const int tap = tile_n / p.tiles_per_tap;
+      const int c0 = (tile_n - tap * p.tiles_per_tap) * kBlockN;
+      col_base = (long long)tap * p.cin + c0;
+      col_limit = p.cin - c0;
+    } else {
+      col_base = (long long)tile_n * kBlockN;
+      col_limit = p.N - tile_n * kBlockN;
+    }
+#pragma unroll 1
+    for (int ch = 0; ch < kBlockN / 32; ++ch) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + ch * 32, acc);
+      int nvalid = col_limit - ch * 32;
+      nvalid = nvalid > 32 ? 32 : nvalid;
+      if (nkb == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0u;
+      }
+      if (m < p.M && nvalid > 0) epilogue_chunk(p.epi, acc, m, col_base + ch * 32, nvalid, p.N, out_override);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_acc, tmem_cols_for(kBlockN));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + dispatch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode_tiled = nullptr;
+static PFN_encodeIm2col g_encode_im2col = nullptr;
+
+static int load_driver_fns() {
+  if (g_encode_tiled && g_encode_im2col) return PSG_OK;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    psg_set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    return PSG_ERR_CUDA;
+  }
+  g_encode_tiled = (PFN_encodeTiled)fn;
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    psg_set_error("cuTensorMapEncodeIm2col not available: %s", cudaGetErrorString(e));
+    return PSG_ERR_CUDA;
+  }
+  g_encode_im2col = (PFN_encodeIm2col)fn;
+  return PSG_OK;
+}
+
+// 2D bf16 matrix [rows][ld] with `cols` valid columns; box = {box_cols (=64), box_rows}
+static int make_tiled_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
+                          int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    psg_set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d ptr=%p", (int)r, rows, cols, ld,
+                  box_cols, box_rows, ptr);
+    return PSG_ERR_CUDA;
+  }
+  return PSG_OK;
+}
+
+// NHWC bf16 tensor, pixel pitch ld; im2col window for a ksize x ksize filter with padding `pad`, traversal stride `stride`.
+static int make_im2col_map(CUtensorMap* tm, const PsgOperand& o, int channels_per_pixel, int pixels_per_column) {
+  cuuint64_t dims[4] = {(cuuint64_t)o.c, (cuuint64_t)o.w, (cuuint64_t)o.h, (cuuint64_t)o.n};
+  cuuint64_t strides[3] = {(cuuint64_t)o.ld * 2, (cuuint64_t)o.ld * 2 * o.w, (cuuint64_t)o.ld * 2 * o.w * o.h};
+  // bounding box of filter-window base positions: [-pad, dim - 1 + upper], upper = pad - (ksize-1)
+  int lower[2] = {-o.pad, -o.pad};
+  int upper[2] = {o.pad - (o.ksize - 1), o.pad - (o.ksize - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)o.stride, (cuuint32_t)o.stride, 1};
+  CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(o.ptr), dims, strides, lower, upper,
+                               (cuuint32_t)channels_per_pixel, (cuuint32_t)pixels_per_column, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    psg_set_error("cuTensorMapEncodeIm2col failed (%d): nhwc=%d,%d,%d,%d ld=%lld k=%d s=%d p=%d", (int)r, o.n, o.h, o.w, o.c,
+                  o.ld, o.ksize, o.stride, o.pad);
+    return PSG_ERR_CUDA;
+  }
+  return PSG_OK;
+}
+
+template <int kBlockN, int kStages, int kMode>
+static int launch(const KernelParams& kp, dim3 grid, cudaStream_t stream) {
+  using L = SmemLayout<kBlockN, kStages>;
+  static bool configured = false;
+  auto kern = umma_gemm_kernel<kBlockN, kStages, kMode>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
+    if (e != cudaSuccess) { psg_set_error("umma: cudaFuncSetAttribute(smem=%u): %s", L::TOTAL, cudaGetErrorString(e)); return PSG_ERR_CUDA; }
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, L::TOTAL, stream>>>(kp);
+  PSG_CHECK_LAUNCH("psg_umma_gemm");
+  return PSG_OK;
+}
+
+}  // namespace umma
+
+extern "C" {
+
+// block_n: 0 = auto, else one of 64/128/160/256 (160 only for K-major B).
+int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) {
+  using namespace umma;
+  PSG_CHECK_ARG(d != nullptr, "psg_umma_gemm: null desc");
+  PSG_CHECK_ARG(d->in_dtype == PSG_DTYPE_BF16, "psg_umma_gemm: operands must be bf16");
+  PSG_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "psg_umma_gemm: empty problem M=%lld N=%lld K=%lld", d->M, d->N, d->K);
+  const int am = d->a.mode, bm = d->b.mode;
+  int mode;
+  if ((am == PSG_OP_KMAJOR || am == PSG_OP_IM2COL) && bm == PSG_OP_KMAJOR) mode = 0;
+  else if (am == PSG_OP_MNMAJOR && (bm == PSG_OP_MNMAJOR || bm == PSG_OP_IM2COL_T)) mode = 1;
+  else { psg_set_error("psg_umma_gemm: unsupported operand modes a=%d b=%d", am, bm); return PSG_ERR_UNSUPPORTED; }
+  PSG_CHECK_ARG(((uintptr_t)d->a.ptr % 16 == 0) && ((uintptr_t)d->b.ptr % 16 == 0), "psg_umma_gemm: operands must be 16B aligned");
+  PSG_CHECK_ARG((d->a.ld % 8 == 0) && (d->b.ld % 8 == 0), "psg_umma_gemm: pitches must be multiples of 8 elements");
+  int rc = load_driver_fns();
+  if (rc) return rc;
+
+  KernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.M = (int)d->M;
+  kp.N = (int)d->N;
+  kp.epi = d->epi;
+  const int split = d->split_k > 1 ? d->split_k : 1;
+
+  if (block_n == 0) {
+    if (mode == 0) block_n = (d->N % 256 == 0) ? 256 : (d->N % 160 == 0 ? 160 : (d->N % 128 == 0 ? 128 : (d->N > 128 ? 256 : (d->N > 64 ? 128 : 64))));
+    else block_n = 128;
+  }
+
+  long long n_tiles;
+  if (mode == 0) {
+    if (am == PSG_OP_IM2COL) {
+      const PsgOperand& a = d->a;
+      PSG_CHECK_ARG(a.c % 64 == 0, "psg_umma_gemm: im2col needs C %% 64 == 0 (C=%d)", a.c);
+      PSG_CHECK_ARG(d->K == (long long)a.ksize * a.ksize * a.c, "psg_umma_gemm: K != ksize^2*C");
+      PSG_CHECK_ARG(d->M == (long long)a.n * a.p * a.q, "psg_umma_gemm: M != n*p*q");
+      rc = make_im2col_map(&kp.tm_a, a, 64, BLOCK_M);
+      if (rc) return rc;
+      kp.a_im2col = 1; kp.cblks = a.c / 64; kp.ksize = a.ksize; kp.conv_stride = a.stride; kp.pad = a.pad; kp.flip = a.flip;
+      kp.P = a.p; kp.Q = a.q;
+    } else {
+      PSG_CHECK_ARG(d->K % 8 == 0, "psg_umma_gemm: K %% 8 != 0");
+      rc = make_tiled_map(&kp.tm_a, d->a.ptr, d->M, d->K, d->a.ld, 64, BLOCK_M);
+      if (rc) return rc;
+    }
+    rc = make_tiled_map(&kp.tm_b, d->b.ptr, d->N, d->K, d->b.ld, 64, block_n);
+    if (rc) return rc;
+    kp.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
+    n_tiles = (d->N + block_n - 1) / block_n;
+  } else {
+    PSG_CHECK_ARG(block_n % 64 == 0, "psg_umma_gemm: MN-major B needs block_n %% 64 == 0");
+    // A: [K rows][M cols]
+    rc = make_tiled_map(&kp.tm_a, d->a.ptr, d->K, d->M, d->a.ld, 64, 64);
+    if (rc) return rc;
+    if (bm == PSG_OP_IM2COL_T) {
+      const PsgOperand& b = d->b;
+      PSG_CHECK_ARG(d->N == (long long)b.ksize * b.ksize * b.c, "psg_umma_gemm: N != ksize^2*C");
+      PSG_CHECK_ARG(d->K == (long long)b.n * b.p * b.q, "psg_umma_gemm: K != n*p*q");
+      PSG_CHECK_ARG(b.c % 8 == 0, "psg_umma_gemm: C %% 8 != 0");
+      rc = make_im2col_map(&kp.tm_b, b, 64, BLOCK_K);
+      if (rc) return rc;
+      kp.b_im2col = 1; kp.cin = b.c; kp.tiles_per_tap = (b.c + block_n - 1) / block_n;
+      kp.ksize = b.ksize; kp.conv_stride = b.stride; kp.pad = b.pad; kp.P = b.p; kp.Q = b.q;
+      n_tiles = (long long)kp.tiles_per_tap * b.ksize * b.ksize;
+    } else {
+      rc = make_tiled_map(&kp.tm_b, d->b.ptr, d->K, d->N, d->b.ld, 64, 64);
+      if (rc) return rc;
+      n_tiles = (d->N + block_n - 1) / block_n;
+    }
+    kp.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
+  }
+  kp.kb_per_split = (kp.num_kb + split - 1) / split;
+  const int eff_split = (kp.num_kb + kp.kb_per_split - 1) / kp.kb_per_split;
+  if (split > 1) {
+    PSG_CHECK_ARG(d->epi.out_dtype == PSG_DTYPE_F32, "psg_umma_gemm: split-K needs fp32 output");
+    PSG_CHECK_ARG(eff_split == split, "psg_umma_gemm: split_k=%d does not divide %d k-blocks evenly enough", split, kp.num_kb);
+    kp.split_stride = d->M * d->epi.ldc;
+  }
+  const long long m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
+  PSG_CHECK_ARG(m_tiles <= 65535 && split <= 65535, "psg_umma_gemm: grid too large");
+  dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)split);
+  cudaStream_t s = (cudaStream_t)stream;
+
+#define PSG_LAUNCH(BN, ST, MODE) return launch<BN, ST, MODE>(kp, grid, s)
+  if (mode == 0) {
+    switch (block_n) {
+      case 64: PSG_LAUNCH(64, 6, 0);
+      case 128: PSG_LAUNCH(128, 6, 0);
+      case 160: PSG_LAUNCH(160, 5, 0);
+      case 256: PSG_LAUNCH(256, 4, 0);
+    }
+  } else {
+    switch (block_n) {
+      case 64: PSG_LAUNCH(64, 6, 1);
+      case 128: PSG_LAUNCH(128, 6, 1);
+      case 256: PSG_LAUNCH(256, 4, 1);
+    }
+  }
+#undef PSG_LAUNCH
+  psg_set_error("psg_umma_gemm: unsupported block_n=%d for mode %d", block_n, mode);
+  return PSG_ERR_UNSUPPORTED;
+}
+
+// Test hook: 1 if any mbarrier wait timed out since the last call (synchronises the device).
+int psg_umma_timeout_flag() {
+  int v = 0, zero = 0;
+  cudaMemcpyFromSymbol(&v, umma::g_timeout_flag, sizeof(int));
+  cudaMemcpyToSymbol(umma::g_timeout_flag, &zero, sizeof(int));
+  return v;
+}
+
+}  // extern "C"

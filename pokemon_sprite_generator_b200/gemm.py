@@ -1,0 +1,156 @@
+"""Host-side description of GEMM / implicit-GEMM convolution problems for the two CUDA engines.
+
+`Operand` wraps a torch tensor view as one of the access modes of csrc/gemm_desc.h; `run_gemm` fills a
+PsgGemmDesc and dispatches to the tcgen05 engine (bf16) or the SIMT engine (fp32 parity mode, odd shapes).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+@dataclass
+class Operand:
+    t: torch.Tensor
+    mode: int
+    ld: int
+    rows: int          # logical rows of the [rows x K] operand
+    k: int             # logical K
+    conv: tuple = (0, 0, 0, 0, 0, 0, 1, 0, 1, 0)   # n,h,w,c,p,q,stride,pad,ksize,flip
+
+    def fill(self, o: L.PsgOperand) -> None:
+        o.ptr = self.t.data_ptr()
+        o.mode = self.mode
+        o.ld = self.ld
+        (o.n, o.h, o.w, o.c, o.p, o.q, o.stride, o.pad, o.ksize, o.flip) = self.conv
+
+
+def kmajor(t: torch.Tensor) -> Operand:
+    """[rows, K] matrix with K contiguous (row pitch arbitrary)."""
+    assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    return Operand(t, L.OP_KMAJOR, t.stride(0), t.shape[0], t.shape[1])
+
+
+def mnmajor(t: torch.Tensor) -> Operand:
+    """Memory is [K, rows] with rows contiguous; logical operand is its transpose."""
+    assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    return Operand(t, L.OP_MNMAJOR, t.stride(0), t.shape[1], t.shape[0])
+
+
+def _nhwc_geom(x: torch.Tensor):
+    assert x.dim() == 4 and x.stride(3) == 1, (x.shape, x.stride())
+    n, h, w, c = x.shape
+    ld = x.stride(2)
+    assert x.stride(1) == ld * w and (n == 1 or x.stride(0) == ld * w * h), "NHWC view must be pixel-pitched"
+    return n, h, w, c, ld
+
+
+def im2col(x: torch.Tensor, ksize: int, stride: int, pad: int, flip: bool = False) -> Operand:
+    """rows = conv output pixels (n,p,q); K = ksize^2 * C over NHWC `x`."""
+    n, h, w, c, ld = _nhwc_geom(x)
+    p = (h + 2 * pad - ksize) // stride + 1
+    q = (w + 2 * pad - ksize) // stride + 1
+    return Operand(x, L.OP_IM2COL, ld, n * p * q, ksize * ksize * c, (n, h, w, c, p, q, stride, pad, ksize, int(flip)))
+
+
+def im2col_t(x: torch.Tensor, ksize: int, stride: int, pad: int) -> Operand:
+    """rows = (tap, c); K = conv output pixels -- the wgrad "B" operand."""
+    n, h, w, c, ld = _nhwc_geom(x)
+    p = (h + 2 * pad - ksize) // stride + 1
+    q = (w + 2 * pad - ksize) // stride + 1
+    return Operand(x, L.OP_IM2COL_T, ld, ksize * ksize * c, n * p * q, (n, h, w, c, p, q, stride, pad, ksize, 0))
+
+
+def dgrad_gather(dy: torch.Tensor, in_h: int, in_w: int, ksize: int, stride: int, pad: int) -> Operand:
+    """rows = conv input pixels; K = ksize^2 * Cout gathered from NHWC `dy` (general stride; SIMT engine only)."""
+    n, h, w, c, ld = _nhwc_geom(dy)
+    return Operand(dy, L.OP_DGRAD, ld, n * in_h * in_w, ksize * ksize * c, (n, h, w, c, in_h, in_w, stride, pad, ksize, 0))
+
+
+@dataclass
+class Epilogue:
+    out: torch.Tensor                      # 2D view [M, >=N], unit column stride
+    bias: Optional[torch.Tensor] = None    # fp32 [N]
+    rowbias: Optional[torch.Tensor] = None  # fp32 [groups, N]
+    rows_per_group: int = 1
+    act: int = L.ACT_NONE
+    alpha: float = 1.0
+    residual: Optional[torch.Tensor] = None
+    aux_out: Optional[torch.Tensor] = None
+    aux_in: Optional[torch.Tensor] = None
+    aux_act: int = L.ACT_NONE
+    accumulate: bool = False
+    drop_seed: int = 0
+    drop_p: float = 0.0
+
+    def fill(self, e: L.PsgEpilogue) -> None:
+        out = self.out
+        assert out.stride(-1) == 1
+        e.out = out.data_ptr()
+        e.ldc = out.stride(0) if out.dim() == 2 else out.stride(-2)
+        e.out_dtype = L.dt(out)
+        act_t = self.residual if self.residual is not None else (self.aux_out if self.aux_out is not None else self.aux_in)
+        e.act_dtype = L.dt(act_t) if act_t is not None else L.dt(out)
+        e.bias = self.bias.data_ptr() if self.bias is not None else None
+        if self.bias is not None:
+            assert self.bias.dtype == torch.float32 and self.bias.is_contiguous()
+        if self.rowbias is not None:
+            assert self.rowbias.dtype == torch.float32 and self.rowbias.stride(1) == 1
+            e.rowbias = self.rowbias.data_ptr()
+            e.ld_rowbias = self.rowbias.stride(0)
+            e.rows_per_group = self.rows_per_group
+        else:
+            e.rowbias = None
+            e.rows_per_group = 1
+            e.ld_rowbias = 0
+        e.act = self.act
+        e.alpha = self.alpha
+        if self.residual is not None:
+            assert self.residual.stride(1) == 1
+            e.residual = self.residual.data_ptr()
+            e.ldr = self.residual.stride(0)
+        else:
+            e.residual = None
+            e.ldr = 0
+        aux = self.aux_out if self.aux_out is not None else self.aux_in
+        e.aux_out = self.aux_out.data_ptr() if self.aux_out is not None else None
+        e.aux_in = self.aux_in.data_ptr() if self.aux_in is not None else None
+        e.ld_aux = aux.stride(0) if aux is not None else 0
+        if self.aux_out is not None and self.aux_in is not None:
+            assert self.aux_out.stride(0) == self.aux_in.stride(0)
+        e.aux_act = self.aux_act
+        e.accumulate = int(self.accumulate)
+        e.drop_seed = self.drop_seed
+        if self.drop_p > 0.0:
+            e.drop_threshold = min(int(self.drop_p * 4294967296.0), 4294967295)
+            e.drop_scale = 1.0 / (1.0 - self.drop_p)
+        else:
+            e.drop_threshold = 0
+            e.drop_scale = 1.0
+
+
+def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", split_k: int = 1, block_n: int = 0) -> None:
+    """C[M,N] = epilogue(sum_k A(m,k) B(n,k)).  engine: 'umma' (tcgen05, bf16), 'simt', or 'auto'."""
+    assert a.k == b.k, f"K mismatch {a.k} vs {b.k}"
+    assert a.t.dtype == b.t.dtype, "operand dtypes differ"
+    d = L.PsgGemmDesc()
+    a.fill(d.a)
+    b.fill(d.b)
+    d.M, d.N, d.K = a.rows, b.rows, a.k
+    d.in_dtype = L.dt(a.t)
+    d.split_k = split_k
+    epi.fill(d.epi)
+    if engine == "auto":
+        engine = "umma" if a.t.dtype == torch.bfloat16 else "simt"
+    lib = L.load()
+    if engine == "umma":
+        L.check(lib.psg_umma_gemm(C.byref(d), C.c_int(block_n), L.stream_ptr()), "psg_umma_gemm")
+    elif engine == "simt":
+        L.check(lib.psg_simt_gemm(C.byref(d), L.stream_ptr()), "psg_simt_gemm")
+    else:
+        raise ValueError(engine)

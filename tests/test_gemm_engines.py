@@ -1,0 +1,209 @@
+"""GPU parity tests of the two GEMM / implicit-conv engines against plain PyTorch fp32 on the same inputs.
+
+The tcgen05 engine takes bf16 operands and accumulates in fp32, so its oracle is an fp32 matmul / conv of the
+bf16-rounded operands; tolerance = accumulation-order noise only (rtol 2e-3 of the output scale).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from pokemon_sprite_generator_b200 import _lib as L
+    from pokemon_sprite_generator_b200 import gemm as G
+    return L, G
+
+
+def _close(out, ref, tol, what):
+    out = out.float()
+    scale = ref.abs().max().item() + 1e-12
+    err = (out - ref).abs().max().item()
+    print(f"[{what}] max_abs_err={err:.3e} scale={scale:.3e} rel={err / scale:.3e}")
+    assert err <= tol * scale, f"{what}: err {err} > {tol} * {scale}"
+
+
+def _check_timeout(L):
+    flag = L.load().psg_umma_timeout_flag()
+    assert flag == 0, "tcgen05 kernel hit an mbarrier timeout"
+
+
+@pytest.mark.parametrize("engine,dtype", [("simt", torch.float32), ("simt", torch.bfloat16), ("umma", torch.bfloat16)])
+@pytest.mark.parametrize("M,N,K,block_n", [
+    (128, 64, 64, 64), (256, 256, 128, 128), (256, 256, 256, 256), (300, 320, 192, 160), (1000, 640, 1280, 0),
+    (77, 1280, 640, 0), (4096, 96, 256, 0),
+])
+def test_gemm_tn(cuda_device, engine, dtype, M, N, K, block_n):
+    L, G = _mods()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    b = torch.randn(N, K, device="cuda", generator=g).to(dtype)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=dtype)
+    G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out), engine=engine, block_n=block_n if engine == "umma" else 0)
+    torch.cuda.synchronize()
+    if engine == "umma":
+        _check_timeout(L)
+    ref = a.float() @ b.float().t()
+    tol = 1e-5 if dtype == torch.float32 else 6e-3   # bf16 output rounding dominates
+    _close(out, ref, tol, f"tn {engine} {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("engine", ["simt", "umma"])
+def test_gemm_fp32_out_and_epilogue(cuda_device, engine):
+    L, G = _mods()
+    M, N, K, rpg = 392, 640, 320, 196
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    rowbias = torch.randn(M // rpg, N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.kmajor(a), G.kmajor(b),
+               G.Epilogue(out=out, bias=bias, rowbias=rowbias, rows_per_group=rpg, act=L.ACT_GELU, alpha=0.6,
+                          residual=res, aux_out=pre), engine=engine)
+    torch.cuda.synchronize()
+    acc = a.float() @ b.float().t() + bias + rowbias.repeat_interleave(rpg, 0)
+    ref = 0.6 * F.gelu(acc) + res.float()
+    _close(pre, acc, 6e-3, f"epi-pre {engine}")
+    _close(out, ref, 6e-3, f"epi-out {engine}")
+    # backward-style epilogue: acc * gelu'(pre), fp32 accumulate into existing buffer
+    out32 = torch.ones(M, N, device="cuda")
+    G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out32, aux_in=pre, aux_act=L.ACT_GELU, accumulate=True), engine=engine)
+    torch.cuda.synchronize()
+    x = pre.float().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    ref2 = 1.0 + (a.float() @ b.float().t()) * x.grad
+    _close(out32, ref2, 2e-3, f"epi-bwd {engine}")
+    if engine == "umma":
+        _check_timeout(L)
+
+
+@pytest.mark.parametrize("engine", ["simt", "umma"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (320, 192, 1000), (640, 1280, 777), (96, 64, 4096)])
+def test_gemm_nt(cuda_device, engine, M, N, K):
+    """C[M,N] = A^T B with A stored [K,M], B stored [K,N] (wgrad layout)."""
+    L, G = _mods()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(K, M, device="cuda", generator=g).bfloat16()
+    b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    G.run_gemm(G.mnmajor(a), G.mnmajor(b), G.Epilogue(out=out), engine=engine)
+    torch.cuda.synchronize()
+    if engine == "umma":
+        _check_timeout(L)
+    ref = a.float().t() @ b.float()
+    _close(out, ref, 1e-4, f"nt {engine} {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("engine", ["simt", "umma"])
+def test_gemm_nt_split_k(cuda_device, engine):
+    if engine == "simt":
+        pytest.skip("split-K is a tcgen05-engine feature")
+    L, G = _mods()
+    M, N, K, S = 256, 128, 64 * 12, 4
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(K, M, device="cuda", generator=g).bfloat16()
+    b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+    part = torch.full((S, M, N), float("nan"), device="cuda")
+    G.run_gemm(G.mnmajor(a), G.mnmajor(b), G.Epilogue(out=part[0]), engine=engine, split_k=S)
+    torch.cuda.synchronize()
+    _check_timeout(L)
+    _close(part.sum(0), a.float().t() @ b.float(), 1e-4, "nt split-k")
+
+
+def _conv_inputs(n, h, w, cin, cout, seed, dtype):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(dtype)            # NHWC
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)).to(dtype)  # OIHW
+    return x, wt
+
+
+@pytest.mark.parametrize("engine,dtype", [("simt", torch.float32), ("umma", torch.bfloat16)])
+@pytest.mark.parametrize("n,h,cin,cout,stride", [(2, 27, 64, 64, 1), (3, 14, 128, 320, 1), (2, 7, 320, 128, 1), (5, 4, 64, 160, 1),
+                                                 (2, 27, 64, 128, 2), (2, 14, 128, 64, 2), (3, 7, 64, 64, 2)])
+def test_conv_fprop(cuda_device, engine, dtype, n, h, cin, cout, stride):
+    L, G = _mods()
+    x, wt = _conv_inputs(n, h, h, cin, cout, 3 * h + cin + cout, dtype)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()   # [Cout][tap][Cin]
+    a = G.im2col(x, 3, stride, 1)
+    out = torch.full((a.rows, cout), float("nan"), device="cuda", dtype=dtype)
+    bias = torch.randn(cout, device="cuda")
+    G.run_gemm(a, G.kmajor(wp), G.Epilogue(out=out, bias=bias), engine=engine)
+    torch.cuda.synchronize()
+    if engine == "umma":
+        _check_timeout(L)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
+    _close(out, ref, 1e-5 if dtype == torch.float32 else 6e-3, f"fprop {engine} n{n} h{h} {cin}->{cout} s{stride}")
+
+
+@pytest.mark.parametrize("engine,dtype", [("simt", torch.float32), ("umma", torch.bfloat16)])
+@pytest.mark.parametrize("n,h,cin,cout", [(2, 27, 64, 64), (3, 14, 128, 320), (4, 4, 64, 192)])
+def test_conv_dgrad_stride1(cuda_device, engine, dtype, n, h, cin, cout):
+    L, G = _mods()
+    x, wt = _conv_inputs(n, h, h, cin, cout, 17 + h, dtype)
+    dy = torch.randn(n, h, h, cout, device="cuda").to(dtype)
+    wd = wt.permute(1, 2, 3, 0).reshape(cin, 9 * cout).contiguous()   # [Cin][tap][Cout]
+    a = G.im2col(dy, 3, 1, 1, flip=True)
+    dx = torch.full((n * h * h, cin), float("nan"), device="cuda", dtype=dtype)
+    G.run_gemm(a, G.kmajor(wd), G.Epilogue(out=dx), engine=engine)
+    torch.cuda.synchronize()
+    if engine == "umma":
+        _check_timeout(L)
+    ref = torch.nn.grad.conv2d_input((n, cin, h, h), wt.float(), dy.float().permute(0, 3, 1, 2), stride=1, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, cin)
+    _close(dx, ref, 1e-5 if dtype == torch.float32 else 6e-3, f"dgrad {engine} h{h} {cin}<-{cout}")
+
+
+@pytest.mark.parametrize("h,cin,cout", [(27, 64, 128), (14, 32, 64), (7, 64, 64)])
+def test_conv_dgrad_stride2_gather(cuda_device, h, cin, cout):
+    """General-stride dgrad gather (SIMT engine)."""
+    L, G = _mods()
+    n = 2
+    _, wt = _conv_inputs(n, h, h, cin, cout, 23 + h, torch.float32)
+    p = (h + 2 - 3) // 2 + 1
+    dy = torch.randn(n, p, p, cout, device="cuda")
+    wd = wt.permute(1, 2, 3, 0).reshape(cin, 9 * cout).contiguous()
+    dx = torch.empty(n * h * h, cin, device="cuda")
+    G.run_gemm(G.dgrad_gather(dy, h, h, 3, 2, 1), G.kmajor(wd), G.Epilogue(out=dx), engine="simt")
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((n, cin, h, h), wt, dy.permute(0, 3, 1, 2), stride=2, padding=1)
+    _close(dx, ref.permute(0, 2, 3, 1).reshape(-1, cin), 1e-5, f"dgrad-s2 h{h}")
+
+
+@pytest.mark.parametrize("engine,dtype", [("simt", torch.float32), ("umma", torch.bfloat16)])
+@pytest.mark.parametrize("n,h,cin,cout,stride,split", [(2, 27, 64, 128, 1, 1), (3, 14, 128, 64, 1, 1), (8, 4, 320, 128, 1, 1),
+                                                       (2, 27, 64, 64, 2, 1), (4, 27, 64, 128, 1, 3)])
+def test_conv_wgrad(cuda_device, engine, dtype, n, h, cin, cout, stride, split):
+    L, G = _mods()
+    if engine == "simt" and split > 1:
+        pytest.skip("split-K is a tcgen05-engine feature")
+    x, wt = _conv_inputs(n, h, h, cin, cout, 31 + h + cin, dtype)
+    b = G.im2col_t(x, 3, stride, 1)
+    p = (h + 2 - 3) // stride + 1
+    dy = torch.randn(n * p * p, cout, device="cuda").to(dtype)
+    part = torch.full((split, cout, 9 * cin), float("nan"), device="cuda")
+    G.run_gemm(G.mnmajor(dy), b, G.Epilogue(out=part[0]), engine=engine, split_k=split)
+    torch.cuda.synchronize()
+    if engine == "umma":
+        _check_timeout(L)
+    dw = part.sum(0).reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3),
+                                      dy.float().reshape(n, p, p, cout).permute(0, 3, 1, 2), stride=stride, padding=1)
+    _close(dw, ref, 1e-4, f"wgrad {engine} h{h} {cin}->{cout} s{stride} split{split}")
+
+
+def test_strided_views(cuda_device):
+    """Operands and outputs that are channel slices of wider (concat) buffers."""
+    L, G = _mods()
+    M, C0, C1, N = 392, 128, 64, 128
+    cat = torch.randn(M, C0 + C1, device="cuda").bfloat16()
+    w = torch.randn(N, C1, device="cuda").bfloat16()
+    outbuf = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.kmajor(cat[:, C0:]), G.kmajor(w), G.Epilogue(out=outbuf[:, N:]), engine="umma")
+    torch.cuda.synchronize()
+    _check_timeout(L)
+    _close(outbuf[:, N:], cat[:, C0:].float() @ w.float().t(), 6e-3, "strided")
+    assert outbuf[:, :N].abs().max().item() == 0.0

@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native latent-diffusion hot path (BASELINE.json metric, config 2 / 3).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1        # CPU arm (oracle port of the reference path)
+
+A "step" is one optimisation step of the stage-2 trainer on synthetic inputs of the reference's shapes
+(SURVEY.md 8d): q_sample -> U-Net forward -> SmoothL1 -> backward -> [NCCL all-reduce] -> global-norm clip -> AdamW ->
+OneCycleLR, bf16 tensor-core compute with fp32 master weights, batch 256 per GPU (weak scaling), dropout on.
+`value` is timed with inputs resident in HBM; `e2e` runs the same step through DiffusionTrainer.train_step with pinned
+HOST inputs copied in and the loss read back every step.  Rank 0 prints exactly one JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FWD_GFLOP_PER_SAMPLE = 77.46          # SURVEY.md 8d (2*MACs over convs, linears, MHA incl. cores)
+TRAIN_GFLOP_PER_SAMPLE = 3 * FWD_GFLOP_PER_SAMPLE
+METRIC = "unet_train_latent_samples_per_s"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"), "src": "measured"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        busy = [s for s in sm if mx and s > 0.3 * mx[0]] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference step (the reference itself cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps: int, warmup: int, batch: int = 2):
+    """Times the reference algorithm's train step (improved_diffusion_trainer.py:363-413) on the host cores: oracle U-Net
+    forward + autograd backward + the 478-`.item()` norm loop + clip_grad_norm_(0.7) + AdamW(eps=1e-6), fp32, batch 2."""
+    import torch
+    from oracle import inputs, unet_oracle
+    from pokemon_sprite_generator_b200.unet import UNet
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = UNet()
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.named_parameters()}
+    sd = dict(params)
+    sd["time_embed.emb_coeff"] = model.time_embed.emb_coeff
+    del model
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-4, eps=1e-6)
+    crit = torch.nn.SmoothL1Loss(beta=0.1)
+    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
+    ns = NoiseScheduler()
+    latent, text, _, _ = inputs.make_inputs(batch, 32, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        lat = torch.clamp(latent, -3.0, 3.0)
+        t = torch.randint(0, 1000, (batch,))
+        noise = torch.randn_like(lat)
+        noisy = ns.sqrt_alphas_cumprod[t].view(-1, 1, 1, 1) * lat + ns.sqrt_one_minus_alphas_cumprod[t].view(-1, 1, 1, 1) * noise
+        opt.zero_grad()
+        pred = unet_oracle.unet_forward(sd, noisy, t, text, num_heads=4)
+        loss = crit(pred, noise)
+        loss.backward()
+        total = 0.0
+        for p in params.values():
+            total += p.grad.norm(2).item() ** 2
+        torch.nn.utils.clip_grad_norm_(list(params.values()), max_norm=0.7)
+        opt.step()
+        loss.item()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"samples_per_s": batch / sec, "ms_per_step": sec * 1e3, "cores": torch.get_num_threads(), "batch": batch, "steps": steps}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(max(1, args.steps), max(0, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "U-Net diffusion train step, 27x27x8 latents, 1000-step cosine schedule, 32x256 text emb",
+                       "sample": f"batch {r['batch']} per step on the host CPU"},
+            "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                             "sample": f"{args.steps} steps of batch {r['batch']} (oracle port of the reference step, fp32)"},
+            "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE config 2: 256)")
+    ap.add_argument("--text-len", type=int, default=32)
+    ap.add_argument("--heads", type=int, default=4, help="trainer default (improved_diffusion_trainer.py:215)")
+    ap.add_argument("--denoise-batch", type=int, default=128)
+    ap.add_argument("--denoise-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropout", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from pokemon_sprite_generator_b200 import _lib as L
+    from pokemon_sprite_generator_b200 import gemm as G
+    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
+    from pokemon_sprite_generator_b200.trainer import DiffusionTrainer, FusedAdamW, TrainStep
+    from pokemon_sprite_generator_b200.unet import UNet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.check(L.load().psg_check_device(), "psg_check_device")
+    W = max(args.warmup, 3)
+    Ksteps = max(args.steps, 1)
+    B, Lt = args.batch, args.text_len
+
+    torch.manual_seed(0)
+    unet = UNet(num_heads=args.heads, compute_dtype=torch.bfloat16).to(dev)
+    unet.train()
+    eng = unet.engine()
+    eng.dropout_enabled = not args.no_dropout
+    ns = NoiseScheduler().to(dev)
+    opt = FusedAdamW(unet, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-4, max_grad_norm=0.7)
+    total_sched = 4 * (W + Ksteps) + 64
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-4, total_steps=total_sched, pct_start=0.1, anneal_strategy="cos")
+    step_fn = TrainStep(unet, ns, opt, sched)
+
+    # synthetic inputs; 4 distinct batches, data seed 1234 + rank
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    nb = 4
+    host_lat = [torch.randn(B, 8, 27, 27, generator=g).clamp_(-3, 3).pin_memory() for _ in range(nb)]
+    host_txt = [torch.randn(B, Lt, 256, generator=g).pin_memory() for _ in range(nb)]
+    dev_lat = [t.to(dev) for t in host_lat]
+    dev_txt = [t.to(dev) for t in host_txt]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step_fn(dev_lat[i % nb], dev_txt[i % nb])
+    barrier()
+
+    # ---- timed region: device-resident inputs, per-launch events on the tensor-core engine for the roofline ----
+    lib = L.load()
+    lib.psg_launch_count.restype = __import__("ctypes").c_longlong
+    lib.psg_launch_count(1)
+    clocks = ClockSampler(local)
+    clocks.start()
+    G.PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(Ksteps):
+        loss = step_fn(dev_lat[i % nb], dev_txt[i % nb])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof, G.PROFILE = G.PROFILE, None
+    clk = clocks.stop()
+    launches = int(lib.psg_launch_count(0))
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    ms_per_step = ms / Ksteps
+    value = world * B * Ksteps / (ms / 1e3)
+    final_loss = loss.item()
+
+    # roofline of the dominant kernel (umma_gemm_kernel: every conv / linear fwd, dgrad, wgrad)
+    um = [(s.elapsed_time(e), fl) for (s, e, fl, engn) in prof if engn == "umma"]
+    um_ms = sum(x[0] for x in um)
+    um_flops = sum(x[1] for x in um)
+    peaks = _peaks()
+    achieved = um_flops / (um_ms / 1e3) / 1e12 if um_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "umma_gemm_kernel (tcgen05 implicit-GEMM conv + GEMM, fwd/dgrad/wgrad)",
+                "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                "peak_source": f"{peaks['src']} sustained cuBLAS bf16", "traffic": None,
+                "launches_per_step": len(um) / Ksteps, "share_of_step": um_ms / ms if ms > 0 else None,
+                "algorithmic_tflop_per_step": um_flops / Ksteps / 1e12,
+                "step_model_tflops": B * TRAIN_GFLOP_PER_SAMPLE / 1e3 / (ms_per_step / 1e3)}
+
+    # ---- end-to-end through the public trainer API: pinned host inputs in, loss out, every step ----
+    trainer = DiffusionTrainer.__new__(DiffusionTrainer)       # public step API without the dataset / VAE set-up
+    trainer.unet, trainer.device, trainer._step = unet, dev, step_fn
+    for i in range(2):
+        trainer.train_step(host_lat[i % nb], host_txt[i % nb]).item()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(Ksteps):
+        trainer.train_step(host_lat[i % nb], host_txt[i % nb]).item()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * Ksteps / (t.item() / 1e3)
+    e2e = {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": host_lat[0].numel() * 4 + host_txt[0].numel() * 4,
+           "d2h_bytes_per_step": 4, "wall_s": time.perf_counter() - t0}
+
+    # ---- DDPM denoise steps/s per GPU (second half of the BASELINE metric), eval mode, prompt-sharded ----
+    denoise = None
+    try:
+        from pokemon_sprite_generator_b200.sampler import _GraphedUNet
+        unet.eval()
+        Bd = args.denoise_batch
+        x = torch.randn(Bd, 8, 27, 27, device=dev)
+        te = torch.randn(Bd, Lt, 256, device=dev)
+        gun = _GraphedUNet(unet, x, torch.zeros(Bd, dtype=torch.long, device=dev), te)
+        tt = 999
+        for _ in range(2):
+            x = ns.ddpm_step(x, gun(x, tt), tt, torch.randn_like(x))
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.denoise_steps):
+            tt = 999 - i
+            x = ns.ddpm_step(x, gun(x, tt), tt, torch.randn_like(x))
+        e1.record()
+        torch.cuda.synchronize()
+        dms = e0.elapsed_time(e1) / args.denoise_steps
+        denoise = {"steps_per_s_per_gpu": 1e3 / dms, "ms_per_step": dms, "batch": Bd, "cuda_graph": True,
+                   "tflops": Bd * FWD_GFLOP_PER_SAMPLE / 1e3 / (dms / 1e3)}
+        unet.train()
+    except Exception as ex:  # the headline metric must still print
+        denoise = {"error": repr(ex)[:200]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_steps(3, 1)
+        cpu_baseline = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                        "sample": "3 steps of batch 2 after 1 warm-up (oracle port of the reference train step, fp32)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": Ksteps, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": f"U-Net diffusion train step (config 2), 27x27x8 latents, batch {B}/GPU, bf16 compute + fp32 master, "
+                                       f"1000-step cosine schedule, {Lt}x256 text emb, AdamW + clip 0.7 + OneCycleLR, dropout "
+                                       f"{'off' if args.no_dropout else 'on'}, heads {args.heads}",
+                           "global_batch": world * B, "parallelism": f"dp{world}",
+                           "l2": "per-step working set (>10 GB activations + 2.6 GB weights) far exceeds the 126 MB L2"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "denoise": denoise, "loss": final_loss}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

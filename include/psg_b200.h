@@ -1,0 +1,148 @@
+/* psg_b200 -- C ABI of the B200-native latent-diffusion hot path (libpsg_b200.so, sm_100a only).
+ *
+ * The reference (GabrieleConte/pokemon-sprite-generator) is pure Python: it has no FFI of its own.  Its "operator API"
+ * for this path is the nn.Module / trainer contract; the Python host side
+ * (pokemon_sprite_generator_b200/{unet,scheduler,trainer}.py) mirrors that contract and binds THIS header through
+ * ctypes.  Each entry point below names the reference op(s) it replaces (paths relative to the reference root).
+ *
+ * Conventions: every function returns 0 (PSG_OK) or a negative error code and never allocates, synchronises or
+ * touches global state beyond a kernel-launch counter; `stream` is a cudaStream_t; all pointers are device pointers
+ * unless noted; the caller owns all memory (workspaces included); psg_last_error() describes the last failure of the
+ * calling thread.  dtype: 0 = fp32, 1 = bf16 (activation storage type).  Token-major tensors are [rows, C] with row
+ * pitch `ld` in elements (channel slices of wider buffers are valid operands).
+ */
+#ifndef PSG_B200_H
+#define PSG_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSG_OK 0
+#define PSG_ERR_INVALID -1
+#define PSG_ERR_CUDA -2
+#define PSG_ERR_UNSUPPORTED -3
+
+#define PSG_DTYPE_F32 0
+#define PSG_DTYPE_BF16 1
+#define PSG_ACT_NONE 0
+#define PSG_ACT_GELU 1
+#define PSG_ACT_SILU 2
+#define PSG_OP_KMAJOR 0
+#define PSG_OP_MNMAJOR 1
+#define PSG_OP_IM2COL 2
+#define PSG_OP_IM2COL_T 3
+#define PSG_OP_DGRAD 4
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+int psg_version(void);
+const char* psg_last_error(void);
+int psg_check_device(void);                 /* 0 iff the current device is compute capability 10.x */
+long long psg_launch_count(int reset);      /* kernels launched by this library so far */
+int psg_umma_timeout_flag(void);            /* test hook: 1 if a tcgen05 pipeline wait timed out (synchronises) */
+
+/* ---- fused epilogue + GEMM / implicit-GEMM convolution (csrc/gemm_epilogue.cuh, csrc/gemm_desc.h) --------------
+ * Replaces aten::conv2d / aten::addmm forward and backward behind nn.Conv2d, nn.Linear and the MHA projections:
+ *   src/models/unet.py:29-33 (time MLP), :80,90,96 (ResBlock convs + 1x1 skip), :83,86 (time/text proj),
+ *   :160-187 (attention in/out projections, text_proj, FFN), :325-399 (init/down/up/final convs).
+ *   v = acc + bias[n] + rowbias[(m / rows_per_group) * ld_rowbias + n]; aux_out = v; v = act(v);
+ *   v *= act'(aux_in); v = dropout(v); out = alpha * v + residual (+ out if accumulate)                              */
+typedef struct PsgEpilogue {
+  void* out; long long ldc; int out_dtype; int act_dtype;
+  const float* bias; const float* rowbias; int rows_per_group; long long ld_rowbias;
+  int act; float alpha;
+  const void* residual; long long ldr;
+  void* aux_out; const void* aux_in; long long ld_aux; int aux_act;
+  int accumulate;
+  unsigned long long drop_seed; unsigned int drop_threshold; float drop_scale;
+} PsgEpilogue;
+
+typedef struct PsgOperand {
+  const void* ptr; int mode; long long ld;
+  int n, h, w, c;          /* NHWC geometry of the gathered tensor (conv modes) */
+  int p, q;                /* spatial size of the row index space */
+  int stride, pad, ksize, flip;
+} PsgOperand;
+
+typedef struct PsgGemmDesc {
+  PsgOperand a, b;         /* C[m,n] = epilogue(sum_k A(m,k) * B(n,k)) */
+  long long M, N, K;
+  int in_dtype;
+  int split_k;             /* >1: fp32 partial planes [split][M][ldc] */
+  PsgEpilogue epi;
+} PsgGemmDesc;
+
+/* tcgen05 / TMEM / TMA engine (bf16 operands, fp32 accumulate).  block_n: 0 = auto, or 64/128/160/256. */
+int psg_umma_gemm(const PsgGemmDesc* desc, int block_n, void* stream);
+/* CUDA-core fp32-accumulate engine (fp32 parity mode, edge shapes, general-stride dgrad gather). */
+int psg_simt_gemm(const PsgGemmDesc* desc, void* stream);
+
+/* ---- diffusion element-wise kernels ------------------------------------------------------------------------------
+ * psg_q_sample          NoiseScheduler.add_noise + clamp  src/training/improved_diffusion_trainer.py:50-65,363
+ * psg_smooth_l1_fwd_bwd nn.SmoothL1Loss(beta) + backward  src/training/improved_diffusion_trainer.py:300,388,396
+ * psg_ddpm_step         mode 0: ddpm_sample update        src/training/improved_diffusion_trainer.py:543-567
+ *                       mode 1: sample_previous_timestep  src/training/final_trainer.py:52-71                        */
+int psg_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
+                 float* out, int batch, int n_per, int num_t, int do_clamp, float clamp_lo, float clamp_hi, int* nonfinite,
+                 void* stream);
+int psg_smooth_l1_fwd_bwd(const float* pred, const float* target, float* dpred, float* loss, void* workspace, long long n,
+                          float beta, float grad_scale, void* stream);
+int psg_ddpm_step(const float* x, const float* eps, const float* z, float* out, long long n, int mode, const float* tab0,
+                  const float* tab1, const float* tab2, const float* tab3, int t, int num_t, void* stream);
+
+/* ---- GroupNorm (+SiLU)  nn.GroupNorm + F.silu, src/models/unet.py:79,89,115,127,156-157,214,231,397-398 ---------- */
+int psg_groupnorm_slices(int B, int HW);
+int psg_groupnorm_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
+                      float* stats, float* workspace, int B, int HW, int C, int G, float eps, int act, int dtype, void* stream);
+int psg_groupnorm_bwd(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,
+                      const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta, float* workspace,
+                      int B, int HW, int C, int G, int act, int dtype, int accumulate_dx, int accumulate_params, void* stream);
+
+/* ---- attention core  nn.MultiheadAttention(batch_first) softmax(QK^T/sqrt(d))V, src/models/unet.py:160-173,217,235 */
+int psg_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                 long long ldo, float* lse, int B, int H, int Lq, int Lk, int hd, float scale, int dtype,
+                 unsigned long long drop_seed, float drop_p, void* stream);
+int psg_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,
+                 long long ldo, const void* dout, long long lddo, const float* lse, float* dsum, void* dq, long long lddq,
+                 void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Lq, int Lk, int hd, float scale,
+                 int dtype, unsigned long long drop_seed, float drop_p, void* stream);
+
+/* ---- layout, resize, reductions, conditioning inputs, weight packing ---------------------------------------------
+ * upsample: nn.Upsample(bilinear, align_corners=False) unet.py:365,375,385; timestep embedding unet.py:47-50;
+ * mean pool: AdaptiveAvgPool1d(1) unet.py:322,445; copy_strided: torch.cat unet.py:482-503; colsum: bias gradients. */
+int psg_nchw_to_tokens(const float* src, void* dst, long long ld, int B, int C, int HW, int dtype, void* stream);
+int psg_tokens_to_nchw(const void* src, long long ld, float* dst, int B, int C, int HW, int dtype, void* stream);
+int psg_copy_strided(const void* src, long long lds, void* dst, long long ldd, long long rows, int C, int accumulate,
+                     int dtype, void* stream);
+int psg_colsum_slices(int groups, int rows_per_group);
+int psg_colsum(const void* x, long long ld, int groups, int rows_per_group, int C, float* out_groups, long long ld_groups,
+               int acc_groups, float* out_total, int acc_total, float scale, float* workspace, int dtype, void* stream);
+int psg_upsample_bilinear_fwd(const void* x, long long ldx, void* y, long long ldy, int B, int C, int IH, int IW, int OH,
+                              int OW, int dtype, void* stream);
+int psg_upsample_bilinear_bwd(const void* dy, long long lddy, void* dx, long long lddx, int B, int C, int IH, int IW, int OH,
+                              int OW, int accumulate, int dtype, void* stream);
+int psg_dilate2(const void* dy, long long lddy, void* out, long long ldo, int B, int C, int P, int Q, int H, int W, int dtype,
+                void* stream);
+int psg_dropout_scale(const void* x, long long ldx, void* out, long long ldo, long long rows, int C, float alpha,
+                      unsigned long long seed, float drop_p, int dtype, void* stream);
+int psg_timestep_embedding(const long long* t, const float* coeff, float* out, int B, int half, void* stream);
+int psg_mean_pool(const float* x, float* out, int B, int L, int D, void* stream);
+int psg_pack_conv_weight(const float* w_oihw, void* wp, void* wd, int Cout, int Cin, int kk, int dtype, void* stream);
+int psg_pack_linear_weight(const float* w, void* wk, void* wt, int N, int K, int dtype, void* stream);
+int psg_wgrad_finalize(const float* partial, int splits, long long split_stride, float* grad_oihw, int Cout, int Cin, int kk,
+                       int accumulate, void* stream);
+int psg_sum_partials(const float* partial, int splits, long long split_stride, float* out, long long n, int accumulate,
+                     void* stream);
+
+/* ---- optimiser  (478 x grad.norm().item() + clip_grad_norm_ + AdamW(eps=1e-6).step(),
+ *                  src/training/improved_diffusion_trainer.py:277-283,399-413) ------------------------------------- */
+int psg_sumsq(const float* x, long long n, float* out_sumsq, int accumulate, void* workspace, void* stream);
+int psg_clip_coef(const float* sumsq, float max_norm, float* state /* [3]: norm, coef, finite */, void* stream);
+int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, long long step, const float* state, void* stream);
+int psg_scale_inplace(float* x, long long n, const float* state, float extra, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSG_B200_H */

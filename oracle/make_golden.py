@@ -71,7 +71,7 @@ def scheduler_golden(ref):
     print("wrote scheduler_tables.npz", {k: v.shape for k, v in out.items() if k.startswith(("ddpm", "post"))})
 
 
-def _run_case(ref, unet, heads, batch, text_len, with_grad, seed=1234):
+def _run_case(ref, unet, heads, batch, text_len, with_grad, seed=1234, fp64=False):
     latent, text, t, noise = inputs.make_inputs(batch, text_len, seed)
     ns = ref.NoiseScheduler()
     noisy = ns.add_noise(latent, noise, t)
@@ -94,6 +94,22 @@ def _run_case(ref, unet, heads, batch, text_len, with_grad, seed=1234):
         with torch.no_grad():
             pred = unet(noisy, t, text)
     case["output"] = pred.detach().clone()
+    if with_grad and fp64:
+        # The reference's fp32 CPU conv weight-gradients lose precision on the deep levels (up to 3e-3 on a
+        # parameter's grad norm vs exact); an fp64 run of the SAME reference module pins the exact values.
+        unet.double()
+        unet.zero_grad(set_to_none=True)
+        pred64 = unet(noisy.double(), t, text.double())
+        loss64 = torch.nn.SmoothL1Loss(beta=0.1)(pred64, noise.double())
+        loss64.backward()
+        g64 = {k: p.grad for k, p in unet.named_parameters()}
+        case["loss_fp64"] = loss64.item()
+        case["output_fp64"] = pred64.detach().float().clone()
+        case["grad_norms_fp64"] = {k: g64[k].norm().item() for k in g64}
+        case["grad_total_norm_fp64"] = float(torch.sqrt(sum(g.pow(2).sum() for g in g64.values())))
+        case["grad_samples_fp64"] = {k: g64[k].flatten()[:: max(1, g64[k].numel() // 64)][:64].float().clone() for k in inputs.GRAD_KEYS}
+        unet.float()
+        unet.zero_grad(set_to_none=True)
     print(f"case heads={heads} B={batch} L={text_len} grad={with_grad}: |y|max={pred.abs().max():.4f} std={pred.std():.4f}"
           + (f" loss={case['loss']:.6f} gnorm={case['grad_total_norm']:.4f}" if with_grad else ""))
     return case
@@ -109,12 +125,12 @@ def unet_golden(ref):
         "num_params": sum(p.numel() for p in unet.parameters()),
         "cases": {},
     }
-    golden["cases"]["init_h8_b2_l32"] = _run_case(ref, unet, 8, 2, 32, True)
+    golden["cases"]["init_h8_b2_l32"] = _run_case(ref, unet, 8, 2, 32, True, fp64=True)
     golden["cases"]["init_h4_b2_l32"] = _run_case(ref, unet, 4, 2, 32, False)
     golden["cases"]["init_h8_b1_l7"] = _run_case(ref, unet, 8, 1, 7, False)
     golden["cases"]["init_h8_b3_l77"] = _run_case(ref, unet, 8, 3, 77, False)
     unet.load_state_dict(inputs.amplify_state_dict(sd))
-    golden["cases"]["amp_h8_b2_l32"] = _run_case(ref, unet, 8, 2, 32, True)
+    golden["cases"]["amp_h8_b2_l32"] = _run_case(ref, unet, 8, 2, 32, True, fp64=True)
     golden["cases"]["amp_h4_b2_l32"] = _run_case(ref, unet, 4, 2, 32, True)
     torch.save(golden, OUT / "unet_cases.pt")
     print("wrote unet_cases.pt")

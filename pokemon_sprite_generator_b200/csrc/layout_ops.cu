@@ -1,0 +1,487 @@
+// Small bandwidth-bound kernels around the GEMM engines: layout conversion, strided copies/adds, column sums
+// (bias / conditioning gradients), bilinear resize, sinusoidal timestep embedding, token mean-pool, weight
+// packing and wgrad finalisation.  All token-major ("NHWC") tensors are addressed as (ptr, pitch) so channel
+// slices of concat buffers work everywhere.
+//
+// Reference ops replaced:
+//   nn.Upsample(bilinear, align_corners=False)      src/models/unet.py:365,375,385
+//   torch.cat([x, skip], 1)                         src/models/unet.py:482,489,496,503
+//   TimestepEmbedding sin/cos                       src/models/unet.py:47-50
+//   AdaptiveAvgPool1d(1) over tokens                src/models/unet.py:322,445
+//   bias / broadcast-add gradients of conv+linear   autograd of unet.py:116-124
+#include "psg_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int blocks_for(long long items, int cap_mult = 8) {
+  long long g = (items + kThreads - 1) / kThreads;
+  long long cap = (long long)psg_num_sms() * cap_mult;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---- NCHW fp32 <-> token-major T -------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_tokens_kernel(const float* __restrict__ src, T* __restrict__ dst, long long ld, int B, int C, int HW) {
+  const long long n = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const int c = (int)(i % C);
+    const long long t = i / C;  // b*HW + pix
+    const int pix = (int)(t % HW);
+    const int b = (int)(t / HW);
+    psg_st(dst + t * ld + c, src[((long long)b * C + c) * HW + pix]);
+  }
+}
+template <typename T>
+__global__ void tokens_to_nchw_kernel(const T* __restrict__ src, long long ld, float* __restrict__ dst, int B, int C, int HW) {
+  const long long n = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const int pix = (int)(i % HW);
+    const long long t = i / HW;  // b*C + c
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    dst[i] = psg_ld(src + ((long long)b * HW + pix) * ld + c);
+  }
+}
+
+// ---- strided copy / add of [rows, C] channel slices (8-wide vectors) -------------------------------------
+template <typename T>
+__global__ void copy_strided_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldd, long long rows,
+                                    int C, int accumulate) {
+  const int vpr = C / 8;
+  const long long n = rows * vpr;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const long long r = i / vpr;
+    const int v = (int)(i - r * vpr);
+    Vec8<T> a;
+    a.load(src + r * lds + v * 8);
+    if (accumulate) {
+      Vec8<T> b;
+      b.load(dst + r * ldd + v * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a.v[j] += b.v[j];
+    }
+    a.store(dst + r * ldd + v * 8);
+  }
+}
+
+// ---- column sums: x[groups*rows_per_group, C] -> partial[groups][S][C] ------------------------------------
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, long long ld, int rows_per_group, int C, int S,
+                                      float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [rows*vpp][8] per-thread sums, folded in a fixed order (deterministic)
+  const int g = blockIdx.y, sl = blockIdx.x;
+  const int vpp = C / 8;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, row = threadIdx.x / vpp;
+  const int per = (rows_per_group + S - 1) / S;
+  const int r0 = sl * per, r1 = min(rows_per_group, r0 + per);
+  if (row < rows) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const T* base = x + ((long long)g * rows_per_group) * ld + v * 8;
+    for (int r = r0 + row; r < r1; r += rows) {
+      Vec8<T> t;
+      t.load(base + (long long)r * ld);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += t.v[j];
+    }
+    float* mine = sm + (size_t)threadIdx.x * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[j] = acc[j];
+  }
+  __syncthreads();
+  float* out = partial + ((long long)(g * S + sl)) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += sm[(size_t)(r * vpp + (c >> 3)) * 8 + (c & 7)];
+    out[c] = s;
+  }
+}
+// out_groups[g][c] (=|+=) sum_s partial[g][s][c] ; out_total[c] (=|+=) sum_g ...
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int groups, int S, int C, float* __restrict__ out_groups,
+                                    long long ld_groups, int acc_groups, float* __restrict__ out_total, int acc_total, float scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tot = 0.f;
+  for (int g = 0; g < groups; ++g) {
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += partial[((long long)(g * S + k)) * C + c];
+    s *= scale;
+    if (out_groups) {
+      float* o = out_groups + (long long)g * ld_groups + c;
+      *o = acc_groups ? *o + s : s;
+    }
+    tot += s;
+  }
+  if (out_total) out_total[c] = acc_total ? out_total[c] + tot : tot;
+}
+
+// ---- bilinear resize (align_corners=False), token-major ----------------------------------------------------
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float s = scale * ((float)dst + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+template <typename T>
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, long long ldy, int B, int C, int IH,
+                                    int IW, int OH, int OW) {
+  const int vpp = C / 8;
+  const long long n = (long long)B * OH * OW * vpp;
+  const float sh = (float)IH / (float)OH, sw = (float)IW / (float)OW;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const int v = (int)(i % vpp);
+    long long t = i / vpp;
+    const int ox = (int)(t % OW); t /= OW;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    int y0, y1, x0, x1; float ly, lx;
+    src_index(oy, sh, IH, y0, y1, ly);
+    src_index(ox, sw, IW, x0, x1, lx);
+    const T* base = x + ((long long)b * IH * IW) * ldx + v * 8;
+    Vec8<T> a, bq, c, d, o;
+    a.load(base + ((long long)y0 * IW + x0) * ldx);
+    bq.load(base + ((long long)y0 * IW + x1) * ldx);
+    c.load(base + ((long long)y1 * IW + x0) * ldx);
+    d.load(base + ((long long)y1 * IW + x1) * ldx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = hy * (hx * a.v[j] + lx * bq.v[j]) + ly * (hx * c.v[j] + lx * d.v[j]);
+    o.store(y + (((long long)b * OH + oy) * OW + ox) * ldy + v * 8);
+  }
+}
+// gather form of the backward: dx[iy,ix] = sum over output pixels that read (iy,ix) of weight * dy
+template <typename T>
+__global__ void upsample_bwd_kernel(const T* __restrict__ dy, long long lddy, T* __restrict__ dx, long long lddx, int B, int C, int IH,
+                                    int IW, int OH, int OW, int accumulate) {
+  const int vpp = C / 8;
+  const long long n = (long long)B * IH * IW * vpp;
+  const float sh = (float)IH / (float)OH, sw = (float)IW / (float)OW;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const int v = (int)(i % vpp);
+    long long t = i / vpp;
+    const int ix = (int)(t % IW); t /= IW;
+    const int iy = (int)(t % IH);
+    const int b = (int)(t / IH);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // candidate output rows/cols: those whose source window [i0, i1] can contain iy / ix
+    const int oy_lo = max(0, (int)floorf(((float)iy - 1.f + 0.5f) / sh - 0.5f) - 1);
+    const int oy_hi = min(OH - 1, (int)ceilf(((float)iy + 1.f + 0.5f) / sh - 0.5f) + 1);
+    const int ox_lo = max(0, (int)floorf(((float)ix - 1.f + 0.5f) / sw - 0.5f) - 1);
+    const int ox_hi = min(OW - 1, (int)ceilf(((float)ix + 1.f + 0.5f) / sw - 0.5f) + 1);
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1; float ly;
+      src_index(oy, sh, IH, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        int x0, x1; float lx;
+        src_index(ox, sw, IW, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx == 0.f) continue;
+        Vec8<T> g;
+        g.load(dy + (((long long)b * OH + oy) * OW + ox) * lddy + v * 8);
+        const float w = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, g.v[j], acc[j]);
+      }
+    }
+    T* o = dx + (((long long)b * IH + iy) * IW + ix) * lddx + v * 8;
+    Vec8<T> r;
+    if (accumulate) {
+      r.load(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] += acc[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] = acc[j];
+    }
+    r.store(o);
+  }
+}
+
+// zero-insertion: out[b, 2p, 2q, :] = dy[b, p, q, :], zeros elsewhere (stride-2 dgrad as a stride-1 conv)
+template <typename T>
+__global__ void dilate2_kernel(const T* __restrict__ dy, long long lddy, T* __restrict__ out, long long ldo, int B, int C, int P, int Q,
+                               int H, int W) {
+  const int vpp = C / 8;
+  const long long n = (long long)B * H * W * vpp;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const int v = (int)(i % vpp);
+    long long t = i / vpp;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    Vec8<T> r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = 0.f;
+    if (!(h & 1) && !(w & 1) && (h >> 1) < P && (w >> 1) < Q) r.load(dy + (((long long)b * P + (h >> 1)) * Q + (w >> 1)) * lddy + v * 8);
+    r.store(out + (((long long)b * H + h) * W + w) * ldo + v * 8);
+  }
+}
+
+// out = alpha * dropout(x; seed, threshold) -- backward of an epilogue dropout applied before a GEMM operand
+template <typename T>
+__global__ void dropout_scale_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo, long long rows, int C,
+                                     float alpha, unsigned long long seed, unsigned int threshold, float keep_scale) {
+  const int vpr = C / 8;
+  const long long n = rows * vpr;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const long long r = i / vpr;
+    const int v = (int)(i - r * vpr);
+    Vec8<T> a;
+    a.load(x + r * ldx + v * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool kp = threshold == 0 || psg_hash32(seed, (uint64_t)(r * C + v * 8 + j)) >= threshold;
+      a.v[j] = kp ? a.v[j] * keep_scale * alpha : 0.f;
+    }
+    a.store(out + r * ldo + v * 8);
+  }
+}
+
+// ---- conditioning inputs -----------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, const float* __restrict__ coeff, float* __restrict__ out,
+                                          int B, int half) {
+  const int n = B * half;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const int b = i / half, k = i - b * half;
+    const float e = __fmul_rn((float)t[b], coeff[k]);
+    out[(long long)b * 2 * half + k] = sinf(e);
+    out[(long long)b * 2 * half + half + k] = cosf(e);
+  }
+}
+__global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int L, int D) {
+  const int n = B * D;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const int b = i / D, d = i - b * D;
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += x[((long long)b * L + l) * D + d];
+    out[i] = s / (float)L;
+  }
+}
+
+// ---- weight packing ----------------------------------------------------------------------------------------
+// OIHW fp32 -> wp[Cout][kk][Cin] (fprop B operand) and wd[Cin][kk][Cout] (dgrad B operand), dtype T
+template <typename T>
+__global__ void pack_conv_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wd, int Cout, int Cin, int kk) {
+  const long long n = (long long)Cout * Cin * kk;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const int tap = (int)(i % kk);
+    const long long t = i / kk;
+    const int ci = (int)(t % Cin);
+    const int co = (int)(t / Cin);
+    const float v = w[i];
+    if (wp) psg_st(wp + ((long long)co * kk + tap) * Cin + ci, v);
+    if (wd) psg_st(wd + ((long long)ci * kk + tap) * Cout + co, v);
+  }
+}
+// [N][K] fp32 -> wk[N][K] (cast) and wt[K][N] (transpose + cast)
+template <typename T>
+__global__ void pack_linear_kernel(const float* __restrict__ w, T* __restrict__ wk, T* __restrict__ wt, int N, int K) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    float v = 0.f;
+    if (n < N && k < K) {
+      v = w[(long long)n * K + k];
+      if (wk) psg_st(wk + (long long)n * K + k, v);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  if (wt) {
+    for (int r = ty; r < 32; r += 8) {
+      const int k = k0 + r, n = n0 + tx;
+      if (n < N && k < K) psg_st(wt + (long long)k * N + n, tile[tx][r]);
+    }
+  }
+}
+// grad_oihw[co][ci][tap] (=|+=) sum_s partial[s][co][tap*Cin + ci]
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int S, long long split_stride, float* __restrict__ grad,
+                                      int Cout, int Cin, int kk, int accumulate) {
+  const long long n = (long long)Cout * Cin * kk;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    // iterate in packed order so partial reads are coalesced
+    const int ci = (int)(i % Cin);
+    const long long t = i / Cin;
+    const int tap = (int)(t % kk);
+    const int co = (int)(t / kk);
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += partial[(long long)k * split_stride + i];
+    float* o = grad + ((long long)co * Cin + ci) * kk + tap;
+    *o = accumulate ? *o + s : s;
+  }
+}
+// out (=|+=) sum_s partial[s][i]   (linear wgrad split-K reduction, same layout)
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int S, long long split_stride, float* __restrict__ out,
+                                    long long n, int accumulate) {
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += partial[(long long)k * split_stride + i];
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                                           \
+  if ((dtype) == PSG_DTYPE_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+  else if ((dtype) == PSG_DTYPE_F32) { using T = float; __VA_ARGS__; }     \
+  else { psg_set_error("bad dtype %d", (int)(dtype)); return PSG_ERR_INVALID; }
+
+extern "C" {
+
+int psg_nchw_to_tokens(const float* src, void* dst, long long ld, int B, int C, int HW, int dtype, void* stream) {
+  PSG_CHECK_ARG(B >= 0 && C > 0 && HW > 0, "psg_nchw_to_tokens: bad sizes");
+  if (B == 0) return PSG_OK;
+  PSG_CHECK_ARG(src && dst, "psg_nchw_to_tokens: null pointer");
+  DISPATCH_T(dtype, (nchw_to_tokens_kernel<T><<<blocks_for((long long)B * C * HW), kThreads, 0, (cudaStream_t)stream>>>(src, (T*)dst, ld, B, C, HW)));
+  PSG_CHECK_LAUNCH("psg_nchw_to_tokens");
+  return PSG_OK;
+}
+
+int psg_tokens_to_nchw(const void* src, long long ld, float* dst, int B, int C, int HW, int dtype, void* stream) {
+  PSG_CHECK_ARG(B >= 0 && C > 0 && HW > 0, "psg_tokens_to_nchw: bad sizes");
+  if (B == 0) return PSG_OK;
+  PSG_CHECK_ARG(src && dst, "psg_tokens_to_nchw: null pointer");
+  DISPATCH_T(dtype, (tokens_to_nchw_kernel<T><<<blocks_for((long long)B * C * HW), kThreads, 0, (cudaStream_t)stream>>>((const T*)src, ld, dst, B, C, HW)));
+  PSG_CHECK_LAUNCH("psg_tokens_to_nchw");
+  return PSG_OK;
+}
+
+int psg_copy_strided(const void* src, long long lds, void* dst, long long ldd, long long rows, int C, int accumulate, int dtype,
+                     void* stream) {
+  PSG_CHECK_ARG(rows >= 0 && C > 0 && C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "psg_copy_strided: C and pitches must be multiples of 8");
+  if (rows == 0) return PSG_OK;
+  PSG_CHECK_ARG(src && dst, "psg_copy_strided: null pointer");
+  DISPATCH_T(dtype, (copy_strided_kernel<T><<<blocks_for(rows * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const T*)src, lds, (T*)dst, ldd, rows, C, accumulate)));
+  PSG_CHECK_LAUNCH("psg_copy_strided");
+  return PSG_OK;
+}
+
+// slices used by psg_colsum for a given group size; workspace floats >= groups * S * C
+int psg_colsum_slices(int groups, int rows_per_group) {
+  int S = (2 * psg_num_sms() + groups - 1) / (groups > 0 ? groups : 1);
+  int max_s = rows_per_group / 16 > 0 ? rows_per_group / 16 : 1;
+  if (S > max_s) S = max_s;
+  return S < 1 ? 1 : S;
+}
+
+// Per-group and total column sums (times `scale`) of x[groups*rows_per_group, C]: out_groups[g][c], out_total[c]
+// (either may be null).
+int psg_colsum(const void* x, long long ld, int groups, int rows_per_group, int C, float* out_groups, long long ld_groups,
+               int acc_groups, float* out_total, int acc_total, float scale, float* workspace, int dtype, void* stream) {
+  PSG_CHECK_ARG(x && workspace, "psg_colsum: null pointer");
+  PSG_CHECK_ARG(groups > 0 && rows_per_group > 0 && C > 0 && C % 8 == 0 && C / 8 <= 512 && ld % 8 == 0, "psg_colsum: bad sizes (C=%d)", C);
+  PSG_CHECK_ARG(groups <= 65535, "psg_colsum: too many groups");
+  const int S = psg_colsum_slices(groups, rows_per_group);
+  const int vpp = C / 8;
+  int rows = 512 / vpp;
+  if (rows < 1) rows = 1;
+  int threads = ((rows * vpp + 31) / 32) * 32;
+  dim3 grid(S, groups);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, threads, (size_t)threads * 8 * sizeof(float), st>>>((const T*)x, ld, rows_per_group, C, S, workspace)));
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, groups, S, C, out_groups, ld_groups, acc_groups, out_total, acc_total, scale);
+  PSG_CHECK_LAUNCH("psg_colsum");
+  g_psg_launch_count += 1;  // two kernels
+  return PSG_OK;
+}
+
+int psg_upsample_bilinear_fwd(const void* x, long long ldx, void* y, long long ldy, int B, int C, int IH, int IW, int OH, int OW,
+                              int dtype, void* stream) {
+  PSG_CHECK_ARG(x && y && B > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "psg_upsample_bilinear_fwd: bad args");
+  DISPATCH_T(dtype, (upsample_fwd_kernel<T><<<blocks_for((long long)B * OH * OW * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)y, ldy, B, C, IH, IW, OH, OW)));
+  PSG_CHECK_LAUNCH("psg_upsample_bilinear_fwd");
+  return PSG_OK;
+}
+
+int psg_upsample_bilinear_bwd(const void* dy, long long lddy, void* dx, long long lddx, int B, int C, int IH, int IW, int OH, int OW,
+                              int accumulate, int dtype, void* stream) {
+  PSG_CHECK_ARG(dy && dx && B > 0 && C % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, "psg_upsample_bilinear_bwd: bad args");
+  DISPATCH_T(dtype, (upsample_bwd_kernel<T><<<blocks_for((long long)B * IH * IW * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const T*)dy, lddy, (T*)dx, lddx, B, C, IH, IW, OH, OW, accumulate)));
+  PSG_CHECK_LAUNCH("psg_upsample_bilinear_bwd");
+  return PSG_OK;
+}
+
+int psg_dilate2(const void* dy, long long lddy, void* out, long long ldo, int B, int C, int P, int Q, int H, int W, int dtype,
+                void* stream) {
+  PSG_CHECK_ARG(dy && out && B > 0 && C % 8 == 0 && lddy % 8 == 0 && ldo % 8 == 0, "psg_dilate2: bad args");
+  DISPATCH_T(dtype, (dilate2_kernel<T><<<blocks_for((long long)B * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const T*)dy, lddy, (T*)out, ldo, B, C, P, Q, H, W)));
+  PSG_CHECK_LAUNCH("psg_dilate2");
+  return PSG_OK;
+}
+
+// out[r, c] = alpha * keep(r*C + c) * x[r, c] / (1 - p): same mask as the GEMM epilogue dropout with N == C.
+int psg_dropout_scale(const void* x, long long ldx, void* out, long long ldo, long long rows, int C, float alpha,
+                      unsigned long long seed, float drop_p, int dtype, void* stream) {
+  PSG_CHECK_ARG(x && out && rows > 0 && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "psg_dropout_scale: bad args");
+  const unsigned int thr = drop_p > 0.f ? (unsigned int)fmin((double)drop_p * 4294967296.0, 4294967295.0) : 0u;
+  const float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  DISPATCH_T(dtype, (dropout_scale_kernel<T><<<blocks_for(rows * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out, ldo, rows, C, alpha, seed, thr, ks)));
+  PSG_CHECK_LAUNCH("psg_dropout_scale");
+  return PSG_OK;
+}
+
+int psg_timestep_embedding(const long long* t, const float* coeff, float* out, int B, int half, void* stream) {
+  PSG_CHECK_ARG(B >= 0 && half > 0, "psg_timestep_embedding: bad sizes");
+  if (B == 0) return PSG_OK;
+  PSG_CHECK_ARG(t && coeff && out, "psg_timestep_embedding: null pointer");
+  timestep_embedding_kernel<<<blocks_for((long long)B * half), kThreads, 0, (cudaStream_t)stream>>>(t, coeff, out, B, half);
+  PSG_CHECK_LAUNCH("psg_timestep_embedding");
+  return PSG_OK;
+}
+
+int psg_mean_pool(const float* x, float* out, int B, int L, int D, void* stream) {
+  PSG_CHECK_ARG(B >= 0 && L > 0 && D > 0, "psg_mean_pool: bad sizes");
+  if (B == 0) return PSG_OK;
+  PSG_CHECK_ARG(x && out, "psg_mean_pool: null pointer");
+  mean_pool_kernel<<<blocks_for((long long)B * D), kThreads, 0, (cudaStream_t)stream>>>(x, out, B, L, D);
+  PSG_CHECK_LAUNCH("psg_mean_pool");
+  return PSG_OK;
+}
+
+int psg_pack_conv_weight(const float* w, void* wp, void* wd, int Cout, int Cin, int kk, int dtype, void* stream) {
+  PSG_CHECK_ARG(w && (wp || wd) && Cout > 0 && Cin > 0 && kk > 0, "psg_pack_conv_weight: bad args");
+  DISPATCH_T(dtype, (pack_conv_kernel<T><<<blocks_for((long long)Cout * Cin * kk), kThreads, 0, (cudaStream_t)stream>>>(w, (T*)wp, (T*)wd, Cout, Cin, kk)));
+  PSG_CHECK_LAUNCH("psg_pack_conv_weight");
+  return PSG_OK;
+}
+
+int psg_pack_linear_weight(const float* w, void* wk, void* wt, int N, int K, int dtype, void* stream) {
+  PSG_CHECK_ARG(w && (wk || wt) && N > 0 && K > 0, "psg_pack_linear_weight: bad args");
+  dim3 grid((K + 31) / 32, (N + 31) / 32);
+  PSG_CHECK_ARG(grid.y <= 65535, "psg_pack_linear_weight: N too large");
+  DISPATCH_T(dtype, (pack_linear_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(w, (T*)wk, (T*)wt, N, K)));
+  PSG_CHECK_LAUNCH("psg_pack_linear_weight");
+  return PSG_OK;
+}
+
+int psg_wgrad_finalize(const float* partial, int splits, long long split_stride, float* grad_oihw, int Cout, int Cin, int kk,
+                       int accumulate, void* stream) {
+  PSG_CHECK_ARG(partial && grad_oihw && splits >= 1, "psg_wgrad_finalize: bad args");
+  wgrad_finalize_kernel<<<blocks_for((long long)Cout * Cin * kk), kThreads, 0, (cudaStream_t)stream>>>(partial, splits, split_stride, grad_oihw, Cout, Cin, kk, accumulate);
+  PSG_CHECK_LAUNCH("psg_wgrad_finalize");
+  return PSG_OK;
+}
+
+int psg_sum_partials(const float* partial, int splits, long long split_stride, float* out, long long n, int accumulate, void* stream) {
+  PSG_CHECK_ARG(partial && out && splits >= 1 && n > 0, "psg_sum_partials: bad args");
+  sum_partials_kernel<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(partial, splits, split_stride, out, n, accumulate);
+  PSG_CHECK_LAUNCH("psg_sum_partials");
+  return PSG_OK;
+}
+
+}  // extern "C"

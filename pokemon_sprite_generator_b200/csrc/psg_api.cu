@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 static thread_local char g_last_error[512] = "";
+long long g_psg_launch_count = 0;
 
 void psg_set_error(const char* fmt, ...) {
   va_list ap;
@@ -16,6 +17,13 @@ extern "C" {
 int psg_version() { return 100; }  // 0.1.0
 
 const char* psg_last_error() { return g_last_error; }
+
+// Number of kernels this library has launched since load (or since the last reset); bench.py reports it.
+long long psg_launch_count(int reset) {
+  long long v = g_psg_launch_count;
+  if (reset) g_psg_launch_count = 0;
+  return v;
+}
 
 // Returns 0 when the current device is compute capability 10.x (the only target of this library).
 int psg_check_device() {

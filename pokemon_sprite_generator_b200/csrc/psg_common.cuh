@@ -16,6 +16,7 @@
 #define PSG_ERR_UNSUPPORTED -3
 
 void psg_set_error(const char* fmt, ...);
+extern long long g_psg_launch_count;  // kernels launched by this library (host-side counter, see psg_launch_count)
 
 #define PSG_CHECK_ARG(cond, ...)                     \
   do {                                               \
@@ -32,6 +33,7 @@ void psg_set_error(const char* fmt, ...);
       psg_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));      \
       return PSG_ERR_CUDA;                                                        \
     }                                                                             \
+    ++g_psg_launch_count;                                                         \
   } while (0)
 
 #define PSG_DTYPE_F32 0

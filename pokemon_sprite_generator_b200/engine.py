@@ -1,0 +1,651 @@
+"""Execution engine of the U-Net: an explicit forward / backward schedule of C-ABI kernel launches.
+
+This is the host side of the hot path: it walks the reference's graph (UNet.forward,
+src/models/unet.py:428-509; ResBlock.forward :112-132; CrossAttentionBlock.forward :206-260) and issues one kernel
+per fused op on the current CUDA stream.  Activations are token-major ("NHWC") in the compute dtype; channel
+concatenation is a strided view of a wider buffer, never a copy of both halves.  A reverse-mode tape of closures
+gives the backward pass; parameter gradients land in one flat fp32 buffer laid out like the flat parameter buffer
+(so the gradient all-reduce, the global-norm clip and fused AdamW each are a single pass over contiguous memory).
+
+No op here is computed by PyTorch: torch provides memory (torch.empty), streams and autograd glue only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import gemm as G
+from . import ops as K
+from .unet import LEVELS
+
+NUM_SMS = 148
+ALIGN = 64  # elements; keeps every parameter 256-byte aligned inside the flat buffers
+
+
+class Act:
+    """A token-major activation [M = B*H*W, C] (possibly a channel slice of a wider buffer) plus its gradient."""
+
+    __slots__ = ("t", "B", "H", "W", "grad", "parent", "col", "pre", "pre_act", "drop")
+
+    def __init__(self, t: torch.Tensor, B: int, H: int, W: int, parent: "Act" = None, col: int = 0):
+        self.t, self.B, self.H, self.W = t, B, H, W
+        self.grad: Optional[torch.Tensor] = None
+        self.parent, self.col = parent, col
+        self.pre: Optional[torch.Tensor] = None   # saved pre-activation when this is act(pre) [+dropout]
+        self.pre_act = L.ACT_NONE
+        self.drop = None                          # (seed, p) of an epilogue dropout applied after the activation
+
+    @property
+    def M(self) -> int:
+        return self.t.shape[0]
+
+    @property
+    def C(self) -> int:
+        return self.t.shape[1]
+
+    def slice(self, col: int, width: int) -> "Act":
+        return Act(self.t[:, col:col + width], self.B, self.H, self.W, parent=self, col=col)
+
+    def g(self) -> torch.Tensor:
+        if self.parent is not None:
+            return self.parent.grad[:, self.col:self.col + self.C]
+        return self.grad
+
+    def nhwc(self) -> torch.Tensor:
+        ld = self.t.stride(0)
+        return self.t.as_strided((self.B, self.H, self.W, self.C), (self.H * self.W * ld, self.W * ld, ld, 1))
+
+    @staticmethod
+    def nhwc_of(t: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+        ld = t.stride(0)
+        return t.as_strided((B, H, W, t.shape[1]), (H * W * ld, W * ld, ld, 1))
+
+
+class ConvW:
+    def __init__(self, conv: nn.Conv2d):
+        self.mod = conv
+        self.cout, self.cin, self.k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
+        self.stride, self.pad = conv.stride[0], conv.padding[0]
+        self.wp = self.wd = None
+        # shapes the tcgen05 engine cannot tile (K or N below one 64-wide TMA box) go to the SIMT engine
+        self.edge = (self.cin % 64 != 0) or (self.cout % 32 != 0)
+
+
+class LinW:
+    """A (row-slice of a) Linear weight [N, K] with optional bias; w/b/gw/gb are views of the flat buffers."""
+
+    def __init__(self, weight: nn.Parameter, bias: Optional[nn.Parameter], rows: Optional[tuple] = None):
+        self.weight, self.bias, self.rows = weight, bias, rows
+        self.wk = self.wt = None
+
+    def views(self, store: "ParamStore"):
+        w, gw = self.weight.data, store.grad_of(self.weight)
+        b = self.bias.data if self.bias is not None else None
+        gb = store.grad_of(self.bias) if self.bias is not None else None
+        if self.rows is not None:
+            a, e = self.rows
+            w, gw = w[a:e], gw[a:e]
+            if b is not None:
+                b, gb = b[a:e], gb[a:e]
+        return w, b, gw, gb
+
+
+class NormW:
+    def __init__(self, gn: nn.GroupNorm):
+        self.mod, self.groups, self.eps = gn, gn.num_groups, gn.eps
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient buffers; every nn.Parameter's .data is a view into `flat`."""
+
+    def __init__(self, module: nn.Module):
+        self.module = module
+        self.named = list(module.named_parameters())
+        self.offsets = {}
+        off = 0
+        for name, p in self.named:
+            self.offsets[name] = off
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.total = off
+        self.flat: Optional[torch.Tensor] = None
+        self.grads: Optional[torch.Tensor] = None
+        self._by_id = {}
+        self.generation = 0
+
+    def ensure_flat(self, device) -> bool:
+        """(Re)builds the flat buffer if any parameter was moved/replaced.  Returns True when rebuilt."""
+        ok = self.flat is not None and self.flat.device == device
+        if ok:
+            base = self.flat.data_ptr()
+            for name, p in (self.named[0], self.named[-1], self.named[len(self.named) // 2]):
+                if p.data_ptr() != base + 4 * self.offsets[name] or p.dtype != torch.float32:
+                    ok = False
+                    break
+        if ok:
+            return False
+        flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for name, p in self.named:
+                off, n = self.offsets[name], p.numel()
+                view = flat[off:off + n].view(p.shape)
+                view.copy_(p.data.to(device=device, dtype=torch.float32))
+                p.data = view
+        self.flat = flat
+        self.grads = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self._index_grads()
+        self.generation += 1
+        return True
+
+    def _index_grads(self):
+        self._by_id = {}
+        for name, p in self.named:
+            off, n = self.offsets[name], p.numel()
+            self._by_id[id(p)] = self.grads[off:off + n].view(p.shape)
+
+    def fresh_grads(self):
+        """Detach the current gradient buffer (it may be referenced by p.grad) and start a new one."""
+        self.grads = torch.zeros(self.total, dtype=torch.float32, device=self.flat.device)
+        self._index_grads()
+
+    def grad_of(self, p: nn.Parameter) -> torch.Tensor:
+        return self._by_id[id(p)]
+
+    def grad_views(self) -> List[torch.Tensor]:
+        return [self._by_id[id(p)] for _, p in self.named]
+
+    def version(self) -> int:
+        return sum(p._version for _, p in self.named)
+
+
+class UNetEngine:
+    def __init__(self, unet: nn.Module, compute_dtype: torch.dtype = torch.bfloat16):
+        if compute_dtype not in (torch.bfloat16, torch.float32):
+            raise L.PsgError(f"compute_dtype must be bfloat16 or float32, got {compute_dtype}")
+        L.load()
+        self.unet = unet
+        self.dtype = compute_dtype
+        self.bf16 = compute_dtype == torch.bfloat16
+        self.store = ParamStore(unet)
+        self._packed_version = None
+        self._packed_generation = None
+        self._build_descriptors()
+        self.step_counter = 0
+        self.dropout_enabled = True      # honoured only in train() mode
+        self.seed = 0x5EED
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    # descriptors
+    # ------------------------------------------------------------------------------------------------------------
+    def _build_descriptors(self):
+        u = self.unet
+        self.convs: List[ConvW] = []
+        self.lins: List[LinW] = []
+
+        def conv(m):
+            c = ConvW(m)
+            self.convs.append(c)
+            return c
+
+        def lin(w, b, rows=None):
+            l = LinW(w, b, rows)
+            self.lins.append(l)
+            return l
+
+        def res(rb):
+            d = {"norm1": NormW(rb.norm1), "conv1": conv(rb.conv1), "time": lin(rb.time_proj.weight, rb.time_proj.bias),
+                 "text": lin(rb.text_proj.weight, rb.text_proj.bias), "norm2": NormW(rb.norm2), "conv2": conv(rb.conv2),
+                 "skip": None, "cin": rb.in_channels, "cout": rb.out_channels}
+            if isinstance(rb.skip_conv, nn.Conv2d):
+                sk = rb.skip_conv
+                d["skip"] = lin(sk.weight, sk.bias)      # 1x1 conv == linear over tokens ([Cout, Cin, 1, 1] viewed [Cout, Cin])
+            return d
+
+        def attn(ab):
+            c = ab.channels
+            sa, ca = ab.self_attn, ab.cross_attn
+            return {"c": c, "norm1": NormW(ab.norm1), "norm2": NormW(ab.norm2),
+                    "qkv": lin(sa.in_proj_weight, sa.in_proj_bias), "so": lin(sa.out_proj.weight, sa.out_proj.bias),
+                    "cq": lin(ca.in_proj_weight, ca.in_proj_bias, (0, c)), "ckv": lin(ca.in_proj_weight, ca.in_proj_bias, (c, 3 * c)),
+                    "co": lin(ca.out_proj.weight, ca.out_proj.bias), "tp": lin(ab.text_proj.weight, ab.text_proj.bias),
+                    "f1": lin(ab.ffn[0].weight, ab.ffn[0].bias), "f2": lin(ab.ffn[3].weight, ab.ffn[3].bias),
+                    "p_attn": ab.ATTN_DROPOUT, "p_ffn": ab.FFN_DROPOUT}
+
+        def block(b):
+            return {"res": res(b.res_block), "attn": attn(b.attn_block) if b.has_attention else None}
+
+        te = u.time_embed.time_mlp
+        self.d_time = [lin(te[0].weight, te[0].bias), lin(te[2].weight, te[2].bias), lin(te[4].weight, te[4].bias)]
+        self.d_init = conv(u.init_conv)
+        self.d_enc = [[block(b) for b in getattr(u, f"enc_block{l}")] for l in range(4)]
+        self.d_down = [None] + [conv(getattr(u, f"downsample{l}")) for l in (1, 2, 3)]
+        self.d_mid = block(u.middle_block)
+        self.d_dec = {l: [block(b) for b in getattr(u, f"dec_block{l}")] for l in (3, 2, 1, 0)}
+        self.d_up = {l: conv(getattr(u, f"upsample{l}")[1]) for l in (3, 2, 1)}
+        self.d_final_norm = NormW(u.final_conv[0])
+        self.d_final = conv(u.final_conv[2])
+
+    # ------------------------------------------------------------------------------------------------------------
+    # weights
+    # ------------------------------------------------------------------------------------------------------------
+    def prepare(self, device) -> None:
+        """Flatten parameters if needed and refresh the packed kernel-layout weight copies if they changed."""
+        rebuilt = self.store.ensure_flat(device)
+        ver = self.store.version()
+        if not rebuilt and self._packed_version == ver and self._packed_generation == self.store.generation:
+            return
+        for c in self.convs:
+            w = c.mod.weight.data
+            if c.wp is None or c.wp.device != device:
+                c.wp = torch.empty(c.cout, c.k * c.k * c.cin, dtype=self.dtype, device=device)
+                c.wd = torch.empty(c.cin, c.k * c.k * c.cout, dtype=self.dtype, device=device)
+            K.pack_conv_weight(w, c.wp, c.wd)
+        if self.bf16:
+            done = {}
+            for l in self.lins:
+                key = id(l.weight)
+                if key not in done:
+                    w = l.weight.data
+                    w2 = w.view(w.shape[0], -1)
+                    cached = getattr(l.weight, "_psg_pack", None)
+                    if cached is None or cached[0].device != device:
+                        cached = (torch.empty(w2.shape, dtype=self.dtype, device=device),
+                                  torch.empty(w2.shape[1], w2.shape[0], dtype=self.dtype, device=device))
+                        l.weight._psg_pack = cached
+                    K.pack_linear_weight(w2, cached[0], cached[1])
+                    done[key] = cached
+                wk, wt = done[key]
+                if l.rows is not None:
+                    a, e = l.rows
+                    wk, wt = wk[a:e], wt[:, a:e]
+                l.wk, l.wt = wk, wt
+        self._packed_version = self.store.version()
+        self._packed_generation = self.store.generation
+
+    def mark_params_dirty(self) -> None:
+        """Call after updating the flat parameter buffer outside of torch (fused optimiser): forces a re-pack."""
+        self._packed_version = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    # primitive ops (forward + tape entry)
+    # ------------------------------------------------------------------------------------------------------------
+    def _new(self, M, C_, B, H, W, dtype=None) -> Act:
+        return Act(torch.empty(M, C_, dtype=dtype or self.dtype, device=self.device), B, H, W)
+
+    def _grad_target(self, a: Act):
+        """Returns (tensor, accumulate) for adding a gradient contribution to `a`."""
+        assert a.parent is None, "gradients of slices are produced through their parent buffer"
+        if a.grad is None:
+            a.grad = torch.empty(a.M, a.C, dtype=a.t.dtype, device=a.t.device)
+            return a.grad, False
+        return a.grad, True
+
+    def _engine_for(self, t: torch.Tensor, edge: bool = False) -> str:
+        return "umma" if (t.dtype == torch.bfloat16 and not edge) else "simt"
+
+    @staticmethod
+    def _pick_split(tiles: int, num_kb: int) -> int:
+        if tiles >= NUM_SMS or num_kb < 8:
+            return 1
+        want = min(max(1, (2 * NUM_SMS) // max(tiles, 1)), max(1, num_kb // 4), 32)
+        per = (num_kb + want - 1) // want
+        return (num_kb + per - 1) // per
+
+    def _seed(self, site: int) -> int:
+        return ((self.seed * 0x9E3779B1 + self.step_counter) * 0x85EBCA77 + site * 0xC2B2AE3D) & 0xFFFFFFFFFFFFFFFF
+
+    # ---- convolution -------------------------------------------------------------------------------------------
+    def conv(self, x: Act, cw: ConvW, *, out: Act = None, rowbias: Act = None, residual: Act = None, x_needs_grad=True) -> Act:
+        P = (x.H + 2 * cw.pad - cw.k) // cw.stride + 1
+        Q = (x.W + 2 * cw.pad - cw.k) // cw.stride + 1
+        if out is None:
+            out = self._new(x.B * P * Q, cw.cout, x.B, P, Q)
+        eng = self._engine_for(x.t, cw.edge)
+        bias = cw.mod.bias.data
+        a = G.im2col(x.nhwc(), cw.k, cw.stride, cw.pad)
+        epi = G.Epilogue(out=out.t, bias=bias, rowbias=rowbias.t if rowbias is not None else None, rows_per_group=P * Q,
+                         residual=residual.t if residual is not None else None)
+        G.run_gemm(a, G.kmajor(cw.wp), epi, engine=eng)
+        if self.taping:
+            self.tape.append(lambda: self._conv_bwd(x, cw, out, rowbias, residual, x_needs_grad, eng))
+        return out
+
+    def _conv_bwd(self, x: Act, cw: ConvW, out: Act, rowbias: Act, residual: Act, x_needs_grad: bool, eng: str):
+        dy = out.g()
+        gb = self.store.grad_of(cw.mod.bias)
+        if rowbias is not None:
+            tgt, acc = self._grad_target(rowbias)
+            K.colsum(dy, x.B, tgt, gb, acc_groups=acc)
+        else:
+            K.colsum(dy, 1, None, gb)
+        if residual is not None:
+            tgt, acc = self._grad_target(residual)
+            K.copy_strided(dy, tgt, accumulate=acc)
+        # wgrad: dW[co][tap][ci] = sum_pix dY[pix, co] * im2col(X)[pix, (tap, ci)]
+        gw = self.store.grad_of(cw.mod.weight)
+        kk = cw.k * cw.k
+        ncols = kk * cw.cin
+        if eng == "umma":
+            tiles = ((cw.cout + 127) // 128) * kk * ((cw.cin + 127) // 128)
+            num_kb = (dy.shape[0] + 63) // 64
+            split = self._pick_split(tiles, num_kb)
+        else:
+            split = 1
+        part = K.workspace(self.device, split * cw.cout * ncols, "wgrad").narrow(0, 0, split * cw.cout * ncols).view(split, cw.cout, ncols)
+        G.run_gemm(G.mnmajor(dy), G.im2col_t(x.nhwc(), cw.k, cw.stride, cw.pad), G.Epilogue(out=part[0]), engine=eng, split_k=split,
+                   block_n=128 if eng == "umma" else 0)
+        K.wgrad_finalize(part, split, cw.cout * ncols, gw)
+        if not x_needs_grad:
+            return
+        # dgrad
+        tgt, acc = self._grad_target(x) if x.parent is None else (x.g(), False)
+        res = tgt if acc else None
+        dy4 = Act.nhwc_of(dy, out.B, out.H, out.W)
+        if cw.stride == 1:
+            a = G.im2col(dy4, cw.k, 1, cw.pad, flip=True)
+            self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng)
+        elif eng == "simt":
+            a = G.dgrad_gather(dy4, x.H, x.W, cw.k, cw.stride, cw.pad)
+            self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng)
+        else:
+            # stride-2 dgrad on the tensor-core engine: zero-insert dY to the input grid, then a stride-1 flipped conv
+            dil = torch.empty(x.B * x.H * x.W, cw.cout, dtype=dy.dtype, device=dy.device)
+            K.dilate2(dy, dil, x.B, out.H, out.W, x.H, x.W)
+            a = G.im2col(Act.nhwc_of(dil, x.B, x.H, x.W), cw.k, 1, cw.pad, flip=True)
+            self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng, algo_flops=2.0 * dy.shape[0] * cw.cin * cw.k * cw.k * cw.cout)
+
+    def _dgrad_gemm(self, a, b, tgt, res, x: Act, eng: str, alpha: float = 1.0, algo_flops=None):
+        """tgt (+)= alpha * (A B^T) [* act'(x.pre) * dropmask]  -- gradient w.r.t. the pre-activation when x carries one."""
+        epi = G.Epilogue(out=tgt, residual=res, alpha=alpha)
+        if x.pre is not None:
+            epi.aux_in, epi.aux_act = x.pre, x.pre_act
+            if x.drop is not None:
+                epi.drop_seed, epi.drop_p = x.drop
+        G.run_gemm(a, b, epi, engine=eng, algo_flops=algo_flops)
+
+    # ---- linear ------------------------------------------------------------------------------------------------
+    def linear(self, x: Act, lw: LinW, *, out: Act = None, act=L.ACT_NONE, alpha: float = 1.0, residual: Act = None,
+               into: Act = None, drop: tuple = None, x_needs_grad: bool = True, B=None, H=None, W=None) -> Act:
+        """y = alpha * drop(act(x W^T + b)) + residual.   `into`: accumulate onto an existing activation in place
+        (y = into + x W^T + b), whose gradient then simply passes through."""
+        w, b, gw, gb = lw.views(self.store)
+        w2 = w.view(w.shape[0], -1)
+        N = w2.shape[0]
+        fp32 = x.t.dtype == torch.float32
+        if into is not None:
+            out = into
+        elif out is None:
+            out = self._new(x.M, N, B or x.B, H or x.H, W or x.W, dtype=x.t.dtype)
+        eng = self._engine_for(x.t, edge=(N % 32 != 0))
+        bmat = w2 if fp32 else lw.wk
+        epi = G.Epilogue(out=out.t, bias=b, act=act, alpha=alpha)
+        res_t = into.t if into is not None else (residual.t if residual is not None else None)
+        epi.residual = res_t
+        if act != L.ACT_NONE and self.taping:
+            out.pre = torch.empty(x.M, N, dtype=x.t.dtype, device=self.device)
+            out.pre_act = act
+            epi.aux_out = out.pre
+        if drop is not None:
+            epi.drop_seed, epi.drop_p = drop
+            if act != L.ACT_NONE:
+                out.drop = drop
+        G.run_gemm(G.kmajor(x.t), G.kmajor(bmat), epi, engine=eng)
+        if self.taping:
+            self.tape.append(lambda: self._linear_bwd(x, lw, out, act, alpha, residual, into, drop, x_needs_grad, eng))
+        return out
+
+    def _linear_bwd(self, x: Act, lw: LinW, out: Act, act, alpha, residual: Act, into: Act, drop, x_needs_grad, eng):
+        w, b, gw, gb = lw.views(self.store)
+        w2, gw2 = w.view(w.shape[0], -1), gw.view(gw.shape[0], -1)
+        N, Kd = w2.shape
+        fp32 = x.t.dtype == torch.float32
+        dy = out.g()            # for act != NONE this already is the gradient w.r.t. the pre-activation
+        if residual is not None:
+            tgt, acc = self._grad_target(residual)
+            K.copy_strided(dy, tgt, accumulate=acc)
+        scale = alpha
+        if act == L.ACT_NONE and drop is not None:
+            dpre = torch.empty(dy.shape, dtype=dy.dtype, device=dy.device)
+            K.dropout_scale(dy, dpre, alpha, drop[0], drop[1])
+            dy, scale = dpre, 1.0
+        if gb is not None:
+            K.colsum(dy, 1, None, gb, scale=scale)
+        # wgrad: dW[n][k] = scale * sum_m dY[m, n] X[m, k]
+        if eng == "umma":
+            tiles = ((N + 127) // 128) * ((Kd + 127) // 128)
+            split = self._pick_split(tiles, (dy.shape[0] + 63) // 64)
+        else:
+            split = 1
+        if split == 1:
+            G.run_gemm(G.mnmajor(dy), G.mnmajor(x.t), G.Epilogue(out=gw2, alpha=scale), engine=eng, block_n=128 if eng == "umma" else 0)
+        else:
+            part = K.workspace(self.device, split * N * Kd, "wgrad").narrow(0, 0, split * N * Kd).view(split, N, Kd)
+            G.run_gemm(G.mnmajor(dy), G.mnmajor(x.t), G.Epilogue(out=part[0], alpha=scale), engine=eng, split_k=split, block_n=128)
+            K.sum_partials(part, split, N * Kd, gw2)
+        if not x_needs_grad:
+            return
+        tgt, acc = self._grad_target(x) if x.parent is None else (x.g(), False)
+        bop = G.mnmajor(w2) if fp32 else G.kmajor(lw.wt)
+        self._dgrad_gemm(G.kmajor(dy), bop, tgt, tgt if acc else None, x, eng, alpha=scale)
+
+    # ---- GroupNorm ---------------------------------------------------------------------------------------------
+    def groupnorm(self, x: Act, nw: NormW, silu: bool, out: Act = None) -> Act:
+        if out is None:
+            out = self._new(x.M, x.C, x.B, x.H, x.W)
+        stats = torch.empty(x.B, nw.groups, 2, dtype=torch.float32, device=self.device)
+        gamma, beta = nw.mod.weight.data, nw.mod.bias.data
+        K.groupnorm_fwd(x.t, out.t, gamma, beta, stats, x.B, nw.groups, nw.eps, silu)
+        if self.taping:
+            def bwd():
+                tgt, acc = self._grad_target(x)
+                K.groupnorm_bwd(out.g(), x.t, tgt, gamma, beta, stats, self.store.grad_of(nw.mod.weight),
+                                self.store.grad_of(nw.mod.bias), x.B, nw.groups, silu, acc)
+            self.tape.append(bwd)
+        return out
+
+    # ---- attention core ----------------------------------------------------------------------------------------
+    def attention(self, q: Act, k: Act, v: Act, lq: int, lk: int, heads: int, drop_p: float, site: int) -> Act:
+        """q/k/v are channel slices of projection outputs; gradients are written into the parents' grad buffers."""
+        c = q.C
+        hd = c // heads
+        o = self._new(q.M, c, q.B, q.H, q.W)
+        lse = torch.empty(q.B, heads, lq, dtype=torch.float32, device=self.device) if self.taping else None
+        p = drop_p if (self.training and self.dropout_enabled) else 0.0
+        seed = self._seed(site)
+        K.attn_fwd(q.t, k.t, v.t, o.t, lse, q.B, heads, lq, lk, hd, seed, p)
+        if self.taping:
+            def bwd():
+                for a in (q, k, v):
+                    par = a.parent if a.parent is not None else a
+                    if par.grad is None:
+                        par.grad = torch.empty(par.M, par.C, dtype=par.t.dtype, device=self.device)
+                K.attn_bwd(q.t, k.t, v.t, o.t, o.g(), lse, q.g(), k.g(), v.g(), q.B, heads, lq, lk, hd, seed, p)
+            self.tape.append(bwd)
+        return o
+
+    # ---- resize / concat ---------------------------------------------------------------------------------------
+    def upsample(self, x: Act, size: int) -> Act:
+        out = self._new(x.B * size * size, x.C, x.B, size, size)
+        K.upsample_fwd(x.t, out.t, x.B, x.H, x.W, size, size)
+        if self.taping:
+            def bwd():
+                tgt, acc = self._grad_target(x)
+                K.upsample_bwd(out.g(), tgt, x.B, x.H, x.W, size, size, acc)
+            self.tape.append(bwd)
+        return out
+
+    def copy_into(self, src: Act, dst_slice: Act) -> None:
+        K.copy_strided(src.t, dst_slice.t)
+        if self.taping:
+            def bwd():
+                tgt, acc = self._grad_target(src)
+                K.copy_strided(dst_slice.g(), tgt, accumulate=acc)
+            self.tape.append(bwd)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # blocks
+    # ------------------------------------------------------------------------------------------------------------
+    def _cond(self, d, temb: Act, pooled: Act) -> Act:
+        """time_proj(time_emb) + text_proj(text_pooled): the [B, Cout] broadcast bias of conv1 (unet.py:119-124)."""
+        cond = self.linear(temb, d["time"])
+        self.linear(pooled, d["text"], into=cond, x_needs_grad=False)
+        return cond
+
+    def _res_block(self, d, x: Act, temb: Act, pooled: Act, out: Act = None) -> Act:
+        a1 = self.groupnorm(x, d["norm1"], silu=True)
+        cond = self._cond(d, temb, pooled)
+        h1 = self.conv(a1, d["conv1"], rowbias=cond)
+        a2 = self.groupnorm(h1, d["norm2"], silu=True)
+        if d["skip"] is None:
+            return self.conv(a2, d["conv2"], residual=x, out=out)
+        y = self.conv(a2, d["conv2"], out=out)
+        self.linear(x, d["skip"], into=y)
+        return y
+
+    def _attn_block(self, d, x: Act, text_tok: Act, lt: int, site: int) -> Act:
+        c, B, HW = d["c"], x.B, x.H * x.W
+        train_drop = self.training and self.dropout_enabled
+        n1 = self.groupnorm(x, d["norm1"], silu=False)
+        qkv = self.linear(n1, d["qkv"])
+        o = self.attention(qkv.slice(0, c), qkv.slice(c, c), qkv.slice(2 * c, c), HW, HW, self.unet.num_heads, d["p_attn"], site)
+        x1 = self.linear(o, d["so"], alpha=0.7, residual=x)
+        n2 = self.groupnorm(x1, d["norm2"], silu=False)
+        q = self.linear(n2, d["cq"])
+        tp = self.linear(text_tok, d["tp"], x_needs_grad=False, B=B, H=lt, W=1)
+        kv = self.linear(tp, d["ckv"])
+        o2 = self.attention(q, kv.slice(0, c), kv.slice(c, c), HW, lt, self.unet.num_heads, d["p_attn"], site + 1)
+        x2 = self.linear(o2, d["co"], alpha=0.8, residual=x1)
+        pf = d["p_ffn"]
+        f = self.linear(x2, d["f1"], act=L.ACT_GELU, drop=(self._seed(site + 2), pf) if train_drop else None)
+        return self.linear(f, d["f2"], alpha=0.6, residual=x2, drop=(self._seed(site + 3), pf) if train_drop else None)
+
+    def _block(self, d, x: Act, temb, pooled, text_tok, lt, site, out: Act = None) -> Act:
+        if d["attn"] is None:
+            return self._res_block(d["res"], x, temb, pooled, out=out)
+        h = self._res_block(d["res"], x, temb, pooled)
+        y = self._attn_block(d["attn"], h, text_tok, lt, site)
+        if out is not None:   # attention output must land in a concat buffer: one strided copy
+            self.copy_into(y, out)
+            return out
+        return y
+
+    # ------------------------------------------------------------------------------------------------------------
+    # whole network
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, noisy_latent: torch.Tensor, timesteps: torch.Tensor, text_emb: torch.Tensor, need_grad: bool):
+        dev = noisy_latent.device
+        self.device = dev
+        self.prepare(dev)
+        self.training = self.unet.training
+        self.taping = need_grad
+        self.tape: List[Callable] = []
+        self.step_counter += 1
+        B, lat_c, Hh, Ww = noisy_latent.shape
+        if (Hh, Ww) != (LEVELS[0][1], LEVELS[0][1]):
+            raise L.PsgError(f"UNet expects {LEVELS[0][1]}x{LEVELS[0][1]} latents, got {Hh}x{Ww}")
+        if text_emb.dim() != 3 or text_emb.shape[0] != B or text_emb.shape[2] != self.unet.text_dim:
+            raise L.PsgError(f"text_emb must be [B, L, {self.unet.text_dim}], got {tuple(text_emb.shape)}")
+        lt = text_emb.shape[1]
+        x_in = noisy_latent.detach().contiguous().float()
+        text = text_emb.detach().contiguous().float()
+        t = timesteps.detach().to(device=dev, dtype=torch.int64).contiguous()
+
+        # ---- conditioning path (fp32, M = B rows) ----
+        u = self.unet
+        coeff = u.time_embed.emb_coeff
+        if coeff.device != dev:
+            coeff = coeff.to(dev)
+        sin = Act(torch.empty(B, 2 * coeff.shape[0], dtype=torch.float32, device=dev), B, 1, 1)
+        K.timestep_embedding(t, coeff.float().contiguous(), sin.t)
+        h = self.linear(sin, self.d_time[0], act=L.ACT_SILU, x_needs_grad=False)
+        h = self.linear(h, self.d_time[1], act=L.ACT_SILU)
+        temb = self.linear(h, self.d_time[2])
+        pooled = Act(torch.empty(B, text.shape[2], dtype=torch.float32, device=dev), B, 1, 1)
+        K.mean_pool(text, pooled.t)
+        text_tok = Act(torch.empty(B * lt, text.shape[2], dtype=self.dtype, device=dev), B, lt, 1)
+        K.nchw_to_tokens(text.view(B * lt, text.shape[2], 1, 1), text_tok.t)
+
+        # ---- encoder ----
+        s0 = LEVELS[0][1]
+        lat = Act(torch.empty(B * s0 * s0, lat_c, dtype=self.dtype, device=dev), B, s0, s0)
+        K.nchw_to_tokens(x_in, lat.t)
+        x = self.conv(lat, self.d_init, x_needs_grad=False)
+        skips = []
+        site = 0
+        for lvl, (ch, size, _) in enumerate(LEVELS):
+            if lvl > 0:
+                x = self.conv(x, self.d_down[lvl])
+            for blk in self.d_enc[lvl]:
+                x = self._block(blk, x, temb, pooled, text_tok, lt, site)
+                site += 4
+            skips.append(x)
+        x = self._block(self.d_mid, x, temb, pooled, text_tok, lt, site)
+        site += 4
+        # ---- decoder: cat([x, skip]) is one [M, 2C] buffer filled by two strided copies ----
+        for lvl in (3, 2, 1, 0):
+            ch, size, _ = LEVELS[lvl]
+            skip = skips.pop()
+            M = B * size * size
+            for i, blk in enumerate(self.d_dec[lvl]):
+                cat = self._new(M, 2 * ch, B, size, size)
+                self.copy_into(x, cat.slice(0, ch))
+                self.copy_into(skip, cat.slice(ch, ch))
+                x = self._block(blk, cat, temb, pooled, text_tok, lt, site)
+                site += 4
+            if lvl > 0:
+                x = self.upsample(x, LEVELS[lvl - 1][1])
+                x = self.conv(x, self.d_up[lvl])
+        a = self.groupnorm(x, self.d_final_norm, silu=True)
+        y = self.conv(a, self.d_final)
+        out = torch.empty(B, lat_c, s0, s0, dtype=torch.float32, device=dev)
+        K.tokens_to_nchw(y.t, out)
+        tape, self.tape = self.tape, []
+        self.taping = False
+        return out, (tape, y)
+
+    def backward(self, ctx, dout: torch.Tensor) -> None:
+        """Runs the tape; parameter gradients are written (not accumulated) into self.store.grads."""
+        tape, y = ctx
+        self.taping = False
+        y.grad = torch.empty(y.M, y.C, dtype=y.t.dtype, device=y.t.device)
+        K.nchw_to_tokens(dout.detach().contiguous().float(), y.grad)
+        while tape:
+            tape.pop()()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # autograd glue
+    # ------------------------------------------------------------------------------------------------------------
+    def autograd_forward(self, noisy_latent, timesteps, text_emb):
+        params = [p for _, p in self.store.named]
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if not need:
+            out, _ = self.forward(noisy_latent, timesteps, text_emb, need_grad=False)
+            return out
+        return _UNetFunction.apply(self, noisy_latent, timesteps, text_emb, *params)
+
+
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng: UNetEngine, x, t, text, *params):
+        out, run = eng.forward(x, t, text, need_grad=True)
+        ctx.eng, ctx.run = eng, run
+        ctx.params = params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng: UNetEngine = ctx.eng
+        store = eng.store
+        # If a previous backward's views are still installed as p.grad, writing into the same buffer would corrupt
+        # autograd's accumulation: start a fresh gradient buffer in that (rare: zero_grad(set_to_none=False)) case.
+        p0 = ctx.params[0]
+        if p0.grad is not None and p0.grad.data_ptr() == store.grad_of(p0).data_ptr():
+            store.fresh_grads()
+        eng.backward(ctx.run, dout)
+        ctx.run = None
+        grads = [store.grad_of(p) if p.requires_grad else None for p in ctx.params]
+        return (None, None, None, None, *grads)

@@ -134,8 +134,15 @@ class Epilogue:
             e.drop_scale = 1.0
 
 
-def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", split_k: int = 1, block_n: int = 0) -> None:
-    """C[M,N] = epilogue(sum_k A(m,k) B(n,k)).  engine: 'umma' (tcgen05, bf16), 'simt', or 'auto'."""
+# When set to a list, every launch appends (start_event, end_event, algorithmic_flops, engine): bench.py uses it to time
+# the tensor-core kernel on its own stream inside the timed region (roofline numerator and denominator).
+PROFILE = None
+
+
+def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", split_k: int = 1, block_n: int = 0,
+             algo_flops: Optional[float] = None) -> None:
+    """C[M,N] = epilogue(sum_k A(m,k) B(n,k)).  engine: 'umma' (tcgen05, bf16), 'simt', or 'auto'.
+    algo_flops: algorithmic FLOPs of this launch when they differ from 2*M*N*K (zero-inserted stride-2 dgrad)."""
     assert a.k == b.k, f"K mismatch {a.k} vs {b.k}"
     assert a.t.dtype == b.t.dtype, "operand dtypes differ"
     d = L.PsgGemmDesc()
@@ -148,9 +155,16 @@ def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", spl
     if engine == "auto":
         engine = "umma" if a.t.dtype == torch.bfloat16 else "simt"
     lib = L.load()
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     if engine == "umma":
         L.check(lib.psg_umma_gemm(C.byref(d), C.c_int(block_n), L.stream_ptr()), "psg_umma_gemm")
     elif engine == "simt":
         L.check(lib.psg_simt_gemm(C.byref(d), L.stream_ptr()), "psg_simt_gemm")
     else:
         raise ValueError(engine)
+    if prof is not None:
+        ev1.record()
+        prof.append((ev0, ev1, float(algo_flops) if algo_flops is not None else 2.0 * a.rows * b.rows * a.k, engine))

@@ -1,0 +1,180 @@
+"""Thin tensor-level wrappers over the C ABI (one function per exported kernel family).
+
+Every tensor argument is a CUDA tensor; token-major activations are 2-D views [rows, C] with unit column
+stride and arbitrary row pitch (channel slices of concat buffers are fine).  Nothing here computes on the
+host and nothing falls back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_ws_cache = {}
+
+
+def workspace(device, floats: int, tag: str = "ws") -> torch.Tensor:
+    """Grow-only fp32 scratch buffer per (device, tag); stream-ordered reuse."""
+    key = (device, tag)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < floats:
+        ws = torch.zeros(max(floats, 4096), dtype=torch.float32, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    return t.stride(0)
+
+
+# ---- layout -------------------------------------------------------------------------------------------------
+def nchw_to_tokens(src: torch.Tensor, dst: torch.Tensor) -> None:
+    b, c, h, w = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    L.call("psg_nchw_to_tokens", L.ptr(src), L.ptr(dst), C.c_longlong(_ld(dst)), C.c_int(b), C.c_int(c), C.c_int(h * w),
+           C.c_int(L.dt(dst)), L.stream_ptr())
+
+
+def tokens_to_nchw(src: torch.Tensor, dst: torch.Tensor) -> None:
+    b, c, h, w = dst.shape
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    L.call("psg_tokens_to_nchw", L.ptr(src), C.c_longlong(_ld(src)), L.ptr(dst), C.c_int(b), C.c_int(c), C.c_int(h * w),
+           C.c_int(L.dt(src)), L.stream_ptr())
+
+
+def copy_strided(src: torch.Tensor, dst: torch.Tensor, accumulate: bool = False) -> None:
+    assert src.shape == dst.shape and src.dtype == dst.dtype
+    L.call("psg_copy_strided", L.ptr(src), C.c_longlong(_ld(src)), L.ptr(dst), C.c_longlong(_ld(dst)), C.c_longlong(src.shape[0]),
+           C.c_int(src.shape[1]), C.c_int(int(accumulate)), C.c_int(L.dt(src)), L.stream_ptr())
+
+
+def colsum(x: torch.Tensor, groups: int, out_groups: torch.Tensor | None, out_total: torch.Tensor | None,
+           acc_groups: bool = False, acc_total: bool = False, scale: float = 1.0) -> None:
+    rows, c = x.shape
+    assert rows % groups == 0
+    rpg = rows // groups
+    s = L.load().psg_colsum_slices(C.c_int(groups), C.c_int(rpg))
+    ws = workspace(x.device, groups * s * c, "colsum")
+    L.call("psg_colsum", L.ptr(x), C.c_longlong(_ld(x)), C.c_int(groups), C.c_int(rpg), C.c_int(c), L.ptr(out_groups),
+           C.c_longlong(out_groups.stride(0) if out_groups is not None else 0), C.c_int(int(acc_groups)), L.ptr(out_total),
+           C.c_int(int(acc_total)), C.c_float(scale), L.ptr(ws), C.c_int(L.dt(x)), L.stream_ptr())
+
+
+def upsample_fwd(x: torch.Tensor, y: torch.Tensor, b: int, ih: int, iw: int, oh: int, ow: int) -> None:
+    L.call("psg_upsample_bilinear_fwd", L.ptr(x), C.c_longlong(_ld(x)), L.ptr(y), C.c_longlong(_ld(y)), C.c_int(b),
+           C.c_int(x.shape[1]), C.c_int(ih), C.c_int(iw), C.c_int(oh), C.c_int(ow), C.c_int(L.dt(x)), L.stream_ptr())
+
+
+def upsample_bwd(dy: torch.Tensor, dx: torch.Tensor, b: int, ih: int, iw: int, oh: int, ow: int, accumulate: bool) -> None:
+    L.call("psg_upsample_bilinear_bwd", L.ptr(dy), C.c_longlong(_ld(dy)), L.ptr(dx), C.c_longlong(_ld(dx)), C.c_int(b),
+           C.c_int(dx.shape[1]), C.c_int(ih), C.c_int(iw), C.c_int(oh), C.c_int(ow), C.c_int(int(accumulate)), C.c_int(L.dt(dx)),
+           L.stream_ptr())
+
+
+def dilate2(dy: torch.Tensor, out: torch.Tensor, b: int, p: int, q: int, h: int, w: int) -> None:
+    L.call("psg_dilate2", L.ptr(dy), C.c_longlong(_ld(dy)), L.ptr(out), C.c_longlong(_ld(out)), C.c_int(b), C.c_int(dy.shape[1]),
+           C.c_int(p), C.c_int(q), C.c_int(h), C.c_int(w), C.c_int(L.dt(dy)), L.stream_ptr())
+
+
+def dropout_scale(x: torch.Tensor, out: torch.Tensor, alpha: float, seed: int, drop_p: float) -> None:
+    L.call("psg_dropout_scale", L.ptr(x), C.c_longlong(_ld(x)), L.ptr(out), C.c_longlong(_ld(out)), C.c_longlong(x.shape[0]),
+           C.c_int(x.shape[1]), C.c_float(alpha), C.c_ulonglong(seed), C.c_float(drop_p), C.c_int(L.dt(x)), L.stream_ptr())
+
+
+def timestep_embedding(t: torch.Tensor, coeff: torch.Tensor, out: torch.Tensor) -> None:
+    assert t.dtype == torch.int64 and coeff.dtype == torch.float32 and out.is_contiguous()
+    L.call("psg_timestep_embedding", L.ptr(t), L.ptr(coeff), L.ptr(out), C.c_int(t.shape[0]), C.c_int(coeff.shape[0]), L.stream_ptr())
+
+
+def mean_pool(x: torch.Tensor, out: torch.Tensor) -> None:
+    b, l, d = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    L.call("psg_mean_pool", L.ptr(x), L.ptr(out), C.c_int(b), C.c_int(l), C.c_int(d), L.stream_ptr())
+
+
+# ---- weights ------------------------------------------------------------------------------------------------
+def pack_conv_weight(w: torch.Tensor, wp: torch.Tensor | None, wd: torch.Tensor | None) -> None:
+    cout, cin, kh, kw = w.shape
+    ref = wp if wp is not None else wd
+    L.call("psg_pack_conv_weight", L.ptr(w), L.ptr(wp), L.ptr(wd), C.c_int(cout), C.c_int(cin), C.c_int(kh * kw), C.c_int(L.dt(ref)),
+           L.stream_ptr())
+
+
+def pack_linear_weight(w: torch.Tensor, wk: torch.Tensor | None, wt: torch.Tensor | None) -> None:
+    n, k = w.shape
+    ref = wk if wk is not None else wt
+    L.call("psg_pack_linear_weight", L.ptr(w), L.ptr(wk), L.ptr(wt), C.c_int(n), C.c_int(k), C.c_int(L.dt(ref)), L.stream_ptr())
+
+
+def wgrad_finalize(partial: torch.Tensor, splits: int, split_stride: int, grad: torch.Tensor, accumulate: bool = False) -> None:
+    cout, cin, kh, kw = grad.shape
+    L.call("psg_wgrad_finalize", L.ptr(partial), C.c_int(splits), C.c_longlong(split_stride), L.ptr(grad), C.c_int(cout), C.c_int(cin),
+           C.c_int(kh * kw), C.c_int(int(accumulate)), L.stream_ptr())
+
+
+def sum_partials(partial: torch.Tensor, splits: int, split_stride: int, out: torch.Tensor, accumulate: bool = False) -> None:
+    assert out.is_contiguous()
+    L.call("psg_sum_partials", L.ptr(partial), C.c_int(splits), C.c_longlong(split_stride), L.ptr(out), C.c_longlong(out.numel()),
+           C.c_int(int(accumulate)), L.stream_ptr())
+
+
+# ---- GroupNorm ----------------------------------------------------------------------------------------------
+def groupnorm_fwd(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, stats: torch.Tensor, b: int,
+                  groups: int, eps: float, silu: bool) -> None:
+    rows, c = x.shape
+    hw = rows // b
+    s = L.load().psg_groupnorm_slices(C.c_int(b), C.c_int(hw))
+    ws = workspace(x.device, b * s * groups * 2, "gn")
+    L.call("psg_groupnorm_fwd", L.ptr(x), C.c_longlong(_ld(x)), L.ptr(y), C.c_longlong(_ld(y)), L.ptr(gamma), L.ptr(beta), L.ptr(stats),
+           L.ptr(ws), C.c_int(b), C.c_int(hw), C.c_int(c), C.c_int(groups), C.c_float(eps), C.c_int(int(silu)), C.c_int(L.dt(x)),
+           L.stream_ptr())
+
+
+def groupnorm_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, stats: torch.Tensor,
+                  dgamma: torch.Tensor, dbeta: torch.Tensor, b: int, groups: int, silu: bool, accumulate_dx: bool) -> None:
+    rows, c = x.shape
+    hw = rows // b
+    s = L.load().psg_groupnorm_slices(C.c_int(b), C.c_int(hw))
+    ws = workspace(x.device, b * s * c * 2, "gn")
+    L.call("psg_groupnorm_bwd", L.ptr(dy), C.c_longlong(_ld(dy)), L.ptr(x), C.c_longlong(_ld(x)), L.ptr(dx), C.c_longlong(_ld(dx)),
+           L.ptr(gamma), L.ptr(beta), L.ptr(stats), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), C.c_int(b), C.c_int(hw), C.c_int(c),
+           C.c_int(groups), C.c_int(int(silu)), C.c_int(L.dt(x)), C.c_int(int(accumulate_dx)), C.c_int(0), L.stream_ptr())
+
+
+# ---- attention ----------------------------------------------------------------------------------------------
+def attn_fwd(q, k, v, o, lse, b: int, heads: int, lq: int, lk: int, hd: int, drop_seed: int = 0, drop_p: float = 0.0) -> None:
+    L.call("psg_attn_fwd", L.ptr(q), C.c_longlong(_ld(q)), L.ptr(k), C.c_longlong(_ld(k)), L.ptr(v), C.c_longlong(_ld(v)), L.ptr(o),
+           C.c_longlong(_ld(o)), L.ptr(lse), C.c_int(b), C.c_int(heads), C.c_int(lq), C.c_int(lk), C.c_int(hd),
+           C.c_float(1.0 / (hd ** 0.5)), C.c_int(L.dt(q)), C.c_ulonglong(drop_seed), C.c_float(drop_p), L.stream_ptr())
+
+
+def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, b: int, heads: int, lq: int, lk: int, hd: int, drop_seed: int = 0,
+             drop_p: float = 0.0) -> None:
+    dsum = workspace(q.device, b * heads * lq, "attn_dsum")
+    L.call("psg_attn_bwd", L.ptr(q), C.c_longlong(_ld(q)), L.ptr(k), C.c_longlong(_ld(k)), L.ptr(v), C.c_longlong(_ld(v)), L.ptr(o),
+           C.c_longlong(_ld(o)), L.ptr(do), C.c_longlong(_ld(do)), L.ptr(lse), L.ptr(dsum), L.ptr(dq), C.c_longlong(_ld(dq)), L.ptr(dk),
+           C.c_longlong(_ld(dk)), L.ptr(dv), C.c_longlong(_ld(dv)), C.c_int(b), C.c_int(heads), C.c_int(lq), C.c_int(lk), C.c_int(hd),
+           C.c_float(1.0 / (hd ** 0.5)), C.c_int(L.dt(q)), C.c_ulonglong(drop_seed), C.c_float(drop_p), L.stream_ptr())
+
+
+# ---- optimiser ----------------------------------------------------------------------------------------------
+def sumsq(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    ws = workspace(x.device, 1024 + 8, "sumsq")
+    L.call("psg_sumsq", L.ptr(x), C.c_longlong(x.numel()), L.ptr(out), C.c_int(int(accumulate)), L.ptr(ws), L.stream_ptr())
+
+
+def clip_coef(sumsq_t: torch.Tensor, max_norm: float, state: torch.Tensor) -> None:
+    L.call("psg_clip_coef", L.ptr(sumsq_t), C.c_float(max_norm), L.ptr(state), L.stream_ptr())
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step: int, state: torch.Tensor | None) -> None:
+    L.call("psg_adamw_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), C.c_longlong(p.numel()), C.c_float(lr), C.c_float(beta1),
+           C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), L.ptr(state), L.stream_ptr())
+
+
+def scale_inplace(x: torch.Tensor, state: torch.Tensor | None, extra: float = 1.0) -> None:
+    L.call("psg_scale_inplace", L.ptr(x), C.c_longlong(x.numel()), L.ptr(state), C.c_float(extra), L.stream_ptr())

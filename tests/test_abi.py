@@ -1,0 +1,52 @@
+"""CPU checks of the C-ABI boundary: the library loads without a GPU/driver and exports every symbol the public
+header declares; the ctypes structure mirrors have the C layout; compute calls fail loudly without CUDA."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pokemon_sprite_generator_b200 import _lib, build
+    if not _lib.lib_file().exists():
+        build.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    text = (ROOT / "include" / "psg_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(psg_[a-z0-9_]+)\s*\(", text)))
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/psg_b200.h but not exported: {missing}"
+    assert lib.psg_version() >= 100
+
+
+def test_ctypes_struct_layout_matches_c():
+    from pokemon_sprite_generator_b200 import _lib as L
+    # sizes implied by the C declarations on LP64 (natural alignment)
+    assert C.sizeof(L.PsgOperand) == 64
+    assert C.sizeof(L.PsgEpilogue) == 128
+    assert C.sizeof(L.PsgGemmDesc) == 64 * 2 + 24 + 8 + 128
+    assert L.PsgEpilogue.alpha.offset == 60 and L.PsgEpilogue.drop_seed.offset == 112
+
+
+def test_compute_paths_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pokemon_sprite_generator_b200._lib import PsgError
+    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
+    from pokemon_sprite_generator_b200.unet import UNet, ResBlock
+    with pytest.raises(PsgError):
+        NoiseScheduler().add_noise(torch.zeros(1, 8, 27, 27), torch.zeros(1, 8, 27, 27), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(PsgError):
+        ResBlock(64, 64)(torch.zeros(1))          # containers never compute
+    # product code must not import the oracle
+    for f in (ROOT / "pokemon_sprite_generator_b200").glob("*.py"):
+        assert "oracle" not in f.read_text().replace("the oracle", ""), f

@@ -1,0 +1,165 @@
+"""GPU parity of the drop-in U-Net against golden vectors produced by executing the real reference
+(oracle/make_golden.py) and against the CPU oracle (oracle/unet_oracle.py) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 mode <= 1e-4 max-abs on the noise prediction; bf16 mode <= 2e-2 max-abs
+and <= 1e-2 relative loss.  Parity is defined with dropout off (eval mode); gradients get their own
+relative checks, including the O(1)-gain "amp" re-initialisation that makes errors visible.
+"""
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD / "unet_cases.pt")
+
+
+@pytest.fixture(scope="module")
+def base_state():
+    """Seed-0 reference initialisation (bit-identical to the reference, see tests/test_oracle.py)."""
+    from pokemon_sprite_generator_b200.unet import UNet
+    torch.manual_seed(0)
+    m = UNet()
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+@pytest.fixture(scope="module")
+def unets(cuda_device, base_state):
+    from pokemon_sprite_generator_b200.unet import UNet
+    out = {}
+    for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        m = UNet(compute_dtype=dt)
+        m.load_state_dict(base_state)
+        out[name] = m.to(cuda_device).eval()
+    return out
+
+
+def _inputs(case, dev):
+    from oracle import inputs
+    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
+    latent, text, t, noise = inputs.make_inputs(case["batch"], case["text_len"], case["seed"])
+    latent, text, t, noise = latent.to(dev), text.to(dev), t.to(dev), noise.to(dev)
+    noisy = NoiseScheduler().add_noise(latent, noise, t)
+    return noisy, text, t, noise
+
+
+def _check_grads(m, case, mode):
+    """Per-parameter gradient parity.  Two oracles: the reference's own fp32 CPU run (whose conv weight-gradients on the
+    deep levels are only good to ~3e-3 of a parameter's grad norm) and, where recorded, an fp64 run of the same reference
+    module, which pins the exact values: the fp32 CUDA mode must sit on the fp64 numbers."""
+    from oracle import inputs
+    named = dict(m.named_parameters())
+    worst32 = max(abs(named[k].grad.norm().item() - n) / (n + 1e-12) for k, n in case["grad_norms"].items())
+    print(f"[{mode}] worst per-parameter grad-norm rel err vs reference fp32 = {worst32:.3e}")
+    assert worst32 <= (5e-3 if mode == "fp32" else 0.15)
+    tot = torch.sqrt(sum(p.grad.double().pow(2).sum() for p in m.parameters())).item()
+    assert abs(tot - case["grad_total_norm"]) / case["grad_total_norm"] <= (2e-4 if mode == "fp32" else 3e-2)
+    samples, norms = case["grad_samples"], None
+    if "grad_norms_fp64" in case:
+        norms, samples = case["grad_norms_fp64"], case["grad_samples_fp64"]
+        worst64 = max(abs(named[k].grad.norm().item() - n) / (n + 1e-12) for k, n in norms.items())
+        print(f"[{mode}] worst per-parameter grad-norm rel err vs reference fp64 = {worst64:.3e}")
+        assert worst64 <= (5e-5 if mode == "fp32" else 0.15)
+    for k in inputs.GRAD_KEYS:
+        g = named[k].grad.flatten()
+        samp = g[:: max(1, g.numel() // 64)][:64].cpu()
+        ref = samples[k]
+        e = (samp - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
+        assert e <= ((2e-4 if norms is not None else 2e-3) if mode == "fp32" else 0.2), (k, e)
+
+
+def _load(m, state):
+    m.load_state_dict(state)
+    return m
+
+
+@pytest.mark.parametrize("case_name", ["init_h8_b2_l32", "init_h4_b2_l32", "init_h8_b1_l7", "init_h8_b3_l77"])
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_forward_matches_reference(cuda_device, gold, unets, base_state, case_name, mode, tol):
+    case = gold["cases"][case_name]
+    m = _load(unets[mode], base_state)
+    m.num_heads = case["heads"]
+    noisy, text, t, _ = _inputs(case, cuda_device)
+    with torch.no_grad():
+        y = m(noisy, t, text)
+    m.num_heads = 8
+    assert y.shape == noisy.shape and y.dtype == torch.float32 and y.is_contiguous()
+    err = (y.cpu() - case["output"]).abs().max().item()
+    print(f"[{case_name} {mode}] max_abs_err={err:.3e} (ref std {case['output'].std():.3e})")
+    assert err <= tol
+    if mode == "fp32":
+        assert err <= 5e-6, "fp32 mode should sit at accumulation-order noise"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_loss_and_gradients_match_reference(cuda_device, gold, unets, base_state, mode):
+    from oracle import inputs
+    from pokemon_sprite_generator_b200.losses import SmoothL1Loss
+    case = gold["cases"]["init_h8_b2_l32"]
+    m = _load(unets[mode], base_state)
+    noisy, text, t, noise = _inputs(case, cuda_device)
+    m.zero_grad(set_to_none=True)
+    pred = m(noisy, t, text)
+    loss = SmoothL1Loss(beta=0.1)(pred, noise)
+    loss.backward()
+    rel = abs(loss.item() - case["loss"]) / case["loss"]
+    print(f"[{mode}] loss={loss.item():.6f} ref={case['loss']:.6f} rel={rel:.2e}")
+    assert rel <= (1e-5 if mode == "fp32" else 1e-2)
+    _check_grads(m, case, mode)
+
+
+@pytest.mark.parametrize("case_name", ["amp_h8_b2_l32", "amp_h4_b2_l32"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_amplified_init_forward_backward(cuda_device, gold, unets, base_state, case_name, mode):
+    """O(1)-gain weights: conditioning, attention and FFN paths contribute at full scale, so errors are visible."""
+    from oracle import inputs
+    from pokemon_sprite_generator_b200.losses import SmoothL1Loss
+    case = gold["cases"][case_name]
+    m = _load(unets[mode], inputs.amplify_state_dict(base_state))
+    m.num_heads = case["heads"]
+    noisy, text, t, noise = _inputs(case, cuda_device)
+    m.zero_grad(set_to_none=True)
+    pred = m(noisy, t, text)
+    loss = SmoothL1Loss(beta=0.1)(pred, noise)
+    loss.backward()
+    m.num_heads = 8
+    scale = case["output"].abs().max().item()
+    err = (pred.detach().cpu() - case["output"]).abs().max().item()
+    print(f"[{case_name} {mode}] out err={err:.3e} / scale {scale:.3f}; loss {loss.item():.6f} vs {case['loss']:.6f}")
+    assert err <= (2e-5 if mode == "fp32" else 4e-2) * scale
+    assert abs(loss.item() - case["loss"]) / case["loss"] <= (1e-5 if mode == "fp32" else 1e-2)
+    _check_grads(m, case, mode)
+
+
+def test_module_contract(cuda_device, unets, base_state):
+    """nn.Module surface the reference trainer relies on."""
+    m = _load(unets["bf16"], base_state)
+    sd = m.state_dict()
+    assert len(sd) == 479 and all(v.dtype == torch.float32 for v in sd.values())
+    params = list(m.parameters())
+    assert len(params) == 478 and all(p.is_leaf and p.requires_grad for p in params)
+    # an external optimizer updates parameters in place and the next forward sees the change
+    x = torch.randn(1, 8, 27, 27, device=cuda_device); t = torch.tensor([5], device=cuda_device)
+    te = torch.randn(1, 4, 256, device=cuda_device)
+    with torch.no_grad():
+        y0 = m(x, t, te)
+        m.final_conv[2].bias.add_(1.0)
+        y1 = m(x, t, te)
+    assert torch.allclose(y1 - y0, torch.ones_like(y0), atol=2e-2)
+    # train()/eval(): dropout makes train-mode outputs differ, eval is deterministic
+    with torch.no_grad():
+        assert torch.equal(m(x, t, te), y1)
+        m.train()
+        yt = m(x, t, te)
+        m.eval()
+    assert not torch.equal(yt, y1)
+    # errors are loud
+    with pytest.raises(Exception):
+        m(x.cpu(), t.cpu(), te.cpu())
+    with pytest.raises(Exception):
+        m(torch.randn(1, 8, 20, 20, device=cuda_device), t, te)

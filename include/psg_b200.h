@@ -107,6 +107,16 @@ int psg_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
                  void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Lq, int Lk, int hd, float scale,
                  int dtype, unsigned long long drop_seed, float drop_p, void* stream);
 
+/* tensor-core attention pieces (bf16 path): batched C[b,h] = alpha * A[b,h] B[b,h]^T with either operand stored
+ * transposed (mma.sync m16n8k16), and the row softmax / its backward with the dropout mask of the probabilities. */
+int psg_bmm_bf16(const void* a, long long a_sb, long long a_sh, long long lda, int trans_a, const void* b, long long b_sb,
+                 long long b_sh, long long ldb, int trans_b, void* c, long long c_sb, long long c_sh, long long ldc, int c_is_f32,
+                 int batch, int heads, int M, int N, int K, float alpha, void* stream);
+int psg_softmax_fwd(const float* S, void* P, void* Pd, long long rows, int Lk, int ldp, unsigned long long seed, float drop_p,
+                    void* stream);
+int psg_softmax_bwd(const void* P, const float* dPd, void* dS, void* Pd, long long rows, int Lk, int ldp, unsigned long long seed,
+                    float drop_p, void* stream);
+
 /* ---- layout, resize, reductions, conditioning inputs, weight packing ---------------------------------------------
  * upsample: nn.Upsample(bilinear, align_corners=False) unet.py:365,375,385; timestep embedding unet.py:47-50;
  * mean pool: AdaptiveAvgPool1d(1) unet.py:322,445; copy_strided: torch.cat unet.py:482-503; colsum: bias gradients. */
@@ -127,10 +137,11 @@ int psg_dropout_scale(const void* x, long long ldx, void* out, long long ldo, lo
                       unsigned long long seed, float drop_p, int dtype, void* stream);
 int psg_timestep_embedding(const long long* t, const float* coeff, float* out, int B, int half, void* stream);
 int psg_mean_pool(const float* x, float* out, int B, int L, int D, void* stream);
-int psg_pack_conv_weight(const float* w_oihw, void* wp, void* wd, int Cout, int Cin, int kk, int dtype, void* stream);
+int psg_pack_conv_weight(const float* w_oihw, void* wp, void* wd, int Cout, int Cin, int kk, int Cin_p, int Cout_p, int dtype,
+                         void* stream);
 int psg_pack_linear_weight(const float* w, void* wk, void* wt, int N, int K, int dtype, void* stream);
 int psg_wgrad_finalize(const float* partial, int splits, long long split_stride, float* grad_oihw, int Cout, int Cin, int kk,
-                       int accumulate, void* stream);
+                       int Cin_p, int accumulate, void* stream);
 int psg_sum_partials(const float* partial, int splits, long long split_stride, float* out, long long n, int accumulate,
                      void* stream);
 

@@ -90,6 +90,19 @@ def dt(t: torch.Tensor) -> int:
     return _TORCH_DT[t.dtype]
 
 
+# When set to a list, every C call appends (name, start_event, end_event): a per-kernel-family time breakdown measured
+# with CUDA events on the launching stream (tools/profile_step.py).
+CALL_PROFILE = None
+
+
 def call(name: str, *args) -> None:
     fn = getattr(load(), name)
+    prof = CALL_PROFILE
+    if prof is None:
+        check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(fn(*args), name)
+    e1.record()
+    prof.append((name, e0, e1))

@@ -271,9 +271,12 @@ __global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict_
 }
 
 // ---- weight packing ----------------------------------------------------------------------------------------
-// OIHW fp32 -> wp[Cout][kk][Cin] (fprop B operand) and wd[Cin][kk][Cout] (dgrad B operand), dtype T
+// OIHW fp32 -> wp[Cout_p][kk][Cin_p] (fprop B operand) and wd[Cin_p][kk][Cout_p] (dgrad B operand), dtype T.  The packed
+// channel counts may exceed the real ones (edge layers padded to the 64-wide tensor-core tile); the padding is zeroed
+// once by the caller and never written here.
 template <typename T>
-__global__ void pack_conv_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wd, int Cout, int Cin, int kk) {
+__global__ void pack_conv_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wd, int Cout, int Cin, int kk,
+                                 int Cin_p, int Cout_p) {
   const long long n = (long long)Cout * Cin * kk;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
     const int tap = (int)(i % kk);
@@ -281,8 +284,8 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, T* __restrict__ wp
     const int ci = (int)(t % Cin);
     const int co = (int)(t / Cin);
     const float v = w[i];
-    if (wp) psg_st(wp + ((long long)co * kk + tap) * Cin + ci, v);
-    if (wd) psg_st(wd + ((long long)ci * kk + tap) * Cout + co, v);
+    if (wp) psg_st(wp + ((long long)co * kk + tap) * Cin_p + ci, v);
+    if (wd) psg_st(wd + ((long long)ci * kk + tap) * Cout_p + co, v);
   }
 }
 // [N][K] fp32 -> wk[N][K] (cast) and wt[K][N] (transpose + cast)
@@ -310,7 +313,7 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, T* __restrict__ 
 }
 // grad_oihw[co][ci][tap] (=|+=) sum_s partial[s][co][tap*Cin + ci]
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int S, long long split_stride, float* __restrict__ grad,
-                                      int Cout, int Cin, int kk, int accumulate) {
+                                      int Cout, int Cin, int kk, int Cin_p, int accumulate) {
   const long long n = (long long)Cout * Cin * kk;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
     // iterate in packed order so partial reads are coalesced
@@ -319,7 +322,8 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int S, 
     const int tap = (int)(t % kk);
     const int co = (int)(t / kk);
     float s = 0.f;
-    for (int k = 0; k < S; ++k) s += partial[(long long)k * split_stride + i];
+    const long long src = ((long long)co * kk + tap) * Cin_p + ci;
+    for (int k = 0; k < S; ++k) s += partial[(long long)k * split_stride + src];
     float* o = grad + ((long long)co * Cin + ci) * kk + tap;
     *o = accumulate ? *o + s : s;
   }
@@ -453,9 +457,10 @@ int psg_mean_pool(const float* x, float* out, int B, int L, int D, void* stream)
   return PSG_OK;
 }
 
-int psg_pack_conv_weight(const float* w, void* wp, void* wd, int Cout, int Cin, int kk, int dtype, void* stream) {
-  PSG_CHECK_ARG(w && (wp || wd) && Cout > 0 && Cin > 0 && kk > 0, "psg_pack_conv_weight: bad args");
-  DISPATCH_T(dtype, (pack_conv_kernel<T><<<blocks_for((long long)Cout * Cin * kk), kThreads, 0, (cudaStream_t)stream>>>(w, (T*)wp, (T*)wd, Cout, Cin, kk)));
+int psg_pack_conv_weight(const float* w, void* wp, void* wd, int Cout, int Cin, int kk, int Cin_p, int Cout_p, int dtype,
+                         void* stream) {
+  PSG_CHECK_ARG(w && (wp || wd) && Cout > 0 && Cin > 0 && kk > 0 && Cin_p >= Cin && Cout_p >= Cout, "psg_pack_conv_weight: bad args");
+  DISPATCH_T(dtype, (pack_conv_kernel<T><<<blocks_for((long long)Cout * Cin * kk), kThreads, 0, (cudaStream_t)stream>>>(w, (T*)wp, (T*)wd, Cout, Cin, kk, Cin_p, Cout_p)));
   PSG_CHECK_LAUNCH("psg_pack_conv_weight");
   return PSG_OK;
 }
@@ -470,9 +475,9 @@ int psg_pack_linear_weight(const float* w, void* wk, void* wt, int N, int K, int
 }
 
 int psg_wgrad_finalize(const float* partial, int splits, long long split_stride, float* grad_oihw, int Cout, int Cin, int kk,
-                       int accumulate, void* stream) {
-  PSG_CHECK_ARG(partial && grad_oihw && splits >= 1, "psg_wgrad_finalize: bad args");
-  wgrad_finalize_kernel<<<blocks_for((long long)Cout * Cin * kk), kThreads, 0, (cudaStream_t)stream>>>(partial, splits, split_stride, grad_oihw, Cout, Cin, kk, accumulate);
+                       int Cin_p, int accumulate, void* stream) {
+  PSG_CHECK_ARG(partial && grad_oihw && splits >= 1 && Cin_p >= Cin, "psg_wgrad_finalize: bad args");
+  wgrad_finalize_kernel<<<blocks_for((long long)Cout * Cin * kk), kThreads, 0, (cudaStream_t)stream>>>(partial, splits, split_stride, grad_oihw, Cout, Cin, kk, Cin_p, accumulate);
   PSG_CHECK_LAUNCH("psg_wgrad_finalize");
   return PSG_OK;
 }

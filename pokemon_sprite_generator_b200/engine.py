@@ -66,13 +66,17 @@ class Act:
 
 
 class ConvW:
-    def __init__(self, conv: nn.Conv2d):
+    def __init__(self, conv: nn.Conv2d, pad_channels: bool):
         self.mod = conv
         self.cout, self.cin, self.k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
         self.stride, self.pad = conv.stride[0], conv.padding[0]
-        self.wp = self.wd = None
-        # shapes the tcgen05 engine cannot tile (K or N below one 64-wide TMA box) go to the SIMT engine
-        self.edge = (self.cin % 64 != 0) or (self.cout % 32 != 0)
+        self.wp = self.wd = self.bias_p = None
+        # Edge layers (init_conv Cin=8, final_conv Cout=8) do not fill a 64-wide tensor-core tile.  In bf16 mode their
+        # channels are zero-padded to 64 in the packed weights / activations so they run on the tcgen05 engine too
+        # (8x the FLOPs of a 0.04%-of-the-model layer, instead of a 100x slower CUDA-core GEMM).
+        self.cin_p = (self.cin + 63) // 64 * 64 if pad_channels else self.cin
+        self.cout_p = (self.cout + 63) // 64 * 64 if pad_channels else self.cout
+        self.padded = (self.cin_p != self.cin) or (self.cout_p != self.cout)
 
 
 class LinW:
@@ -187,7 +191,7 @@ class UNetEngine:
         self.lins: List[LinW] = []
 
         def conv(m):
-            c = ConvW(m)
+            c = ConvW(m, pad_channels=self.bf16)
             self.convs.append(c)
             return c
 
@@ -241,9 +245,12 @@ class UNetEngine:
         for c in self.convs:
             w = c.mod.weight.data
             if c.wp is None or c.wp.device != device:
-                c.wp = torch.empty(c.cout, c.k * c.k * c.cin, dtype=self.dtype, device=device)
-                c.wd = torch.empty(c.cin, c.k * c.k * c.cout, dtype=self.dtype, device=device)
-            K.pack_conv_weight(w, c.wp, c.wd)
+                c.wp = torch.zeros(c.cout_p, c.k * c.k * c.cin_p, dtype=self.dtype, device=device)
+                c.wd = torch.zeros(c.cin_p, c.k * c.k * c.cout_p, dtype=self.dtype, device=device)
+                c.bias_p = torch.zeros(1, c.cout_p, dtype=torch.float32, device=device) if c.padded else None
+            K.pack_conv_weight(w, c.wp, c.wd, c.cin_p, c.cout_p)
+            if c.bias_p is not None:
+                K.copy_strided(c.mod.bias.data.view(1, c.cout), c.bias_p[:, :c.cout])
         if self.bf16:
             done = {}
             for l in self.lins:
@@ -303,9 +310,10 @@ class UNetEngine:
         P = (x.H + 2 * cw.pad - cw.k) // cw.stride + 1
         Q = (x.W + 2 * cw.pad - cw.k) // cw.stride + 1
         if out is None:
-            out = self._new(x.B * P * Q, cw.cout, x.B, P, Q)
-        eng = self._engine_for(x.t, cw.edge)
-        bias = cw.mod.bias.data
+            out = self._new(x.B * P * Q, cw.cout_p, x.B, P, Q)
+        assert x.C == cw.cin_p and out.C == cw.cout_p, (x.C, cw.cin_p, out.C, cw.cout_p)
+        eng = self._engine_for(x.t)
+        bias = cw.bias_p[0] if cw.bias_p is not None else cw.mod.bias.data
         a = G.im2col(x.nhwc(), cw.k, cw.stride, cw.pad)
         epi = G.Epilogue(out=out.t, bias=bias, rowbias=rowbias.t if rowbias is not None else None, rows_per_group=P * Q,
                          residual=residual.t if residual is not None else None)
@@ -317,28 +325,30 @@ class UNetEngine:
     def _conv_bwd(self, x: Act, cw: ConvW, out: Act, rowbias: Act, residual: Act, x_needs_grad: bool, eng: str):
         dy = out.g()
         gb = self.store.grad_of(cw.mod.bias)
+        dy_real = dy[:, :cw.cout] if cw.cout_p != cw.cout else dy
         if rowbias is not None:
             tgt, acc = self._grad_target(rowbias)
-            K.colsum(dy, x.B, tgt, gb, acc_groups=acc)
+            K.colsum(dy_real, x.B, tgt, gb, acc_groups=acc)
         else:
-            K.colsum(dy, 1, None, gb)
+            K.colsum(dy_real, 1, None, gb)
         if residual is not None:
             tgt, acc = self._grad_target(residual)
             K.copy_strided(dy, tgt, accumulate=acc)
         # wgrad: dW[co][tap][ci] = sum_pix dY[pix, co] * im2col(X)[pix, (tap, ci)]
         gw = self.store.grad_of(cw.mod.weight)
         kk = cw.k * cw.k
-        ncols = kk * cw.cin
+        ncols = kk * cw.cin_p
         if eng == "umma":
-            tiles = ((cw.cout + 127) // 128) * kk * ((cw.cin + 127) // 128)
+            tiles = ((cw.cout_p + 127) // 128) * kk * ((cw.cin_p + 127) // 128)
             num_kb = (dy.shape[0] + 63) // 64
             split = self._pick_split(tiles, num_kb)
         else:
             split = 1
-        part = K.workspace(self.device, split * cw.cout * ncols, "wgrad").narrow(0, 0, split * cw.cout * ncols).view(split, cw.cout, ncols)
+        nel = split * cw.cout_p * ncols
+        part = K.workspace(self.device, nel, "wgrad").narrow(0, 0, nel).view(split, cw.cout_p, ncols)
         G.run_gemm(G.mnmajor(dy), G.im2col_t(x.nhwc(), cw.k, cw.stride, cw.pad), G.Epilogue(out=part[0]), engine=eng, split_k=split,
                    block_n=128 if eng == "umma" else 0)
-        K.wgrad_finalize(part, split, cw.cout * ncols, gw)
+        K.wgrad_finalize(part, split, cw.cout_p * ncols, gw, cin_p=cw.cin_p)
         if not x_needs_grad:
             return
         # dgrad
@@ -353,10 +363,10 @@ class UNetEngine:
             self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng)
         else:
             # stride-2 dgrad on the tensor-core engine: zero-insert dY to the input grid, then a stride-1 flipped conv
-            dil = torch.empty(x.B * x.H * x.W, cw.cout, dtype=dy.dtype, device=dy.device)
+            dil = torch.empty(x.B * x.H * x.W, cw.cout_p, dtype=dy.dtype, device=dy.device)
             K.dilate2(dy, dil, x.B, out.H, out.W, x.H, x.W)
             a = G.im2col(Act.nhwc_of(dil, x.B, x.H, x.W), cw.k, 1, cw.pad, flip=True)
-            self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng, algo_flops=2.0 * dy.shape[0] * cw.cin * cw.k * cw.k * cw.cout)
+            self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng, algo_flops=2.0 * dy.shape[0] * cw.cin_p * cw.k * cw.k * cw.cout_p)
 
     def _dgrad_gemm(self, a, b, tgt, res, x: Act, eng: str, alpha: float = 1.0, algo_flops=None):
         """tgt (+)= alpha * (A B^T) [* act'(x.pre) * dropmask]  -- gradient w.r.t. the pre-activation when x carries one."""
@@ -453,17 +463,25 @@ class UNetEngine:
         c = q.C
         hd = c // heads
         o = self._new(q.M, c, q.B, q.H, q.W)
-        lse = torch.empty(q.B, heads, lq, dtype=torch.float32, device=self.device) if self.taping else None
         p = drop_p if (self.training and self.dropout_enabled) else 0.0
         seed = self._seed(site)
-        K.attn_fwd(q.t, k.t, v.t, o.t, lse, q.B, heads, lq, lk, hd, seed, p)
+        tensor_core = q.t.dtype == torch.bfloat16 and lk <= 1024
+        if tensor_core:
+            P = K.attn_tc_fwd(q.t, k.t, v.t, o.t, q.B, heads, lq, lk, hd, seed, p)
+            lse = None
+        else:
+            lse = torch.empty(q.B, heads, lq, dtype=torch.float32, device=self.device) if self.taping else None
+            K.attn_fwd(q.t, k.t, v.t, o.t, lse, q.B, heads, lq, lk, hd, seed, p)
         if self.taping:
             def bwd():
                 for a in (q, k, v):
                     par = a.parent if a.parent is not None else a
                     if par.grad is None:
                         par.grad = torch.empty(par.M, par.C, dtype=par.t.dtype, device=self.device)
-                K.attn_bwd(q.t, k.t, v.t, o.t, o.g(), lse, q.g(), k.g(), v.g(), q.B, heads, lq, lk, hd, seed, p)
+                if tensor_core:
+                    K.attn_tc_bwd(q.t, k.t, v.t, o.g(), P, q.g(), k.g(), v.g(), q.B, heads, lq, lk, hd, seed, p)
+                else:
+                    K.attn_bwd(q.t, k.t, v.t, o.t, o.g(), lse, q.g(), k.g(), v.g(), q.B, heads, lq, lk, hd, seed, p)
             self.tape.append(bwd)
         return o
 
@@ -571,8 +589,9 @@ class UNetEngine:
 
         # ---- encoder ----
         s0 = LEVELS[0][1]
-        lat = Act(torch.empty(B * s0 * s0, lat_c, dtype=self.dtype, device=dev), B, s0, s0)
-        K.nchw_to_tokens(x_in, lat.t)
+        cin_p = self.d_init.cin_p
+        lat = Act((torch.zeros if cin_p != lat_c else torch.empty)(B * s0 * s0, cin_p, dtype=self.dtype, device=dev), B, s0, s0)
+        K.nchw_to_tokens(x_in, lat.t[:, :lat_c])
         x = self.conv(lat, self.d_init, x_needs_grad=False)
         skips = []
         site = 0
@@ -602,7 +621,7 @@ class UNetEngine:
         a = self.groupnorm(x, self.d_final_norm, silu=True)
         y = self.conv(a, self.d_final)
         out = torch.empty(B, lat_c, s0, s0, dtype=torch.float32, device=dev)
-        K.tokens_to_nchw(y.t, out)
+        K.tokens_to_nchw(y.t[:, :lat_c], out)
         tape, self.tape = self.tape, []
         self.taping = False
         return out, (tape, y)
@@ -611,8 +630,9 @@ class UNetEngine:
         """Runs the tape; parameter gradients are written (not accumulated) into self.store.grads."""
         tape, y = ctx
         self.taping = False
-        y.grad = torch.empty(y.M, y.C, dtype=y.t.dtype, device=y.t.device)
-        K.nchw_to_tokens(dout.detach().contiguous().float(), y.grad)
+        lat_c = dout.shape[1]
+        y.grad = (torch.zeros if y.C != lat_c else torch.empty)(y.M, y.C, dtype=y.t.dtype, device=y.t.device)
+        K.nchw_to_tokens(dout.detach().contiguous().float(), y.grad[:, :lat_c])
         while tape:
             tape.pop()()
 

@@ -167,4 +167,5 @@ def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", spl
         raise ValueError(engine)
     if prof is not None:
         ev1.record()
-        prof.append((ev0, ev1, float(algo_flops) if algo_flops is not None else 2.0 * a.rows * b.rows * a.k, engine))
+        prof.append((ev0, ev1, float(algo_flops) if algo_flops is not None else 2.0 * a.rows * b.rows * a.k, engine,
+                     (a.mode, b.mode, a.rows, b.rows, a.k, split_k)))

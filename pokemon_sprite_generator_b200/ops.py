@@ -96,11 +96,12 @@ def mean_pool(x: torch.Tensor, out: torch.Tensor) -> None:
 
 
 # ---- weights ------------------------------------------------------------------------------------------------
-def pack_conv_weight(w: torch.Tensor, wp: torch.Tensor | None, wd: torch.Tensor | None) -> None:
+def pack_conv_weight(w: torch.Tensor, wp: torch.Tensor | None, wd: torch.Tensor | None, cin_p: int = 0, cout_p: int = 0) -> None:
+    """wp [cout_p, kk*cin_p], wd [cin_p, kk*cout_p]; padded entries (cin_p > Cin / cout_p > Cout) must be pre-zeroed."""
     cout, cin, kh, kw = w.shape
     ref = wp if wp is not None else wd
-    L.call("psg_pack_conv_weight", L.ptr(w), L.ptr(wp), L.ptr(wd), C.c_int(cout), C.c_int(cin), C.c_int(kh * kw), C.c_int(L.dt(ref)),
-           L.stream_ptr())
+    L.call("psg_pack_conv_weight", L.ptr(w), L.ptr(wp), L.ptr(wd), C.c_int(cout), C.c_int(cin), C.c_int(kh * kw),
+           C.c_int(cin_p or cin), C.c_int(cout_p or cout), C.c_int(L.dt(ref)), L.stream_ptr())
 
 
 def pack_linear_weight(w: torch.Tensor, wk: torch.Tensor | None, wt: torch.Tensor | None) -> None:
@@ -109,10 +110,11 @@ def pack_linear_weight(w: torch.Tensor, wk: torch.Tensor | None, wt: torch.Tenso
     L.call("psg_pack_linear_weight", L.ptr(w), L.ptr(wk), L.ptr(wt), C.c_int(n), C.c_int(k), C.c_int(L.dt(ref)), L.stream_ptr())
 
 
-def wgrad_finalize(partial: torch.Tensor, splits: int, split_stride: int, grad: torch.Tensor, accumulate: bool = False) -> None:
+def wgrad_finalize(partial: torch.Tensor, splits: int, split_stride: int, grad: torch.Tensor, accumulate: bool = False,
+                   cin_p: int = 0) -> None:
     cout, cin, kh, kw = grad.shape
     L.call("psg_wgrad_finalize", L.ptr(partial), C.c_int(splits), C.c_longlong(split_stride), L.ptr(grad), C.c_int(cout), C.c_int(cin),
-           C.c_int(kh * kw), C.c_int(int(accumulate)), L.stream_ptr())
+           C.c_int(kh * kw), C.c_int(cin_p or cin), C.c_int(int(accumulate)), L.stream_ptr())
 
 
 def sum_partials(partial: torch.Tensor, splits: int, split_stride: int, out: torch.Tensor, accumulate: bool = False) -> None:
@@ -158,6 +160,48 @@ def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, b: int, heads: int, lq: int, lk: i
            C.c_longlong(_ld(o)), L.ptr(do), C.c_longlong(_ld(do)), L.ptr(lse), L.ptr(dsum), L.ptr(dq), C.c_longlong(_ld(dq)), L.ptr(dk),
            C.c_longlong(_ld(dk)), L.ptr(dv), C.c_longlong(_ld(dv)), C.c_int(b), C.c_int(heads), C.c_int(lq), C.c_int(lk), C.c_int(hd),
            C.c_float(1.0 / (hd ** 0.5)), C.c_int(L.dt(q)), C.c_ulonglong(drop_seed), C.c_float(drop_p), L.stream_ptr())
+
+
+# ---- tensor-core attention (bf16): batched mma.sync GEMMs + row softmax ------------------------------------------
+def _bmm(a, a_sb, a_sh, lda, ta, b, b_sb, b_sh, ldb, tb, c, c_sb, c_sh, ldc, batch, heads, m, n, k, alpha):
+    L.call("psg_bmm_bf16", L.ptr(a), C.c_longlong(a_sb), C.c_longlong(a_sh), C.c_longlong(lda), C.c_int(ta), L.ptr(b),
+           C.c_longlong(b_sb), C.c_longlong(b_sh), C.c_longlong(ldb), C.c_int(tb), L.ptr(c), C.c_longlong(c_sb), C.c_longlong(c_sh),
+           C.c_longlong(ldc), C.c_int(int(c.dtype == torch.float32)), C.c_int(batch), C.c_int(heads), C.c_int(m), C.c_int(n),
+           C.c_int(k), C.c_float(alpha), L.stream_ptr())
+
+
+def attn_tc_fwd(q, k, v, o, b: int, heads: int, lq: int, lk: int, hd: int, drop_seed: int = 0, drop_p: float = 0.0):
+    """Returns P (bf16 [b*heads*lq, lkp], un-dropped softmax) to be saved for backward."""
+    lkp = (lk + 7) // 8 * 8
+    rows = b * heads * lq
+    scale = 1.0 / (hd ** 0.5)
+    S = workspace(q.device, rows * lkp, "attn_s").narrow(0, 0, rows * lkp)
+    _bmm(q, lq * _ld(q), hd, _ld(q), 0, k, lk * _ld(k), hd, _ld(k), 0, S, heads * lq * lkp, lq * lkp, lkp, b, heads, lq, lk, hd, scale)
+    P = torch.empty(rows, lkp, dtype=torch.bfloat16, device=q.device)
+    Pd = torch.empty_like(P) if drop_p > 0.0 else None
+    L.call("psg_softmax_fwd", L.ptr(S), L.ptr(P), L.ptr(Pd), C.c_longlong(rows), C.c_int(lk), C.c_int(lkp), C.c_ulonglong(drop_seed),
+           C.c_float(drop_p), L.stream_ptr())
+    pv = Pd if Pd is not None else P
+    _bmm(pv, heads * lq * lkp, lq * lkp, lkp, 0, v, lk * _ld(v), hd, _ld(v), 1, o, lq * _ld(o), hd, _ld(o), b, heads, lq, hd, lk, 1.0)
+    return P
+
+
+def attn_tc_bwd(q, k, v, do, P, dq, dk, dv, b: int, heads: int, lq: int, lk: int, hd: int, drop_seed: int = 0,
+                drop_p: float = 0.0) -> None:
+    lkp = P.shape[1]
+    rows = b * heads * lq
+    scale = 1.0 / (hd ** 0.5)
+    bs, hs = heads * lq * lkp, lq * lkp
+    dPd = workspace(q.device, rows * lkp, "attn_s").narrow(0, 0, rows * lkp)
+    _bmm(do, lq * _ld(do), hd, _ld(do), 0, v, lk * _ld(v), hd, _ld(v), 0, dPd, bs, hs, lkp, b, heads, lq, lk, hd, 1.0)
+    dS = torch.empty(rows, lkp, dtype=torch.bfloat16, device=q.device)
+    Pd = torch.empty_like(dS) if drop_p > 0.0 else None
+    L.call("psg_softmax_bwd", L.ptr(P), L.ptr(dPd), L.ptr(dS), L.ptr(Pd), C.c_longlong(rows), C.c_int(lk), C.c_int(lkp),
+           C.c_ulonglong(drop_seed), C.c_float(drop_p), L.stream_ptr())
+    pv = Pd if Pd is not None else P
+    _bmm(pv, bs, hs, lkp, 1, do, lq * _ld(do), hd, _ld(do), 1, dv, lk * _ld(dv), hd, _ld(dv), b, heads, lk, hd, lq, 1.0)
+    _bmm(dS, bs, hs, lkp, 0, k, lk * _ld(k), hd, _ld(k), 1, dq, lq * _ld(dq), hd, _ld(dq), b, heads, lq, hd, lk, scale)
+    _bmm(dS, bs, hs, lkp, 1, q, lq * _ld(q), hd, _ld(q), 1, dk, lk * _ld(dk), hd, _ld(dk), b, heads, lk, hd, lq, scale)
 
 
 # ---- optimiser ----------------------------------------------------------------------------------------------

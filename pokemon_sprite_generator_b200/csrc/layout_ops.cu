@@ -100,23 +100,35 @@ __global__ void colsum_partial_kernel(const T* __restrict__ x, long long ld, int
     out[c] = s;
   }
 }
-// out_groups[g][c] (=|+=) sum_s partial[g][s][c] ; out_total[c] (=|+=) sum_g ...
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int groups, int S, int C, float* __restrict__ out_groups,
-                                    long long ld_groups, int acc_groups, float* __restrict__ out_total, int acc_total, float scale) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// out_groups[g][c] (=|+=) scale * sum_s partial[g][s][c] ; out_total[c] (=|+=) sum_g of that.
+// 32 channels x 8 group-lanes per block, fixed-order fold (deterministic).
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int groups, int S, int C,
+                                                           float* __restrict__ out_groups, long long ld_groups, int acc_groups,
+                                                           float* __restrict__ out_total, int acc_total, float scale) {
+  __shared__ float sh[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float tot = 0.f;
-  for (int g = 0; g < groups; ++g) {
-    float s = 0.f;
-    for (int k = 0; k < S; ++k) s += partial[((long long)(g * S + k)) * C + c];
-    s *= scale;
-    if (out_groups) {
-      float* o = out_groups + (long long)g * ld_groups + c;
-      *o = acc_groups ? *o + s : s;
+  if (c < C) {
+    for (int g = ty; g < groups; g += 8) {
+      float s = 0.f;
+      for (int k = 0; k < S; ++k) s += partial[((long long)(g * S + k)) * C + c];
+      s *= scale;
+      if (out_groups) {
+        float* o = out_groups + (long long)g * ld_groups + c;
+        *o = acc_groups ? *o + s : s;
+      }
+      tot += s;
     }
-    tot += s;
   }
-  if (out_total) out_total[c] = acc_total ? out_total[c] + tot : tot;
+  sh[ty][tx] = tot;
+  __syncthreads();
+  if (ty == 0 && c < C && out_total) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][tx];
+    out_total[c] = acc_total ? out_total[c] + t : t;
+  }
 }
 
 // ---- bilinear resize (align_corners=False), token-major ----------------------------------------------------
@@ -275,17 +287,37 @@ __global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict_
 // channel counts may exceed the real ones (edge layers padded to the 64-wide tensor-core tile); the padding is zeroed
 // once by the caller and never written here.
 template <typename T>
-__global__ void pack_conv_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wd, int Cout, int Cin, int kk,
-                                 int Cin_p, int Cout_p) {
-  const long long n = (long long)Cout * Cin * kk;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-    const int tap = (int)(i % kk);
-    const long long t = i / kk;
-    const int ci = (int)(t % Cin);
-    const int co = (int)(t / Cin);
-    const float v = w[i];
-    if (wp) psg_st(wp + ((long long)co * kk + tap) * Cin_p + ci, v);
-    if (wd) psg_st(wd + ((long long)ci * kk + tap) * Cout_p + co, v);
+__global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wd, int Cout,
+                                                        int Cin, int kk, int Cin_p, int Cout_p) {
+  extern __shared__ float tile[];  // [32 co][32 ci][kk] (+1 pad per ci row)
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int row = 32 * kk + 1;    // floats per co
+  // coalesced read: for each co, the (ci, tap) block of 32*kk consecutive floats
+  for (int idx = threadIdx.x; idx < 32 * 32 * kk; idx += blockDim.x) {
+    const int co = idx / (32 * kk), r = idx - co * (32 * kk);
+    const int ci = r / kk;
+    float v = 0.f;
+    if (co0 + co < Cout && ci0 + ci < Cin) v = w[((long long)(co0 + co) * Cin + ci0) * kk + r];
+    tile[co * row + r] = v;
+  }
+  __syncthreads();
+  // wp[co][tap][ci]: 32 consecutive ci per (co, tap)
+  if (wp) {
+    for (int idx = threadIdx.x; idx < 32 * kk * 32; idx += blockDim.x) {
+      const int ci = idx & 31, t = idx >> 5;
+      const int tap = t % kk, co = t / kk;
+      if (co0 + co < Cout && ci0 + ci < Cin)
+        psg_st(wp + ((long long)(co0 + co) * kk + tap) * Cin_p + ci0 + ci, tile[co * row + ci * kk + tap]);
+    }
+  }
+  // wd[ci][tap][co]: 32 consecutive co per (ci, tap)
+  if (wd) {
+    for (int idx = threadIdx.x; idx < 32 * kk * 32; idx += blockDim.x) {
+      const int co = idx & 31, t = idx >> 5;
+      const int tap = t % kk, ci = t / kk;
+      if (co0 + co < Cout && ci0 + ci < Cin)
+        psg_st(wd + ((long long)(ci0 + ci) * kk + tap) * Cout_p + co0 + co, tile[co * row + ci * kk + tap]);
+    }
   }
 }
 // [N][K] fp32 -> wk[N][K] (cast) and wt[K][N] (transpose + cast)
@@ -311,21 +343,29 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, T* __restrict__ 
     }
   }
 }
-// grad_oihw[co][ci][tap] (=|+=) sum_s partial[s][co][tap*Cin + ci]
-__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int S, long long split_stride, float* __restrict__ grad,
-                                      int Cout, int Cin, int kk, int Cin_p, int accumulate) {
-  const long long n = (long long)Cout * Cin * kk;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-    // iterate in packed order so partial reads are coalesced
-    const int ci = (int)(i % Cin);
-    const long long t = i / Cin;
-    const int tap = (int)(t % kk);
-    const int co = (int)(t / kk);
+// grad_oihw[co][ci][tap] (=|+=) sum_s partial[s][co][tap*Cin_p + ci]; one block per (co, 64-wide ci chunk): coalesced
+// reads of the packed layout, smem transpose, coalesced writes of the OIHW layout.
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ partial, int S, long long split_stride,
+                                                             float* __restrict__ grad, int Cout, int Cin, int kk, int Cin_p,
+                                                             int accumulate) {
+  extern __shared__ float tile[];  // [kk][64+1]
+  const int co = blockIdx.y, ci0 = blockIdx.x * 64;
+  for (int idx = threadIdx.x; idx < kk * 64; idx += blockDim.x) {
+    const int tap = idx >> 6, ci = idx & 63;
     float s = 0.f;
-    const long long src = ((long long)co * kk + tap) * Cin_p + ci;
-    for (int k = 0; k < S; ++k) s += partial[(long long)k * split_stride + src];
-    float* o = grad + ((long long)co * Cin + ci) * kk + tap;
-    *o = accumulate ? *o + s : s;
+    if (ci0 + ci < Cin) {
+      const long long src = ((long long)co * kk + tap) * Cin_p + ci0 + ci;
+      for (int k = 0; k < S; ++k) s += partial[(long long)k * split_stride + src];
+    }
+    tile[tap * 65 + ci] = s;
+  }
+  __syncthreads();
+  const int nci = min(64, Cin - ci0);
+  float* out = grad + ((long long)co * Cin + ci0) * kk;
+  for (int idx = threadIdx.x; idx < nci * kk; idx += blockDim.x) {
+    const int ci = idx / kk, tap = idx - ci * kk;
+    const float v = tile[tap * 65 + ci];
+    out[idx] = accumulate ? out[idx] + v : v;
   }
 }
 // out (=|+=) sum_s partial[s][i]   (linear wgrad split-K reduction, same layout)
@@ -398,7 +438,7 @@ int psg_colsum(const void* x, long long ld, int groups, int rows_per_group, int 
   dim3 grid(S, groups);
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, threads, (size_t)threads * 8 * sizeof(float), st>>>((const T*)x, ld, rows_per_group, C, S, workspace)));
-  colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, groups, S, C, out_groups, ld_groups, acc_groups, out_total, acc_total, scale);
+  colsum_final_kernel<<<(C + 31) / 32, 256, 0, st>>>(workspace, groups, S, C, out_groups, ld_groups, acc_groups, out_total, acc_total, scale);
   PSG_CHECK_LAUNCH("psg_colsum");
   g_psg_launch_count += 1;  // two kernels
   return PSG_OK;
@@ -460,7 +500,11 @@ int psg_mean_pool(const float* x, float* out, int B, int L, int D, void* stream)
 int psg_pack_conv_weight(const float* w, void* wp, void* wd, int Cout, int Cin, int kk, int Cin_p, int Cout_p, int dtype,
                          void* stream) {
   PSG_CHECK_ARG(w && (wp || wd) && Cout > 0 && Cin > 0 && kk > 0 && Cin_p >= Cin && Cout_p >= Cout, "psg_pack_conv_weight: bad args");
-  DISPATCH_T(dtype, (pack_conv_kernel<T><<<blocks_for((long long)Cout * Cin * kk), kThreads, 0, (cudaStream_t)stream>>>(w, (T*)wp, (T*)wd, Cout, Cin, kk, Cin_p, Cout_p)));
+  PSG_CHECK_ARG(kk <= 9, "psg_pack_conv_weight: kernel area > 9 unsupported");
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+  PSG_CHECK_ARG(grid.y <= 65535, "psg_pack_conv_weight: Cout too large");
+  const size_t smem = (size_t)32 * (32 * kk + 1) * sizeof(float);
+  DISPATCH_T(dtype, (pack_conv_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (T*)wp, (T*)wd, Cout, Cin, kk, Cin_p, Cout_p)));
   PSG_CHECK_LAUNCH("psg_pack_conv_weight");
   return PSG_OK;
 }
@@ -477,7 +521,9 @@ int psg_pack_linear_weight(const float* w, void* wk, void* wt, int N, int K, int
 int psg_wgrad_finalize(const float* partial, int splits, long long split_stride, float* grad_oihw, int Cout, int Cin, int kk,
                        int Cin_p, int accumulate, void* stream) {
   PSG_CHECK_ARG(partial && grad_oihw && splits >= 1 && Cin_p >= Cin, "psg_wgrad_finalize: bad args");
-  wgrad_finalize_kernel<<<blocks_for((long long)Cout * Cin * kk), kThreads, 0, (cudaStream_t)stream>>>(partial, splits, split_stride, grad_oihw, Cout, Cin, kk, Cin_p, accumulate);
+  dim3 grid((Cin + 63) / 64, Cout);
+  PSG_CHECK_ARG(Cout <= 65535, "psg_wgrad_finalize: Cout too large");
+  wgrad_finalize_kernel<<<grid, 256, (size_t)kk * 65 * sizeof(float), (cudaStream_t)stream>>>(partial, splits, split_stride, grad_oihw, Cout, Cin, kk, Cin_p, accumulate);
   PSG_CHECK_LAUNCH("psg_wgrad_finalize");
   return PSG_OK;
 }

@@ -24,12 +24,21 @@ txt = torch.randn(B, 32, 256, device=dev)
 for _ in range(3):
     step(lat, txt)
 torch.cuda.synchronize()
-L.CALL_PROFILE, G.PROFILE = [], []
+import os
+NCU = os.environ.get("PSG_NCU") == "1"      # under ncu: --profile-from-start off, one step between start/stop
+if not NCU:
+    L.CALL_PROFILE, G.PROFILE = [], []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if NCU:
+    torch.cuda.profiler.start()
 e0.record()
 step(lat, txt)
 e1.record()
 torch.cuda.synchronize()
+if NCU:
+    torch.cuda.profiler.stop()
+    print(f"step under profiler: {e0.elapsed_time(e1):.1f} ms")
+    sys.exit(0)
 calls, gemms = L.CALL_PROFILE, G.PROFILE
 L.CALL_PROFILE, G.PROFILE = None, None
 total = e0.elapsed_time(e1)

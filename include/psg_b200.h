@@ -72,8 +72,11 @@ typedef struct PsgGemmDesc {
   PsgEpilogue epi;
 } PsgGemmDesc;
 
-/* tcgen05 / TMEM / TMA engine (bf16 operands, fp32 accumulate).  block_n: 0 = auto, or 64/128/160/256. */
+/* tcgen05 / TMEM / TMA engine (bf16 operands, fp32 accumulate), persistent CTAs.  block_n: 0 = auto, or 64/128/160/256;
+ * m_tiles: 0 = auto, 1 or 2 (CTA tile = 128*m_tiles rows).  psg_umma_plan reports the automatic choice. */
 int psg_umma_gemm(const PsgGemmDesc* desc, int block_n, void* stream);
+int psg_umma_gemm_ex(const PsgGemmDesc* desc, int block_n, int m_tiles, void* stream);
+int psg_umma_plan(const PsgGemmDesc* desc, int* block_n, int* m_tiles);
 /* CUDA-core fp32-accumulate engine (fp32 parity mode, edge shapes, general-stride dgrad gather). */
 int psg_simt_gemm(const PsgGemmDesc* desc, void* stream);
 

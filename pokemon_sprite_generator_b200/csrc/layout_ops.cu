@@ -110,15 +110,24 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
   const int c = blockIdx.x * 32 + tx;
   float tot = 0.f;
   if (c < C) {
-    for (int g = ty; g < groups; g += 8) {
-      float s = 0.f;
-      for (int k = 0; k < S; ++k) s += partial[((long long)(g * S + k)) * C + c];
-      s *= scale;
-      if (out_groups) {
+    if (out_groups == nullptr) {
+      // total only: all groups*S partial rows are equivalent -> spread them over the 8 row-lanes
+      const int rows = groups * S;
+      int r = ty;
+      for (; r + 24 < rows; r += 32)
+        tot += (partial[(long long)r * C + c] + partial[(long long)(r + 8) * C + c]) +
+               (partial[(long long)(r + 16) * C + c] + partial[(long long)(r + 24) * C + c]);
+      for (; r < rows; r += 8) tot += partial[(long long)r * C + c];
+      tot *= scale;
+    } else {
+      for (int g = ty; g < groups; g += 8) {
+        float s = 0.f;
+        for (int k = 0; k < S; ++k) s += partial[((long long)(g * S + k)) * C + c];
+        s *= scale;
         float* o = out_groups + (long long)g * ld_groups + c;
         *o = acc_groups ? *o + s : s;
+        tot += s;
       }
-      tot += s;
     }
   }
   sh[ty][tx] = tot;

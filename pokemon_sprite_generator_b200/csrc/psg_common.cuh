@@ -110,11 +110,14 @@ __device__ __forceinline__ float psg_gelu_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Stateless counter-based dropout mask: keep iff hash(seed, idx) >= threshold (threshold = p * 2^32).
+// Stateless counter-based dropout mask: keep iff hash(seed, idx) >= threshold (threshold = p * 2^32).  32-bit mixer
+// (two multiply/xorshift rounds): it runs once per element inside GEMM epilogues, where a 64-bit mixer was the bottleneck.
 __device__ __forceinline__ uint32_t psg_hash32(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+  uint32_t x = (uint32_t)idx ^ ((uint32_t)(idx >> 32) * 0x9E3779B9u) ^ (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu);
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
 }

@@ -1,9 +1,9 @@
 // tcgen05 / TMEM / TMA GEMM + implicit-GEMM convolution engine for sm_100a (bf16 in, fp32 accumulate).
 //
-// One warp-specialised kernel, three roles (192 threads):
+// One warp-specialised persistent kernel, three roles (320 threads):
 //   warp 0      TMA producer  : cp.async.bulk.tensor (tiled 2D, or im2col 4D over NHWC) -> 128B-swizzled smem ring
 //   warp 1      MMA issuer    : one thread issues tcgen05.mma (M=128, N=kBlockN, K=16) into a TMEM accumulator
-//   warps 2..5  epilogue      : tcgen05.ld TMEM -> registers -> fused epilogue (gemm_epilogue.cuh) -> global
+//   warps 2..9  epilogue      : tcgen05.ld TMEM -> registers -> fused epilogue (gemm_epilogue.cuh) -> global
 //
 // kMode 0 ("TN"):  A K-major (tiled matrix or im2col pixels), B K-major matrix.   fprop / dgrad / linears.
 // kMode 1 ("NT"):  A MN-major matrix, B MN-major (tiled matrix or im2col pixels). wgrad (reduction over rows).
@@ -19,7 +19,7 @@ namespace umma {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
 
 struct alignas(64) KernelParams {
@@ -27,6 +27,7 @@ struct alignas(64) KernelParams {
   CUtensorMap tm_b;
   int M, N;
   int num_kb, kb_per_split;
+  int num_m_tiles, num_n_tiles, splits;
   // mode 0, A im2col
   int a_im2col, cblks, ksize, conv_stride, pad, flip, P, Q;
   // mode 1, B im2col (wgrad): columns are (tap, cin)
@@ -251,106 +252,131 @@ __device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint3
 
 __host__ __device__ constexpr uint32_t tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-template <int kBlockN, int kStages>
+// kMT = number of 128-row MMA tiles stacked in one CTA tile (BLOCK_M = 128 * kMT).  The two MMAs of a k-step share
+// the B tile in shared memory, which halves the L2->SM bytes per FLOP of the weight operand; measured on B200 the
+// engine is bound by operand delivery (bytes per FLOP), not by the tensor pipe, so larger CTA tiles are what moves it.
+template <int kBlockN, int kStages, int kMT>
 struct SmemLayout {
+  static constexpr uint32_t A_TILE_BYTES = A_BYTES * kMT;
   static constexpr uint32_t B_BYTES = kBlockN * BLOCK_K * 2;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_BYTES;
+  static constexpr int kAcc = (2 * kMT * kBlockN <= 512) ? 2 : 1;          // TMEM accumulator stages
+  static constexpr uint32_t TMEM_COLS = tmem_cols_for(kAcc * kMT * kBlockN);
   static constexpr uint32_t BAR_OFFSET = STAGE_BYTES * kStages;
-  static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * kStages + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * kStages + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// the kernel: persistent CTAs, static round-robin over (tile, split) work items
 // ---------------------------------------------------------------------------------------------
-template <int kBlockN, int kStages, int kMode>
+template <int kBlockN, int kStages, int kMode, int kMT>
 __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_constant__ KernelParams p) {
-  using L = SmemLayout<kBlockN, kStages>;
+  using L = SmemLayout<kBlockN, kStages, kMT>;
+  constexpr int kAcc = L::kAcc;
+  constexpr int BM = BLOCK_M * kMT;
   static_assert(kBlockN % 32 == 0 && kBlockN <= 256, "BLOCK_N must be a multiple of 32 (epilogue chunk) and <= 256");
   static_assert(kMode == 0 || kBlockN % 64 == 0, "MN-major B tiles are built from 64-wide TMA boxes");
+  static_assert(kMT * kBlockN <= 512, "accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = smem + L::BAR_OFFSET;
   const uint32_t bar_empty = bar_full + 8 * kStages;
-  const uint32_t bar_tmem = bar_empty + 8 * kStages;
-  const uint32_t tmem_slot = bar_tmem + 8;
-  uint32_t* tmem_slot_ptr =
-      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const uint32_t bar_tfull = bar_empty + 8 * kStages;     // [kAcc] accumulator ready for the epilogue
+  const uint32_t bar_tempty = bar_tfull + 16;             // [kAcc] accumulator drained by the epilogue
+  const uint32_t tmem_slot = bar_tempty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y, split = blockIdx.z;
-  const int m0 = tile_m * BLOCK_M;
-  const int kb0 = split * p.kb_per_split;
-  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-  const int nkb = kb1 - kb0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tm_a);
     prefetch_tmap(&p.tm_b);
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_tmem, 1);
+    for (int a = 0; a < kAcc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols_for(kBlockN));
+  if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot_ptr;
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_work = p.num_m_tiles * p.num_n_tiles * p.splits;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      int w0 = 0, h0 = 0, img0 = 0;
-      if (kMode == 0 && p.a_im2col) {
-        const int pq = p.P * p.Q;
-        img0 = m0 / pq;
-        const int rem = m0 - img0 * pq;
-        const int pp = rem / p.Q, qq = rem - pp * p.Q;
-        w0 = qq * p.conv_stride - p.pad;
-        h0 = pp * p.conv_stride - p.pad;
-      }
-      int b_tap = 0, b_c0 = tile_n * kBlockN;
-      if (kMode == 1 && p.b_im2col) {
-        b_tap = tile_n / p.tiles_per_tap;
-        b_c0 = (tile_n - b_tap * p.tiles_per_tap) * kBlockN;
-      }
-      for (int it = 0; it < nkb; ++it) {
-        const int kb = kb0 + it;
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t full = bar_full + 8 * s;
-        mbar_expect_tx(full, L::STAGE_BYTES);
-        const uint32_t sa = smem + s * L::STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
-        if (kMode == 0) {
-          if (p.a_im2col) {
-            const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
-            int r = tap / p.ksize, ss = tap - r * p.ksize;
-            if (p.flip) { r = p.ksize - 1 - r; ss = p.ksize - 1 - ss; }
-            tma_load_im2col_4d(sa, &p.tm_a, full, cb * BLOCK_K, w0, h0, img0, (uint16_t)ss, (uint16_t)r);
-          } else {
-            tma_load_2d(sa, &p.tm_a, full, kb * BLOCK_K, m0);
-          }
-          tma_load_2d(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN);
-        } else {
+      uint32_t it = 0;   // global k-block counter: smem ring position and phase carry across work items
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int split = work % p.splits;
+        const int tile = work / p.splits;
+        const int tile_n = tile % p.num_n_tiles, tile_m = tile / p.num_n_tiles;
+        const int m0 = tile_m * BM;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        int w0[kMT], h0[kMT], img0[kMT];
+        if (kMode == 0 && p.a_im2col) {
+          const int pq = p.P * p.Q;
 #pragma unroll
-          for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * 8192, &p.tm_a, full, m0 + 64 * j, kb * BLOCK_K);
-          if (p.b_im2col) {
-            const int pix = kb * BLOCK_K;
-            const int pq = p.P * p.Q;
-            const int img = pix / pq;
-            const int rem = pix - img * pq;
+          for (int t = 0; t < kMT; ++t) {
+            const int mm = m0 + t * BLOCK_M;
+            img0[t] = mm / pq;
+            const int rem = mm - img0[t] * pq;
             const int pp = rem / p.Q, qq = rem - pp * p.Q;
-            const int r = b_tap / p.ksize, ss = b_tap - r * p.ksize;
+            w0[t] = qq * p.conv_stride - p.pad;
+            h0[t] = pp * p.conv_stride - p.pad;
+          }
+        }
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, L::STAGE_BYTES);
+          const uint32_t sa = smem + s * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_TILE_BYTES;
+          if (kMode == 0) {
+            if (p.a_im2col) {
+              const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
+              int r = tap / p.ksize, ss = tap - r * p.ksize;
+              if (p.flip) { r = p.ksize - 1 - r; ss = p.ksize - 1 - ss; }
 #pragma unroll
-            for (int j = 0; j < kBlockN / 64; ++j)
-              tma_load_im2col_4d(sb + j * 8192, &p.tm_b, full, b_c0 + 64 * j, qq * p.conv_stride - p.pad,
-                                 pp * p.conv_stride - p.pad, img, (uint16_t)ss, (uint16_t)r);
+              for (int t = 0; t < kMT; ++t)
+                tma_load_im2col_4d(sa + t * A_BYTES, &p.tm_a, full, cb * BLOCK_K, w0[t], h0[t], img0[t], (uint16_t)ss, (uint16_t)r);
+            } else {
+#pragma unroll
+              for (int t = 0; t < kMT; ++t) tma_load_2d(sa + t * A_BYTES, &p.tm_a, full, kb * BLOCK_K, m0 + t * BLOCK_M);
+            }
+            tma_load_2d(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN);
           } else {
 #pragma unroll
-            for (int j = 0; j < kBlockN / 64; ++j)
-              tma_load_2d(sb + j * 8192, &p.tm_b, full, tile_n * kBlockN + 64 * j, kb * BLOCK_K);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &p.tm_a, full, m0 + 64 * j, kb * BLOCK_K);
+            if (p.b_im2col) {
+              const int pix = kb * BLOCK_K;
+              const int pq = p.P * p.Q;
+              const int img = pix / pq;
+              const int rem = pix - img * pq;
+              const int pp = rem / p.Q, qq = rem - pp * p.Q;
+              // columns are the flat (tap, cin) index; cin % 64 == 0, so every 64-wide box lies inside one tap
+#pragma unroll
+              for (int j = 0; j < kBlockN / 64; ++j) {
+                const int col = tile_n * kBlockN + 64 * j;
+                int tap = col / p.cin;
+                int c0 = col - tap * p.cin;
+                if (tap >= p.ksize * p.ksize) { tap = 0; c0 = p.cin; }     // past the last tap: channel OOB -> zero fill
+                const int r = tap / p.ksize, ss = tap - r * p.ksize;
+                tma_load_im2col_4d(sb + j * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
+                                   (uint16_t)ss, (uint16_t)r);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < kBlockN / 64; ++j)
+                tma_load_2d(sb + j * 8192, &p.tm_b, full, tile_n * kBlockN + 64 * j, kb * BLOCK_K);
+            }
           }
         }
       }
@@ -360,65 +386,80 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc(kBlockN, kMode, kMode);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
+      uint32_t it = 0;
+      int wi = 0;   // local work counter -> accumulator stage and phase
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++wi) {
+        const int split = work % p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int acc = wi % kAcc;
+        const uint32_t aph = (wi / kAcc) & 1;
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem + s * L::STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t tmem_acc = tmem_base + acc * (kMT * kBlockN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem + s * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          uint64_t ad, bd;
-          if (kMode == 0) {
-            ad = make_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            bd = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-          } else {
-            ad = make_desc(sa + k * (UMMA_K * 128), 8192, 1024);
-            bd = make_desc(sb + k * (UMMA_K * 128), 8192, 1024);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            uint64_t bd;
+            if (kMode == 0) bd = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            else            bd = make_desc(sb + k * (UMMA_K * 128), 8192, 1024);
+#pragma unroll
+            for (int t = 0; t < kMT; ++t) {
+              uint64_t ad;
+              if (kMode == 0) ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 2), 16, 1024);
+              else            ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 128), 8192, 1024);
+              umma_bf16(tmem_acc + t * kBlockN, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_bf16(tmem_acc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);   // frees the smem slot once these MMAs have read it
         }
-        umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs have read it
+        umma_commit(bar_tfull + 8 * acc);   // accumulator complete
       }
-      umma_commit(bar_tmem);             // accumulator complete
     }
     __syncwarp();
   } else {
     // ===== epilogue warps =====
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    mbar_wait(bar_tmem, 0);
-    tc_fence_after();
-    const long long m = (long long)m0 + q * 32 + lane;
-    float* out_override = nullptr;
-    if (p.kb_per_split < p.num_kb) out_override = reinterpret_cast<float*>(p.epi.out) + (long long)split * p.split_stride;
-    long long col_base;
-    int col_limit;
-    if (kMode == 1 && p.b_im2col) {
-      const int tap = tile_n / p.tiles_per_tap;
-      const int c0 = (tile_n - tap * p.tiles_per_tap) * kBlockN;
-      col_base = (long long)tap * p.cin + c0;
-      col_limit = p.cin - c0;
-    } else {
-      col_base = (long long)tile_n * kBlockN;
-      col_limit = p.N - tile_n * kBlockN;
-    }
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;       // the two warps of a quarter take alternate 32-column chunks
+    int wi = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++wi) {
+      const int split = work % p.splits;
+      const int tile = work / p.splits;
+      const int tile_n = tile % p.num_n_tiles, tile_m = tile / p.num_n_tiles;
+      const int acc = wi % kAcc;
+      const uint32_t aph = (wi / kAcc) & 1;
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * (kMT * kBlockN);
+      float* out_override = nullptr;
+      if (p.splits > 1) out_override = reinterpret_cast<float*>(p.epi.out) + (long long)split * p.split_stride;
+      const long long col_base = (long long)tile_n * kBlockN;
+      const int col_limit = p.N - tile_n * kBlockN;
 #pragma unroll 1
-    for (int ch = 0; ch < kBlockN / 32; ++ch) {
-      uint32_t acc[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + ch * 32, acc);
-      int nvalid = col_limit - ch * 32;
-      nvalid = nvalid > 32 ? 32 : nvalid;
-      if (nkb == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = 0u;
+      for (int t = 0; t < kMT; ++t) {
+        const long long m = (long long)tile_m * BM + t * BLOCK_M + q * 32 + lane;
+#pragma unroll 1
+        for (int ch = chalf; ch < kBlockN / 32; ch += 2) {
+          uint32_t accv[32];
+          tmem_ld32(tmem_acc + t * kBlockN + ((uint32_t)(q * 32) << 16) + ch * 32, accv);
+          int nvalid = col_limit - ch * 32;
+          nvalid = nvalid > 32 ? 32 : nvalid;
+          if (m < p.M && nvalid > 0) epilogue_chunk(p.epi, accv, m, col_base + ch * 32, nvalid, p.N, out_override);
+        }
       }
-      if (m < p.M && nvalid > 0) epilogue_chunk(p.epi, acc, m, col_base + ch * 32, nvalid, p.N, out_override);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_acc, tmem_cols_for(kBlockN));
+  if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -491,11 +532,12 @@ static int make_im2col_map(CUtensorMap* tm, const PsgOperand& o, int channels_pe
   return PSG_OK;
 }
 
-template <int kBlockN, int kStages, int kMode>
+template <int kBlockN, int kStages, int kMode, int kMT>
 static int launch(const KernelParams& kp, dim3 grid, cudaStream_t stream) {
-  using L = SmemLayout<kBlockN, kStages>;
+  using L = SmemLayout<kBlockN, kStages, kMT>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static bool configured = false;
-  auto kern = umma_gemm_kernel<kBlockN, kStages, kMode>;
+  auto kern = umma_gemm_kernel<kBlockN, kStages, kMode, kMT>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
     if (e != cudaSuccess) { psg_set_error("umma: cudaFuncSetAttribute(smem=%u): %s", L::TOTAL, cudaGetErrorString(e)); return PSG_ERR_CUDA; }
@@ -510,8 +552,43 @@ static int launch(const KernelParams& kp, dim3 grid, cudaStream_t stream) {
 
 extern "C" {
 
-// block_n: 0 = auto, else one of 64/128/160/256 (160 only for K-major B).
-int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) {
+// Tile-shape heuristic shared by the auto path and psg_umma_plan (the host needs the tile counts to pick split-K).
+static void plan_tiles(int mode, long long M, long long N, long long K, int* block_n, int* m_tiles) {
+  const int sms = psg_num_sms();
+  int bn = *block_n;
+  if (bn == 0) {
+    if (mode == 0) {
+      if (N % 256 == 0 || N >= 512) bn = 256;          // OOB-padded 256-wide tiles beat exact 128/160-wide ones (measured)
+      else if (N % 160 == 0) bn = 160;
+      else bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    } else {
+      bn = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+    }
+  }
+  int mt = *m_tiles;
+  if (mt == 0) {
+    const long long n_tiles = (N + bn - 1) / bn;
+    const long long tiles2 = ((M + 255) / 256) * n_tiles;
+    const long long pad1 = (M + 127) / 128 * 128, pad2 = (M + 255) / 256 * 256;
+    mt = 1;
+    // 256-row CTA tiles (two MMAs share the B tile) pay off for long reductions with at least a full wave of tiles and
+    // no extra row padding; short-K GEMMs prefer 128-row tiles with double-buffered TMEM (epilogue overlap).
+    if (M > 128 && tiles2 >= sms && pad2 == pad1 && (mode == 1 || K >= 2048)) mt = 2;
+  }
+  *block_n = bn;
+  *m_tiles = mt;
+}
+
+// Reports the tile shape psg_umma_gemm would use for this problem (block_n / m_tiles: in = request or 0, out = choice).
+int psg_umma_plan(const PsgGemmDesc* d, int* block_n, int* m_tiles) {
+  PSG_CHECK_ARG(d && block_n && m_tiles, "psg_umma_plan: null pointer");
+  const int mode = (d->a.mode == PSG_OP_MNMAJOR) ? 1 : 0;
+  plan_tiles(mode, d->M, d->N, d->K, block_n, m_tiles);
+  return PSG_OK;
+}
+
+// block_n: 0 = auto, else 64/128/160/256 (160 only for K-major B).  m_tiles: 0 = auto, 1 or 2 (CTA tile = 128*m_tiles rows).
+int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* stream) {
   using namespace umma;
   PSG_CHECK_ARG(d != nullptr, "psg_umma_gemm: null desc");
   PSG_CHECK_ARG(d->in_dtype == PSG_DTYPE_BF16, "psg_umma_gemm: operands must be bf16");
@@ -523,6 +600,7 @@ int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) {
   else { psg_set_error("psg_umma_gemm: unsupported operand modes a=%d b=%d", am, bm); return PSG_ERR_UNSUPPORTED; }
   PSG_CHECK_ARG(((uintptr_t)d->a.ptr % 16 == 0) && ((uintptr_t)d->b.ptr % 16 == 0), "psg_umma_gemm: operands must be 16B aligned");
   PSG_CHECK_ARG((d->a.ld % 8 == 0) && (d->b.ld % 8 == 0), "psg_umma_gemm: pitches must be multiples of 8 elements");
+  PSG_CHECK_ARG(m_tiles >= 0 && m_tiles <= 2, "psg_umma_gemm: m_tiles must be 0, 1 or 2");
   int rc = load_driver_fns();
   if (rc) return rc;
 
@@ -532,11 +610,7 @@ int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) {
   kp.N = (int)d->N;
   kp.epi = d->epi;
   const int split = d->split_k > 1 ? d->split_k : 1;
-
-  if (block_n == 0) {
-    if (mode == 0) block_n = (d->N % 256 == 0) ? 256 : (d->N % 160 == 0 ? 160 : (d->N % 128 == 0 ? 128 : (d->N > 128 ? 256 : (d->N > 64 ? 128 : 64))));
-    else block_n = 128;
-  }
+  plan_tiles(mode, d->M, d->N, d->K, &block_n, &m_tiles);
 
   long long n_tiles;
   if (mode == 0) {
@@ -567,12 +641,12 @@ int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) {
       const PsgOperand& b = d->b;
       PSG_CHECK_ARG(d->N == (long long)b.ksize * b.ksize * b.c, "psg_umma_gemm: N != ksize^2*C");
       PSG_CHECK_ARG(d->K == (long long)b.n * b.p * b.q, "psg_umma_gemm: K != n*p*q");
-      PSG_CHECK_ARG(b.c % 8 == 0, "psg_umma_gemm: C %% 8 != 0");
+      PSG_CHECK_ARG(b.c % 64 == 0, "psg_umma_gemm: wgrad im2col needs C %% 64 == 0 (C=%d)", b.c);
       rc = make_im2col_map(&kp.tm_b, b, 64, BLOCK_K);
       if (rc) return rc;
-      kp.b_im2col = 1; kp.cin = b.c; kp.tiles_per_tap = (b.c + block_n - 1) / block_n;
+      kp.b_im2col = 1; kp.cin = b.c; kp.tiles_per_tap = 0;
       kp.ksize = b.ksize; kp.conv_stride = b.stride; kp.pad = b.pad; kp.P = b.p; kp.Q = b.q;
-      n_tiles = (long long)kp.tiles_per_tap * b.ksize * b.ksize;
+      n_tiles = (d->N + block_n - 1) / block_n;
     } else {
       rc = make_tiled_map(&kp.tm_b, d->b.ptr, d->K, d->N, d->b.ld, 64, 64);
       if (rc) return rc;
@@ -587,30 +661,39 @@ int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) {
     PSG_CHECK_ARG(eff_split == split, "psg_umma_gemm: split_k=%d does not divide %d k-blocks evenly enough", split, kp.num_kb);
     kp.split_stride = d->M * d->epi.ldc;
   }
-  const long long m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
-  PSG_CHECK_ARG(m_tiles <= 65535 && split <= 65535, "psg_umma_gemm: grid too large");
-  dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)split);
+  const long long m_tiles_n = (d->M + BLOCK_M * m_tiles - 1) / (BLOCK_M * m_tiles);
+  const long long work = m_tiles_n * n_tiles * split;
+  PSG_CHECK_ARG(work < 2147483647LL, "psg_umma_gemm: too many tiles");
+  kp.num_m_tiles = (int)m_tiles_n;
+  kp.num_n_tiles = (int)n_tiles;
+  kp.splits = split;
+  const int sms = psg_num_sms();
+  dim3 grid((unsigned)(work < sms ? work : sms));
   cudaStream_t s = (cudaStream_t)stream;
 
-#define PSG_LAUNCH(BN, ST, MODE) return launch<BN, ST, MODE>(kp, grid, s)
+#define PSG_LAUNCH(BN, ST1, ST2, MODE)                              \
+  if (m_tiles == 1) return launch<BN, ST1, MODE, 1>(kp, grid, s);  \
+  else return launch<BN, ST2, MODE, 2>(kp, grid, s)
   if (mode == 0) {
     switch (block_n) {
-      case 64: PSG_LAUNCH(64, 6, 0);
-      case 128: PSG_LAUNCH(128, 6, 0);
-      case 160: PSG_LAUNCH(160, 5, 0);
-      case 256: PSG_LAUNCH(256, 4, 0);
+      case 64: PSG_LAUNCH(64, 6, 5, 0);
+      case 128: PSG_LAUNCH(128, 6, 4, 0);
+      case 160: PSG_LAUNCH(160, 5, 4, 0);
+      case 256: PSG_LAUNCH(256, 4, 3, 0);
     }
   } else {
     switch (block_n) {
-      case 64: PSG_LAUNCH(64, 6, 1);
-      case 128: PSG_LAUNCH(128, 6, 1);
-      case 256: PSG_LAUNCH(256, 4, 1);
+      case 64: PSG_LAUNCH(64, 6, 5, 1);
+      case 128: PSG_LAUNCH(128, 6, 4, 1);
+      case 256: PSG_LAUNCH(256, 4, 3, 1);
     }
   }
 #undef PSG_LAUNCH
   psg_set_error("psg_umma_gemm: unsupported block_n=%d for mode %d", block_n, mode);
   return PSG_ERR_UNSUPPORTED;
 }
+
+int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) { return psg_umma_gemm_ex(d, block_n, 0, stream); }
 
 // Test hook: 1 if any mbarrier wait timed out since the last call (synchronises the device).
 int psg_umma_timeout_flag() {

@@ -134,13 +134,27 @@ class Epilogue:
             e.drop_scale = 1.0
 
 
+def plan(a: Operand, b: Operand, block_n: int = 0, m_tiles: int = 0):
+    """Tile shape the tcgen05 engine will use for this problem: (block_n, m_tiles, number of output tiles)."""
+    d = L.PsgGemmDesc()
+    a.fill(d.a)
+    b.fill(d.b)
+    d.M, d.N, d.K = a.rows, b.rows, a.k
+    bn, mt = C.c_int(block_n), C.c_int(m_tiles)
+    L.check(L.load().psg_umma_plan(C.byref(d), C.byref(bn), C.byref(mt)), "psg_umma_plan")
+    bn, mt = bn.value, mt.value
+    mtiles = -(-a.rows // (128 * mt))
+    ntiles = -(-b.rows // bn)
+    return bn, mt, mtiles * ntiles
+
+
 # When set to a list, every launch appends (start_event, end_event, algorithmic_flops, engine): bench.py uses it to time
 # the tensor-core kernel on its own stream inside the timed region (roofline numerator and denominator).
 PROFILE = None
 
 
 def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", split_k: int = 1, block_n: int = 0,
-             algo_flops: Optional[float] = None) -> None:
+             m_tiles: int = 0, algo_flops: Optional[float] = None) -> None:
     """C[M,N] = epilogue(sum_k A(m,k) B(n,k)).  engine: 'umma' (tcgen05, bf16), 'simt', or 'auto'.
     algo_flops: algorithmic FLOPs of this launch when they differ from 2*M*N*K (zero-inserted stride-2 dgrad)."""
     assert a.k == b.k, f"K mismatch {a.k} vs {b.k}"
@@ -160,7 +174,7 @@ def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", spl
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     if engine == "umma":
-        L.check(lib.psg_umma_gemm(C.byref(d), C.c_int(block_n), L.stream_ptr()), "psg_umma_gemm")
+        L.check(lib.psg_umma_gemm_ex(C.byref(d), C.c_int(block_n), C.c_int(m_tiles), L.stream_ptr()), "psg_umma_gemm")
     elif engine == "simt":
         L.check(lib.psg_simt_gemm(C.byref(d), L.stream_ptr()), "psg_simt_gemm")
     else:

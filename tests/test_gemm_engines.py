@@ -207,3 +207,51 @@ def test_strided_views(cuda_device):
     _check_timeout(L)
     _close(outbuf[:, N:], cat[:, C0:].float() @ w.float().t(), 6e-3, "strided")
     assert outbuf[:, :N].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("mt", [1, 2])
+@pytest.mark.parametrize("bn", [64, 128, 160, 256])
+def test_umma_tile_shapes_tn(cuda_device, mt, bn):
+    """Every CTA tile shape of the persistent tcgen05 kernel (128*mt x bn), multiple work items per CTA."""
+    L, G = _mods()
+    M, N, K = 128 * 150 * mt + 77, 640, 320          # > 148 tiles so that CTAs loop; ragged M; N not a multiple of 256
+    g = torch.Generator(device="cuda").manual_seed(mt * 1000 + bn)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out, bias=bias), engine="umma", block_n=bn, m_tiles=mt)
+    torch.cuda.synchronize()
+    _check_timeout(L)
+    _close(out, a.float() @ b.float().t() + bias, 6e-3, f"tile {128 * mt}x{bn}")
+
+
+@pytest.mark.parametrize("mt", [1, 2])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_umma_tile_shapes_wgrad(cuda_device, mt, bn):
+    L, G = _mods()
+    n, h, cin, cout, split = 6, 14, 320, 384, 3
+    x, wt = _conv_inputs(n, h, h, cin, cout, 77 + bn + mt, torch.bfloat16)
+    dy = torch.randn(n * h * h, cout, device="cuda").bfloat16()
+    part = torch.full((split, cout, 9 * cin), float("nan"), device="cuda")
+    G.run_gemm(G.mnmajor(dy), G.im2col_t(x, 3, 1, 1), G.Epilogue(out=part[0]), engine="umma", split_k=split, block_n=bn, m_tiles=mt)
+    torch.cuda.synchronize()
+    _check_timeout(L)
+    dw = part.sum(0).reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy.float().reshape(n, h, h, cout).permute(0, 3, 1, 2),
+                                      stride=1, padding=1)
+    _close(dw, ref, 1e-4, f"wgrad tile {128 * mt}x{bn}")
+
+
+@pytest.mark.parametrize("mt", [1, 2])
+def test_umma_tile_shapes_conv(cuda_device, mt):
+    L, G = _mods()
+    n, h, cin, cout = 40, 27, 64, 320
+    x, wt = _conv_inputs(n, h, h, cin, cout, 5 + mt, torch.bfloat16)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    out = torch.full((n * h * h, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.im2col(x, 3, 1, 1), G.kmajor(wp), G.Epilogue(out=out), engine="umma", m_tiles=mt)
+    torch.cuda.synchronize()
+    _check_timeout(L)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), None, padding=1).permute(0, 2, 3, 1).reshape(-1, cout)
+    _close(out, ref, 6e-3, f"conv tile mt={mt}")

@@ -101,6 +101,18 @@ int psg_groupnorm_bwd(const void* dy, long long ld_dy, const void* x, long long 
                       const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta, float* workspace,
                       int B, int HW, int C, int G, int act, int dtype, int accumulate_dx, int accumulate_params, void* stream);
 
+/* single-pass variants (bf16; the (sample, channel-chunk) slab is staged once in shared memory: 2N / 3N bytes of traffic).
+ * The backward optionally emits sum-over-pixels of dx per (sample, channel) [B, ld_colsum] and per channel [C]: the
+ * gradients of the conv bias and of the broadcast time/text conditioning that produced x (unet.py:116-124).           */
+int psg_groupnorm_fused_ok(int B, int HW, int C, int G, int dtype);
+int psg_groupnorm_fused_plan(int B, int HW, int C, int G, int* out8);
+int psg_groupnorm_fused_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
+                            float* stats, int B, int HW, int C, int G, float eps, int act, void* stream);
+int psg_groupnorm_fused_bwd(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,
+                            const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta,
+                            float* workspace, float* dx_colsum, long long ld_colsum, float* bias_total, int B, int HW, int C, int G,
+                            int act, int accumulate_dx, int accumulate_params, void* stream);
+
 /* ---- attention core  nn.MultiheadAttention(batch_first) softmax(QK^T/sqrt(d))V, src/models/unet.py:160-173,217,235 */
 int psg_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
                  long long ldo, float* lse, int B, int H, int Lq, int Lk, int hd, float scale, int dtype,

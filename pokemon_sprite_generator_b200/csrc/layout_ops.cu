@@ -82,7 +82,17 @@ __global__ void colsum_partial_kernel(const T* __restrict__ x, long long ld, int
   if (row < rows) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const T* base = x + ((long long)g * rows_per_group) * ld + v * 8;
-    for (int r = r0 + row; r < r1; r += rows) {
+    int r = r0 + row;
+    for (; r + 3 * rows < r1; r += 4 * rows) {      // four independent 16-byte loads in flight per thread
+      Vec8<T> t0, t1, t2, t3;
+      t0.load(base + (long long)r * ld);
+      t1.load(base + (long long)(r + rows) * ld);
+      t2.load(base + (long long)(r + 2 * rows) * ld);
+      t3.load(base + (long long)(r + 3 * rows) * ld);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (t0.v[j] + t1.v[j]) + (t2.v[j] + t3.v[j]);
+    }
+    for (; r < r1; r += rows) {
       Vec8<T> t;
       t.load(base + (long long)r * ld);
 #pragma unroll
@@ -437,6 +447,17 @@ int psg_colsum_slices(int groups, int rows_per_group) {
 int psg_colsum(const void* x, long long ld, int groups, int rows_per_group, int C, float* out_groups, long long ld_groups,
                int acc_groups, float* out_total, int acc_total, float scale, float* workspace, int dtype, void* stream) {
   PSG_CHECK_ARG(x && workspace, "psg_colsum: null pointer");
+  if (C > 4096 && C % 8 == 0) {
+    // wide matrices (the [B, sum Cout] conditioning gradient): column chunks of 4096, same workspace (stream-ordered)
+    const size_t esz = dtype == PSG_DTYPE_BF16 ? 2 : 4;
+    for (int c0 = 0; c0 < C; c0 += 4096) {
+      const int cw = C - c0 < 4096 ? C - c0 : 4096;
+      int rc = psg_colsum((const char*)x + (size_t)c0 * esz, ld, groups, rows_per_group, cw, out_groups ? out_groups + c0 : nullptr,
+                          ld_groups, acc_groups, out_total ? out_total + c0 : nullptr, acc_total, scale, workspace, dtype, stream);
+      if (rc) return rc;
+    }
+    return PSG_OK;
+  }
   PSG_CHECK_ARG(groups > 0 && rows_per_group > 0 && C > 0 && C % 8 == 0 && C / 8 <= 512 && ld % 8 == 0, "psg_colsum: bad sizes (C=%d)", C);
   PSG_CHECK_ARG(groups <= 65535, "psg_colsum: too many groups");
   const int S = psg_colsum_slices(groups, rows_per_group);

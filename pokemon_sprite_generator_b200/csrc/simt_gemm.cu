@@ -63,7 +63,8 @@ __device__ __forceinline__ float fetch(const OperandView<T>& o, long long i, lon
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) simt_gemm_kernel(OperandView<T> A, OperandView<T> B, long long M, long long N,
-                                                            long long K, PsgEpilogue epi) {
+                                                            long long K, PsgEpilogue epi, long long k_per_split,
+                                                            long long split_stride) {
   __shared__ float sA[TK][TM + 4];
   __shared__ float sB[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -79,7 +80,15 @@ __global__ void __launch_bounds__(kThreads) simt_gemm_kernel(OperandView<T> A, O
   const bool a_kfast = (A.mode == PSG_OP_KMAJOR || A.mode == PSG_OP_IM2COL || A.mode == PSG_OP_DGRAD);
   const bool b_kfast = (B.mode == PSG_OP_KMAJOR || B.mode == PSG_OP_IM2COL || B.mode == PSG_OP_DGRAD);
 
-  for (long long k0 = 0; k0 < K; k0 += TK) {
+  // split-K: blockIdx.z owns k in [kbeg, kend) and writes its own fp32 partial [M, ldc] at out + z * split_stride
+  const long long kbeg = (long long)blockIdx.z * k_per_split;
+  const long long kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+  if (gridDim.z > 1) {
+    A.K = kend;
+    B.K = kend;
+    epi.out = reinterpret_cast<float*>(epi.out) + (long long)blockIdx.z * split_stride;
+  }
+  for (long long k0 = kbeg; k0 < kend; k0 += TK) {
 #pragma unroll
     for (int e = 0; e < (TM * TK) / kThreads; ++e) {
       int idx = tid + e * kThreads;
@@ -139,19 +148,28 @@ int psg_simt_gemm(const PsgGemmDesc* d, void* stream) {
   using namespace simt;
   PSG_CHECK_ARG(d != nullptr, "psg_simt_gemm: null desc");
   PSG_CHECK_ARG(d->M > 0 && d->N > 0 && d->K >= 0, "psg_simt_gemm: bad sizes M=%lld N=%lld K=%lld", d->M, d->N, d->K);
-  PSG_CHECK_ARG(d->split_k <= 1, "psg_simt_gemm: split-K not supported");
   PSG_CHECK_ARG(d->a.ptr && d->b.ptr && d->epi.out, "psg_simt_gemm: null pointer");
   long long gy = (d->M + TM - 1) / TM, gx = (d->N + TN - 1) / TN;
   PSG_CHECK_ARG(gy <= 65535, "psg_simt_gemm: M too large for grid.y");
-  dim3 grid((unsigned)gx, (unsigned)gy);
+  // split-K (split_k > 1): fp32 partials [split][M][ldc] at epi.out, to be folded by psg_sum_partials
+  int split = d->split_k > 1 ? d->split_k : 1;
+  long long k_per_split = d->K;
+  if (split > 1) {
+    PSG_CHECK_ARG(d->epi.out_dtype == PSG_DTYPE_F32 && !d->epi.accumulate && !d->epi.residual, "psg_simt_gemm: split-K needs a plain fp32 epilogue");
+    k_per_split = ((d->K + split - 1) / split + TK - 1) / TK * TK;
+    split = (int)((d->K + k_per_split - 1) / k_per_split);
+    PSG_CHECK_ARG(split == d->split_k, "psg_simt_gemm: split_k=%d does not divide K=%lld into TK-aligned slices", d->split_k, d->K);
+  }
+  const long long split_stride = d->M * d->epi.ldc;
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)split);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->in_dtype == PSG_DTYPE_F32) {
     simt_gemm_kernel<float><<<grid, kThreads, 0, s>>>(make_view<float>(d->a, d->M, d->K), make_view<float>(d->b, d->N, d->K),
-                                                     d->M, d->N, d->K, d->epi);
+                                                     d->M, d->N, d->K, d->epi, k_per_split, split_stride);
   } else if (d->in_dtype == PSG_DTYPE_BF16) {
     simt_gemm_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(make_view<__nv_bfloat16>(d->a, d->M, d->K),
                                                              make_view<__nv_bfloat16>(d->b, d->N, d->K), d->M, d->N, d->K,
-                                                             d->epi);
+                                                             d->epi, k_per_split, split_stride);
   } else {
     psg_set_error("psg_simt_gemm: bad in_dtype %d", d->in_dtype);
     return PSG_ERR_INVALID;

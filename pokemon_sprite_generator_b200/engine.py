@@ -29,7 +29,7 @@ ALIGN = 64  # elements; keeps every parameter 256-byte aligned inside the flat b
 class Act:
     """A token-major activation [M = B*H*W, C] (possibly a channel slice of a wider buffer) plus its gradient."""
 
-    __slots__ = ("t", "B", "H", "W", "grad", "parent", "col", "pre", "pre_act", "drop")
+    __slots__ = ("t", "B", "H", "W", "grad", "parent", "col", "pre", "pre_act", "drop", "sink", "colsum_done")
 
     def __init__(self, t: torch.Tensor, B: int, H: int, W: int, parent: "Act" = None, col: int = 0):
         self.t, self.B, self.H, self.W = t, B, H, W
@@ -38,6 +38,8 @@ class Act:
         self.pre: Optional[torch.Tensor] = None   # saved pre-activation when this is act(pre) [+dropout]
         self.pre_act = L.ACT_NONE
         self.drop = None                          # (seed, p) of an epilogue dropout applied after the activation
+        self.sink = None                          # (rowbias Act, bias grad) fed by the column sums of this conv output's gradient
+        self.colsum_done = False                  # ... already produced by the consumer's fused GroupNorm backward
 
     @property
     def M(self) -> int:
@@ -98,6 +100,21 @@ class LinW:
         return w, b, gw, gb
 
 
+class FlatLinW(LinW):
+    """A Linear whose weight [N, K] (and bias [N]) is a contiguous run of several parameters inside the flat buffers:
+    the 17 ResBlock time_proj (resp. text_proj) layers evaluated as ONE GEMM (reference unet.py:83,86,119-124)."""
+
+    def __init__(self, first_w: nn.Parameter, first_b: nn.Parameter, n: int, k: int):
+        super().__init__(first_w, first_b)
+        self.n, self.k = n, k
+
+    def views(self, store: "ParamStore"):
+        ow, ob = store.offset_of(self.weight), store.offset_of(self.bias)
+        n, k = self.n, self.k
+        return (store.flat[ow:ow + n * k].view(n, k), store.flat[ob:ob + n], store.grads[ow:ow + n * k].view(n, k),
+                store.grads[ob:ob + n])
+
+
 class NormW:
     def __init__(self, gn: nn.GroupNorm):
         self.mod, self.groups, self.eps = gn, gn.num_groups, gn.eps
@@ -106,15 +123,23 @@ class NormW:
 class ParamStore:
     """Flat fp32 parameter / gradient buffers; every nn.Parameter's .data is a view into `flat`."""
 
-    def __init__(self, module: nn.Module):
+    def __init__(self, module: nn.Module, front: Optional[List[nn.Parameter]] = None):
+        """`front`: parameters laid out first, contiguously and in the given order (the ResBlock conditioning
+        projections, so that all time_proj / text_proj weights form one [sum C, K] matrix each); every other parameter
+        follows in registration order."""
         self.module = module
-        self.named = list(module.named_parameters())
+        named = list(module.named_parameters())
+        name_of = {id(p): n for n, p in named}
+        front = list(front or [])
+        front_ids = {id(p) for p in front}
+        self.named = [(name_of[id(p)], p) for p in front] + [(n, p) for n, p in named if id(p) not in front_ids]
         self.offsets = {}
         off = 0
         for name, p in self.named:
             self.offsets[name] = off
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.total = off
+        self._name_of = name_of
         self.flat: Optional[torch.Tensor] = None
         self.grads: Optional[torch.Tensor] = None
         self._by_id = {}
@@ -158,6 +183,9 @@ class ParamStore:
     def grad_of(self, p: nn.Parameter) -> torch.Tensor:
         return self._by_id[id(p)]
 
+    def offset_of(self, p: nn.Parameter) -> int:
+        return self.offsets[self._name_of[id(p)]]
+
     def grad_views(self) -> List[torch.Tensor]:
         return [self._by_id[id(p)] for _, p in self.named]
 
@@ -173,7 +201,6 @@ class UNetEngine:
         self.unet = unet
         self.dtype = compute_dtype
         self.bf16 = compute_dtype == torch.bfloat16
-        self.store = ParamStore(unet)
         self._packed_version = None
         self._packed_generation = None
         self._build_descriptors()
@@ -200,10 +227,15 @@ class UNetEngine:
             self.lins.append(l)
             return l
 
+        res_blocks = []
+
         def res(rb):
-            d = {"norm1": NormW(rb.norm1), "conv1": conv(rb.conv1), "time": lin(rb.time_proj.weight, rb.time_proj.bias),
-                 "text": lin(rb.text_proj.weight, rb.text_proj.bias), "norm2": NormW(rb.norm2), "conv2": conv(rb.conv2),
-                 "skip": None, "cin": rb.in_channels, "cout": rb.out_channels}
+            # time_proj / text_proj of all ResBlocks are evaluated up front as two GEMMs over their concatenated weights
+            # (FlatLinW); each block's conditioning is a column slice [cond_off, cond_off + cout) of that result.
+            d = {"norm1": NormW(rb.norm1), "conv1": conv(rb.conv1), "norm2": NormW(rb.norm2), "conv2": conv(rb.conv2),
+                 "skip": None, "cin": rb.in_channels, "cout": rb.out_channels,
+                 "cond_off": sum(r.out_channels for r in res_blocks)}
+            res_blocks.append(rb)
             if isinstance(rb.skip_conv, nn.Conv2d):
                 sk = rb.skip_conv
                 d["skip"] = lin(sk.weight, sk.bias)      # 1x1 conv == linear over tokens ([Cout, Cin, 1, 1] viewed [Cout, Cin])
@@ -232,6 +264,16 @@ class UNetEngine:
         self.d_up = {l: conv(getattr(u, f"upsample{l}")[1]) for l in (3, 2, 1)}
         self.d_final_norm = NormW(u.final_conv[0])
         self.d_final = conv(u.final_conv[2])
+        # flat layout: [time_proj weights | text_proj weights | time_proj biases | text_proj biases | everything else]
+        front = ([rb.time_proj.weight for rb in res_blocks] + [rb.text_proj.weight for rb in res_blocks] +
+                 [rb.time_proj.bias for rb in res_blocks] + [rb.text_proj.bias for rb in res_blocks])
+        for p in front:
+            assert p.numel() % ALIGN == 0, "conditioning projections must tile the flat buffer without padding"
+        self.store = ParamStore(u, front=front)
+        self.cond_width = sum(rb.out_channels for rb in res_blocks)
+        rb0 = res_blocks[0]
+        self.d_cond_time = FlatLinW(rb0.time_proj.weight, rb0.time_proj.bias, self.cond_width, rb0.time_proj.in_features)
+        self.d_cond_text = FlatLinW(rb0.text_proj.weight, rb0.text_proj.bias, self.cond_width, rb0.text_proj.in_features)
 
     # ------------------------------------------------------------------------------------------------------------
     # weights
@@ -330,15 +372,27 @@ class UNetEngine:
                          residual=residual.t if residual is not None else None)
         G.run_gemm(a, G.kmajor(cw.wp), epi, engine=eng)
         if self.taping:
+            if rowbias is not None and cw.cout_p == cw.cout:
+                out.sink = (rowbias, cw)
             self.tape.append(lambda: self._conv_bwd(x, cw, out, rowbias, residual, x_needs_grad, eng))
         return out
+
+    def _rowbias_target(self, rowbias: Act):
+        if rowbias.parent is not None:      # a column slice of the all-blocks conditioning buffer: written once
+            par = rowbias.parent
+            if par.grad is None:
+                par.grad = torch.empty(par.M, par.C, dtype=par.t.dtype, device=par.t.device)
+            return rowbias.g(), False
+        return self._grad_target(rowbias)
 
     def _conv_bwd(self, x: Act, cw: ConvW, out: Act, rowbias: Act, residual: Act, x_needs_grad: bool, eng: str):
         dy = out.g()
         gb = self.store.grad_of(cw.mod.bias)
         dy_real = dy[:, :cw.cout] if cw.cout_p != cw.cout else dy
-        if rowbias is not None:
-            tgt, acc = self._grad_target(rowbias)
+        if out.colsum_done:
+            pass        # bias / conditioning gradients came out of the consumer GroupNorm's backward
+        elif rowbias is not None:
+            tgt, acc = self._rowbias_target(rowbias)
             K.colsum(dy_real, x.B, tgt, gb, acc_groups=acc)
         else:
             K.colsum(dy_real, 1, None, gb)
@@ -453,6 +507,20 @@ class UNetEngine:
             return
         tgt, acc = self._grad_target(x) if x.parent is None else (x.g(), False)
         bop = G.mnmajor(w2) if fp32 else G.kmajor(lw.wt)
+        if eng == "simt" and x.pre is None and scale == 1.0 and tgt.dtype == torch.float32 and tgt.is_contiguous() \
+                and N >= 2048 and x.M * Kd <= 256 * 512:
+            # skinny dgrad with a long reduction (the all-blocks conditioning projection): split-K over the CUDA-core engine
+            split = min(32, N // 512)
+            while True:     # fixed point of the engine's own slicing rule (16-aligned k slices)
+                per = -(-(-(-N // split)) // 16) * 16
+                eff = -(-N // per)
+                if eff == split:
+                    break
+                split = eff
+            part = K.workspace(self.device, split * x.M * Kd, "wgrad").narrow(0, 0, split * x.M * Kd).view(split, x.M, Kd)
+            G.run_gemm(G.kmajor(dy), bop, G.Epilogue(out=part[0]), engine=eng, split_k=split)
+            K.sum_partials(part, split, x.M * Kd, tgt, accumulate=acc)
+            return
         self._dgrad_gemm(G.kmajor(dy), bop, tgt, tgt if acc else None, x, eng, alpha=scale)
 
     # ---- GroupNorm ---------------------------------------------------------------------------------------------
@@ -461,12 +529,30 @@ class UNetEngine:
             out = self._new(x.M, x.C, x.B, x.H, x.W)
         stats = torch.empty(x.B, nw.groups, 2, dtype=torch.float32, device=self.device)
         gamma, beta = nw.mod.weight.data, nw.mod.bias.data
-        K.groupnorm_fwd(x.t, out.t, gamma, beta, stats, x.B, nw.groups, nw.eps, silu)
+        fused = K.groupnorm_fused_ok(x.B, x.H * x.W, x.C, nw.groups, x.t.dtype)
+        if fused:
+            K.groupnorm_fused_fwd(x.t, out.t, gamma, beta, stats, x.B, nw.groups, nw.eps, silu)
+        else:
+            K.groupnorm_fwd(x.t, out.t, gamma, beta, stats, x.B, nw.groups, nw.eps, silu)
         if self.taping:
             def bwd():
                 tgt, acc = self._grad_target(x)
-                K.groupnorm_bwd(out.g(), x.t, tgt, gamma, beta, stats, self.store.grad_of(nw.mod.weight),
-                                self.store.grad_of(nw.mod.bias), x.B, nw.groups, silu, acc)
+                gw, gb = self.store.grad_of(nw.mod.weight), self.store.grad_of(nw.mod.bias)
+                if not fused:
+                    K.groupnorm_bwd(out.g(), x.t, tgt, gamma, beta, stats, gw, gb, x.B, nw.groups, silu, acc)
+                    return
+                colsum = total = None
+                if x.sink is not None and not acc:
+                    # x is a conv output consumed only here: its gradient's column sums are the conv's bias gradient and
+                    # the gradient of its broadcast conditioning; the kernel has them for free
+                    rowbias, cw = x.sink
+                    colsum, racc = self._rowbias_target(rowbias)
+                    if racc:
+                        colsum = None
+                    else:
+                        total = self.store.grad_of(cw.mod.bias)
+                        x.colsum_done = True
+                K.groupnorm_fused_bwd(out.g(), x.t, tgt, gamma, beta, stats, gw, gb, x.B, nw.groups, silu, acc, colsum, total)
             self.tape.append(bwd)
         return out
 
@@ -520,15 +606,15 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------------------------
     # blocks
     # ------------------------------------------------------------------------------------------------------------
-    def _cond(self, d, temb: Act, pooled: Act) -> Act:
-        """time_proj(time_emb) + text_proj(text_pooled): the [B, Cout] broadcast bias of conv1 (unet.py:119-124)."""
-        cond = self.linear(temb, d["time"])
-        self.linear(pooled, d["text"], into=cond, x_needs_grad=False)
+    def _cond_all(self, temb: Act, pooled: Act) -> Act:
+        """time_proj(time_emb) + text_proj(text_pooled) of every ResBlock at once: [B, sum Cout] (unet.py:119-124)."""
+        cond = self.linear(temb, self.d_cond_time)
+        self.linear(pooled, self.d_cond_text, into=cond, x_needs_grad=False)
         return cond
 
-    def _res_block(self, d, x: Act, temb: Act, pooled: Act, out: Act = None) -> Act:
+    def _res_block(self, d, x: Act, cond_all: Act, out: Act = None) -> Act:
         a1 = self.groupnorm(x, d["norm1"], silu=True)
-        cond = self._cond(d, temb, pooled)
+        cond = cond_all.slice(d["cond_off"], d["cout"])     # the [B, Cout] broadcast bias of conv1
         h1 = self.conv(a1, d["conv1"], rowbias=cond)
         a2 = self.groupnorm(h1, d["norm2"], silu=True)
         if d["skip"] is None:
@@ -554,10 +640,10 @@ class UNetEngine:
         f = self.linear(x2, d["f1"], act=L.ACT_GELU, drop=(self._seed(site + 2), pf) if train_drop else None)
         return self.linear(f, d["f2"], alpha=0.6, residual=x2, drop=(self._seed(site + 3), pf) if train_drop else None)
 
-    def _block(self, d, x: Act, temb, pooled, text_tok, lt, site, out: Act = None) -> Act:
+    def _block(self, d, x: Act, cond_all, text_tok, lt, site, out: Act = None) -> Act:
         if d["attn"] is None:
-            return self._res_block(d["res"], x, temb, pooled, out=out)
-        h = self._res_block(d["res"], x, temb, pooled)
+            return self._res_block(d["res"], x, cond_all, out=out)
+        h = self._res_block(d["res"], x, cond_all)
         y = self._attn_block(d["attn"], h, text_tok, lt, site)
         if out is not None:   # attention output must land in a concat buffer: one strided copy
             self.copy_into(y, out)
@@ -597,6 +683,7 @@ class UNetEngine:
         temb = self.linear(h, self.d_time[2])
         pooled = Act(torch.empty(B, text.shape[2], dtype=torch.float32, device=dev), B, 1, 1)
         K.mean_pool(text, pooled.t)
+        cond_all = self._cond_all(temb, pooled)
         text_tok = Act(torch.empty(B * lt, text.shape[2], dtype=self.dtype, device=dev), B, lt, 1)
         K.nchw_to_tokens(text.view(B * lt, text.shape[2], 1, 1), text_tok.t)
 
@@ -612,10 +699,10 @@ class UNetEngine:
             if lvl > 0:
                 x = self.conv(x, self.d_down[lvl])
             for blk in self.d_enc[lvl]:
-                x = self._block(blk, x, temb, pooled, text_tok, lt, site)
+                x = self._block(blk, x, cond_all, text_tok, lt, site)
                 site += 4
             skips.append(x)
-        x = self._block(self.d_mid, x, temb, pooled, text_tok, lt, site)
+        x = self._block(self.d_mid, x, cond_all, text_tok, lt, site)
         site += 4
         # ---- decoder: cat([x, skip]) is one [M, 2C] buffer filled by two strided copies ----
         for lvl in (3, 2, 1, 0):
@@ -626,7 +713,7 @@ class UNetEngine:
                 cat = self._new(M, 2 * ch, B, size, size)
                 self.copy_into(x, cat.slice(0, ch))
                 self.copy_into(skip, cat.slice(ch, ch))
-                x = self._block(blk, cat, temb, pooled, text_tok, lt, site)
+                x = self._block(blk, cat, cond_all, text_tok, lt, site)
                 site += 4
             if lvl > 0:
                 x = self.upsample(x, LEVELS[lvl - 1][1])

@@ -146,6 +146,39 @@ def groupnorm_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor, gamma: to
            C.c_int(groups), C.c_int(int(silu)), C.c_int(L.dt(x)), C.c_int(int(accumulate_dx)), C.c_int(0), L.stream_ptr())
 
 
+_gn_fused_cache = {}
+
+
+def groupnorm_fused_ok(b: int, hw: int, c: int, groups: int, dtype: torch.dtype) -> bool:
+    """True when the single-pass (slab in shared memory) GroupNorm kernels handle this problem."""
+    key = (b, hw, c, groups, dtype)
+    ok = _gn_fused_cache.get(key)
+    if ok is None:
+        ok = dtype == torch.bfloat16 and bool(L.load().psg_groupnorm_fused_ok(C.c_int(b), C.c_int(hw), C.c_int(c), C.c_int(groups),
+                                                                              C.c_int(L.DT_BF16)))
+        _gn_fused_cache[key] = ok
+    return ok
+
+
+def groupnorm_fused_fwd(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, stats: torch.Tensor, b: int,
+                        groups: int, eps: float, silu: bool) -> None:
+    rows, c = x.shape
+    L.call("psg_groupnorm_fused_fwd", L.ptr(x), C.c_longlong(_ld(x)), L.ptr(y), C.c_longlong(_ld(y)), L.ptr(gamma), L.ptr(beta),
+           L.ptr(stats), C.c_int(b), C.c_int(rows // b), C.c_int(c), C.c_int(groups), C.c_float(eps), C.c_int(int(silu)), L.stream_ptr())
+
+
+def groupnorm_fused_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                        stats: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, b: int, groups: int, silu: bool,
+                        accumulate_dx: bool, dx_colsum: torch.Tensor | None = None, bias_total: torch.Tensor | None = None) -> None:
+    """dx_colsum [b, C] (row pitch free) / bias_total [C]: optional sums over pixels of dx per (sample, channel) / per channel."""
+    rows, c = x.shape
+    ws = workspace(x.device, b * c * 3, "gn")
+    L.call("psg_groupnorm_fused_bwd", L.ptr(dy), C.c_longlong(_ld(dy)), L.ptr(x), C.c_longlong(_ld(x)), L.ptr(dx), C.c_longlong(_ld(dx)),
+           L.ptr(gamma), L.ptr(beta), L.ptr(stats), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), L.ptr(dx_colsum),
+           C.c_longlong(dx_colsum.stride(0) if dx_colsum is not None else 0), L.ptr(bias_total), C.c_int(b), C.c_int(rows // b),
+           C.c_int(c), C.c_int(groups), C.c_int(int(silu)), C.c_int(int(accumulate_dx)), C.c_int(0), L.stream_ptr())
+
+
 # ---- attention ----------------------------------------------------------------------------------------------
 def attn_fwd(q, k, v, o, lse, b: int, heads: int, lq: int, lk: int, hd: int, drop_seed: int = 0, drop_p: float = 0.0) -> None:
     L.call("psg_attn_fwd", L.ptr(q), C.c_longlong(_ld(q)), L.ptr(k), C.c_longlong(_ld(k)), L.ptr(v), C.c_longlong(_ld(v)), L.ptr(o),

@@ -59,6 +59,60 @@ def test_groupnorm_fwd_bwd(cuda_device, dtype, B, HW, C, G, silu, eps):
     assert torch.all(wide[:, :C] == 1)
 
 
+@pytest.mark.parametrize("B,HW,C,G,silu,eps", [(2, 729, 320, 32, True, 1e-5), (3, 729, 640, 32, True, 1e-5), (3, 196, 640, 32, False, 1e-6),
+                                               (2, 196, 1280, 32, True, 1e-5), (2, 49, 2560, 32, True, 1e-5), (5, 49, 1280, 32, False, 1e-6),
+                                               (5, 16, 1280, 32, False, 1e-6), (7, 16, 2560, 32, True, 1e-5), (1, 729, 64, 32, True, 1e-5),
+                                               (300, 16, 640, 32, True, 1e-5), (2, 100, 96, 8, True, 1e-5)])
+def test_groupnorm_fused_fwd_bwd(cuda_device, B, HW, C, G, silu, eps):
+    """Single-pass bf16 GroupNorm(+SiLU) forward/backward, including the free column sums of dx, vs torch fp32."""
+    K = _ops()
+    dtype = torch.bfloat16
+    assert K.groupnorm_fused_ok(B, HW, C, G, dtype)
+    g = torch.Generator(device="cuda").manual_seed(B * HW + C + 1)
+    x = (torch.randn(B * HW, C, device="cuda", generator=g) * 1.5 + 0.3).to(dtype)
+    gamma = torch.randn(C, device="cuda", generator=g) * 0.5 + 1.0
+    beta = torch.randn(C, device="cuda", generator=g) * 0.2
+    dy = torch.randn(B * HW, C, device="cuda", generator=g).to(dtype)
+    wide_y = torch.zeros(B * HW, C + 64, device="cuda", dtype=dtype)
+    y = wide_y[:, 64:]
+    stats = torch.empty(B, G, 2, device="cuda")
+    K.groupnorm_fused_fwd(x, y, gamma, beta, stats, B, G, eps, silu)
+    xr = x.float().view(B, HW, C).permute(0, 2, 1).contiguous().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.group_norm(xr, G, gr, br, eps)
+    if silu:
+        yr = F.silu(yr)
+    yr.backward(dy.float().view(B, HW, C).permute(0, 2, 1))
+    _cmp(y, yr.detach().permute(0, 2, 1).reshape(B * HW, C), dtype, "gnf fwd")
+    assert torch.all(wide_y[:, :64] == 0)
+    xg = xr.view(B, G, -1)
+    _cmp(stats[..., 0], xg.mean(-1).detach(), torch.float32, "gnf mean", 50.0)
+    _cmp(stats[..., 1], (xg.var(-1, unbiased=False) + eps).rsqrt().detach(), torch.float32, "gnf rstd", 50.0)
+    dx = torch.empty_like(x)
+    dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    cs_wide = torch.full((B, 2 * C), 7.0, device="cuda")
+    total = torch.empty(C, device="cuda")
+    K.groupnorm_fused_bwd(dy, x, dx, gamma, beta, stats, dgamma, dbeta, B, G, silu, False, cs_wide[:, C:], total)
+    dxr = xr.grad.permute(0, 2, 1).reshape(B * HW, C)
+    _cmp(dx, dxr, dtype, "gnf dx", 2.0)
+    _cmp(dgamma, gr.grad, dtype, "gnf dgamma", 4.0)
+    _cmp(dbeta, br.grad, dtype, "gnf dbeta", 4.0)
+    cs_ref = dxr.view(B, HW, C).sum(1)
+    scale = max(cs_ref.abs().max().item(), dxr.abs().max().item() * math.sqrt(HW))
+    assert (cs_wide[:, C:] - cs_ref).abs().max().item() <= 2e-2 * scale, "gnf colsum"
+    assert torch.all(cs_wide[:, :C] == 7.0)
+    assert (total - cs_ref.sum(0)).abs().max().item() <= 2e-2 * scale * math.sqrt(B), "gnf colsum total"
+    # accumulate into an existing dx, on a strided (concat-slice) view
+    wide = torch.ones(B * HW, 2 * C, device="cuda", dtype=dtype)
+    K.groupnorm_fused_bwd(dy, x, wide[:, C:], gamma, beta, stats, dgamma, dbeta, B, G, silu, True)
+    _cmp(wide[:, C:], 1.0 + dxr, dtype, "gnf dx acc", 2.0)
+    assert torch.all(wide[:, :C] == 1)
+    # run-to-run determinism (fixed-order reductions)
+    dx2, dg2, db2 = torch.empty_like(x), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    K.groupnorm_fused_bwd(dy, x, dx2, gamma, beta, stats, dg2, db2, B, G, silu, False)
+    assert torch.equal(dx2, dx) and torch.equal(dg2, dgamma) and torch.equal(db2, dbeta)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,Lq,Lk,hd,p", [(2, 8, 196, 196, 80, 0.0), (2, 4, 196, 32, 160, 0.0), (3, 8, 49, 49, 160, 0.0), (2, 4, 16, 7, 320, 0.0),
                                             (1, 8, 196, 256, 80, 0.0), (2, 8, 49, 32, 160, 0.25)])

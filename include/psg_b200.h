@@ -14,6 +14,8 @@
 #ifndef PSG_B200_H
 #define PSG_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -68,7 +70,7 @@ typedef struct PsgGemmDesc {
   PsgOperand a, b;         /* C[m,n] = epilogue(sum_k A(m,k) * B(n,k)) */
   long long M, N, K;
   int in_dtype;
-  int split_k;             /* >1: fp32 partial planes [split][M][ldc] */
+  int split_k;             /* SIMT engine only: >1 = fp32 partial planes [split][M][ldc] (the tcgen05 engine is stream-K) */
   PsgEpilogue epi;
 } PsgGemmDesc;
 
@@ -77,6 +79,10 @@ typedef struct PsgGemmDesc {
 int psg_umma_gemm(const PsgGemmDesc* desc, int block_n, void* stream);
 int psg_umma_gemm_ex(const PsgGemmDesc* desc, int block_n, int m_tiles, void* stream);
 int psg_umma_plan(const PsgGemmDesc* desc, int* block_n, int* m_tiles);
+/* Stream-K scheduling: tiles whose k-range is shared between CTAs exchange fp32 partial accumulators through a
+ * caller-owned workspace (psg_umma_workspace_bytes() bytes, 256B aligned, first 1 KiB zeroed), registered once. */
+size_t psg_umma_workspace_bytes(void);
+int psg_umma_set_workspace(void* workspace, size_t bytes);
 /* CUDA-core fp32-accumulate engine (fp32 parity mode, edge shapes, general-stride dgrad gather). */
 int psg_simt_gemm(const PsgGemmDesc* desc, void* stream);
 

@@ -8,6 +8,14 @@
 // kMode 0 ("TN"):  A K-major (tiled matrix or im2col pixels), B K-major matrix.   fprop / dgrad / linears.
 // kMode 1 ("NT"):  A MN-major matrix, B MN-major (tiled matrix or im2col pixels). wgrad (reduction over rows).
 //
+// Scheduling is "data-parallel + stream-K": whole waves of tiles are dealt round-robin to the persistent CTAs; the
+// remainder tiles (all tiles, when there are fewer tiles than SMs) form a stream-K region whose (tile, k-block)
+// iteration space is cut into one contiguous range per CTA, done BEFORE the CTA's whole tiles -- every SM gets the same
+// number of k-blocks (no wave quantisation, no split-K workspace pass).  A tile whose k-range is shared is finished by
+// the CTA that owns its FIRST k-block; the other CTAs reach their share of it first thing, park their raw fp32
+// accumulators in a per-CTA workspace slot and raise a flag.  The owner adds the slots in CTA order, so results are
+// run-to-run deterministic.
+//
 // Replaces the ATen calls behind nn.Conv2d / nn.Linear / MHA projections on the reference hot path
 // (src/models/unet.py:80,90,96,160-187,325-399); SURVEY.md §2.1 K1-K3, K6-K9.
 #include "gemm_desc.h"
@@ -26,13 +34,17 @@ struct alignas(64) KernelParams {
   CUtensorMap tm_a;
   CUtensorMap tm_b;
   int M, N;
-  int num_kb, kb_per_split;
-  int num_m_tiles, num_n_tiles, splits;
+  int num_kb;
+  int num_m_tiles, num_n_tiles;
+  int num_tiles;             // num_m_tiles * num_n_tiles
+  int sk_tiles, sk_ctas;     // stream-K region: tiles [0, sk_tiles) shared by CTAs [0, sk_ctas)
+  long long sk_units;        // sk_tiles * num_kb
+  float* sk_slots;           // [gridDim.x][kMT*128*kBlockN] fp32 partial accumulators of shared tiles
+  int* sk_flags;             // [gridDim.x] 1 = slot holds a partial that has not been consumed yet
   // mode 0, A im2col
   int a_im2col, cblks, ksize, conv_stride, pad, flip, P, Q;
   // mode 1, B im2col (wgrad): columns are (tap, cin)
   int b_im2col, cin, tiles_per_tap;
-  long long split_stride;
   PsgEpilogue epi;
 };
 
@@ -140,21 +152,118 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogue for one thread's 32 consecutive columns of one row
+// Epilogue for one warp's 32-row x 32-column chunk of the accumulator.
+//
+// tcgen05.ld hands every thread ONE ROW (32 consecutive columns).  Touching global memory in that shape makes each
+// warp-level 16-byte access hit 32 different rows (32 L2 requests of 16 bytes): the epilogue, not the tensor pipe, was
+// what bounded the short-K GEMMs.  So every tensor the epilogue reads or writes goes through a per-warp staging tile in
+// shared memory (XOR-swizzled, conflict-free both ways): global accesses are issued "piece-major" -- consecutive lanes
+// take consecutive 16-byte pieces of a row, 64 or 128 contiguous bytes per row and instruction -- and each thread
+// picks up / drops off its own row on the shared-memory side.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint32_t (&acc)[32], long long m, long long n0,
-                                               int nvalid, long long N, float* out_override) {
-  // fast path: whole chunk valid and 16B-aligned everywhere
+template <int kElemBytes>      // 2 (bf16) or 4 (fp32): a 32 x 32 tile has rows of 64 or 128 bytes
+struct WarpTile {
+  static constexpr int kCpr = 32 * kElemBytes / 16;     // 16-byte pieces per row: 4 or 8
+  static constexpr int kPerLane = kCpr;                 // pieces each lane moves: 32 rows * kCpr / 32 lanes
+  __device__ static __forceinline__ uint32_t off(int r, int c) {
+    return (uint32_t)(r * (kCpr * 16) + ((kCpr == 8 ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3))) << 4));
+  }
+  // global tile (row pitch ld_bytes) -> staging; rows >= rows_valid are skipped
+  __device__ static __forceinline__ void load(uint8_t* stage, const uint8_t* g, long long ld_bytes, int rows_valid, int lane) {
+    uint4 v[kPerLane];
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int pc = lane + 32 * i, r = pc / kCpr, c = pc % kCpr;
+      v[i] = (r < rows_valid) ? *reinterpret_cast<const uint4*>(g + (long long)r * ld_bytes + c * 16) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int pc = lane + 32 * i, r = pc / kCpr, c = pc % kCpr;
+      *reinterpret_cast<uint4*>(stage + off(r, c)) = v[i];
+    }
+  }
+  __device__ static __forceinline__ void store(const uint8_t* stage, uint8_t* g, long long ld_bytes, int rows_valid, int lane) {
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int pc = lane + 32 * i, r = pc / kCpr, c = pc % kCpr;
+      if (r < rows_valid) *reinterpret_cast<uint4*>(g + (long long)r * ld_bytes + c * 16) = *reinterpret_cast<const uint4*>(stage + off(r, c));
+    }
+  }
+};
+
+// staging <-> this thread's row, as 32 floats
+__device__ __forceinline__ void row_get(const uint8_t* stage, int dtype, int lane, float (&a)[32]) {
+  if (dtype == PSG_DTYPE_BF16) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 r = *reinterpret_cast<const uint4*>(stage + WarpTile<2>::off(lane, c));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); a[8 * c + 2 * i] = f.x; a[8 * c + 2 * i + 1] = f.y; }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 r = *reinterpret_cast<const float4*>(stage + WarpTile<4>::off(lane, c));
+      a[4 * c] = r.x; a[4 * c + 1] = r.y; a[4 * c + 2] = r.z; a[4 * c + 3] = r.w;
+    }
+  }
+}
+__device__ __forceinline__ void row_put(uint8_t* stage, int dtype, int lane, const float (&v)[32]) {
+  if (dtype == PSG_DTYPE_BF16) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 r;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+      *reinterpret_cast<uint4*>(stage + WarpTile<2>::off(lane, c)) = r;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<float4*>(stage + WarpTile<4>::off(lane, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  }
+}
+// whole-warp: fetch the [32 x 32] tile at (m_base, n0) of a row-pitched tensor and hand every thread its row
+__device__ __forceinline__ void tile_in(uint8_t* stage, const void* base, long long ld, int dtype, long long m_base, long long n0,
+                                        int rows_valid, int lane, float (&a)[32]) {
+  __syncwarp();
+  if (dtype == PSG_DTYPE_BF16)
+    WarpTile<2>::load(stage, reinterpret_cast<const uint8_t*>(base) + (m_base * ld + n0) * 2, ld * 2, rows_valid, lane);
+  else
+    WarpTile<4>::load(stage, reinterpret_cast<const uint8_t*>(base) + (m_base * ld + n0) * 4, ld * 4, rows_valid, lane);
+  __syncwarp();
+  row_get(stage, dtype, lane, a);
+}
+__device__ __forceinline__ void tile_out(uint8_t* stage, void* base, long long ld, int dtype, long long m_base, long long n0,
+                                         int rows_valid, int lane, const float (&v)[32]) {
+  __syncwarp();
+  row_put(stage, dtype, lane, v);
+  __syncwarp();
+  if (dtype == PSG_DTYPE_BF16)
+    WarpTile<2>::store(stage, reinterpret_cast<uint8_t*>(base) + (m_base * ld + n0) * 2, ld * 2, rows_valid, lane);
+  else
+    WarpTile<4>::store(stage, reinterpret_cast<uint8_t*>(base) + (m_base * ld + n0) * 4, ld * 4, rows_valid, lane);
+}
+
+// Called by the whole warp (rows m_base .. m_base+31, this thread's row m = m_base + lane; rows >= M are dead).
+__device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint32_t (&acc)[32], long long m_base, int lane,
+                                               long long M, long long n0, int nvalid, long long N, uint8_t* stage) {
+  const long long m = m_base + lane;
+  const int rows_valid = (M - m_base) < 32 ? (int)(M - m_base) : 32;
+  // fast path: whole chunk valid and 16B-aligned everywhere (warp-uniform condition)
   const bool vec = (nvalid == 32) && ((n0 & 7) == 0) && ((e.ldc & 7) == 0) && ((e.ldr & 7) == 0) && ((e.ld_aux & 7) == 0) &&
                    ((e.ld_rowbias & 3) == 0);
   if (!vec) {
-    PsgEpilogue t = e;
-    if (out_override) t.out = out_override;
+    if (m < M) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) psg_epilogue_scalar(t, __uint_as_float(acc[j]), m, n0 + j, N);
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) psg_epilogue_scalar(e, __uint_as_float(acc[j]), m, n0 + j, N);
+    }
     return;
   }
+  const bool live = m < M;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
@@ -163,25 +272,12 @@ __device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint3
 #pragma unroll
     for (int j = 0; j < 8; ++j) { float4 b = __ldg(b4 + j); v[4*j] += b.x; v[4*j+1] += b.y; v[4*j+2] += b.z; v[4*j+3] += b.w; }
   }
-  if (e.rowbias) {
+  if (e.rowbias && live) {
     const float4* b4 = reinterpret_cast<const float4*>(e.rowbias + (m / e.rows_per_group) * e.ld_rowbias + n0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { float4 b = __ldg(b4 + j); v[4*j] += b.x; v[4*j+1] += b.y; v[4*j+2] += b.z; v[4*j+3] += b.w; }
   }
-  if (e.aux_out) {
-    if (e.act_dtype == PSG_DTYPE_BF16) {
-      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(e.aux_out) + m * e.ld_aux + n0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { Vec8<__nv_bfloat16> t;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t.v[i] = v[8*j+i];
-        t.store(p + 8*j); }
-    } else {
-      float* p = reinterpret_cast<float*>(e.aux_out) + m * e.ld_aux + n0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(p + 4*j) = make_float4(v[4*j], v[4*j+1], v[4*j+2], v[4*j+3]);
-    }
-  }
+  if (e.aux_out) tile_out(stage, e.aux_out, e.ld_aux, e.act_dtype, m_base, n0, rows_valid, lane, v);
   if (e.act == PSG_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = psg_gelu(v[j]);
@@ -191,17 +287,7 @@ __device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint3
   }
   if (e.aux_in) {
     float a[32];
-    if (e.act_dtype == PSG_DTYPE_BF16) {
-      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + m * e.ld_aux + n0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { Vec8<__nv_bfloat16> t; t.load(p + 8*j);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[8*j+i] = t.v[i]; }
-    } else {
-      const float* p = reinterpret_cast<const float*>(e.aux_in) + m * e.ld_aux + n0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = p[j];
-    }
+    tile_in(stage, e.aux_in, e.ld_aux, e.act_dtype, m_base, n0, rows_valid, lane, a);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       v[j] *= (e.aux_act == PSG_ACT_GELU) ? psg_gelu_grad(a[j]) : (e.aux_act == PSG_ACT_SILU ? psg_silu_grad(a[j]) : 1.f);
@@ -218,36 +304,18 @@ __device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint3
     for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
   }
   if (e.residual) {
-    if (e.act_dtype == PSG_DTYPE_BF16) {
-      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(e.residual) + m * e.ldr + n0;
+    float a[32];
+    tile_in(stage, e.residual, e.ldr, e.act_dtype, m_base, n0, rows_valid, lane, a);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { Vec8<__nv_bfloat16> t; t.load(p + 8*j);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[8*j+i] += t.v[i]; }
-    } else {
-      const float* p = reinterpret_cast<const float*>(e.residual) + m * e.ldr + n0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { float4 r = *reinterpret_cast<const float4*>(p + 4*j); v[4*j] += r.x; v[4*j+1] += r.y; v[4*j+2] += r.z; v[4*j+3] += r.w; }
-    }
+    for (int j = 0; j < 32; ++j) v[j] += a[j];
   }
-  if (e.out_dtype == PSG_DTYPE_BF16) {
-    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(e.out) + m * e.ldc + n0;
+  if (e.out_dtype == PSG_DTYPE_F32 && e.accumulate) {
+    float a[32];
+    tile_in(stage, e.out, e.ldc, PSG_DTYPE_F32, m_base, n0, rows_valid, lane, a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { Vec8<__nv_bfloat16> t;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t.v[i] = v[8*j+i];
-      t.store(p + 8*j); }
-  } else {
-    float* p = (out_override ? out_override : reinterpret_cast<float*>(e.out)) + m * e.ldc + n0;
-    if (e.accumulate) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { float4 o = *reinterpret_cast<float4*>(p + 4*j);
-        *reinterpret_cast<float4*>(p + 4*j) = make_float4(o.x + v[4*j], o.y + v[4*j+1], o.z + v[4*j+2], o.w + v[4*j+3]); }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(p + 4*j) = make_float4(v[4*j], v[4*j+1], v[4*j+2], v[4*j+3]);
-    }
+    for (int j = 0; j < 32; ++j) v[j] += a[j];
   }
+  tile_out(stage, e.out, e.ldc, e.out_dtype, m_base, n0, rows_valid, lane, v);
 }
 
 __host__ __device__ constexpr uint32_t tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -262,7 +330,9 @@ struct SmemLayout {
   static constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_BYTES;
   static constexpr int kAcc = (2 * kMT * kBlockN <= 512) ? 2 : 1;          // TMEM accumulator stages
   static constexpr uint32_t TMEM_COLS = tmem_cols_for(kAcc * kMT * kBlockN);
-  static constexpr uint32_t BAR_OFFSET = STAGE_BYTES * kStages;
+  static constexpr uint32_t EPI_OFFSET = STAGE_BYTES * kStages;         // 8 epilogue warps x 4 KiB staging tiles
+  static constexpr uint32_t EPI_BYTES = 8 * 4096;
+  static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * kStages + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
@@ -270,8 +340,57 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Work decomposition.  Stream-K region: unit u = tile * num_kb + kb over tiles [0, sk_tiles); CTA c < sk_ctas owns units
+// [sk_begin(c), sk_begin(c+1)).  Data-parallel region: CTA c then takes tiles sk_tiles + c, sk_tiles + c + gridDim.x, ...
+__device__ __forceinline__ long long sk_begin(long long sk_units, int c, int sk_ctas) {
+  return c >= sk_ctas ? sk_units : sk_units * c / sk_ctas;
+}
+
+struct Segment {          // a maximal run of one CTA's k-blocks inside one tile
+  int tile, kb0, kb1;
+};
+struct SegmentIter {
+  long long cur, end;
+  int num_kb, dp_tile, num_tiles, stride;
+  __device__ __forceinline__ SegmentIter(const long long sk_units, int sk_ctas, int sk_tiles, int num_tiles_, int num_kb_, int c, int ctas)
+      : cur(sk_begin(sk_units, c, sk_ctas)), end(sk_begin(sk_units, c + 1, sk_ctas)), num_kb(num_kb_), dp_tile(sk_tiles + c),
+        num_tiles(num_tiles_), stride(ctas) {}
+  __device__ __forceinline__ bool next(Segment& s) {
+    if (cur < end) {
+      s.tile = (int)(cur / num_kb);
+      s.kb0 = (int)(cur - (long long)s.tile * num_kb);
+      const long long left = end - cur;
+      s.kb1 = (left < (long long)(num_kb - s.kb0)) ? s.kb0 + (int)left : num_kb;
+      cur += s.kb1 - s.kb0;
+      return true;
+    }
+    if (dp_tile < num_tiles) {
+      s.tile = dp_tile;
+      s.kb0 = 0;
+      s.kb1 = num_kb;
+      dp_tile += stride;
+      return true;
+    }
+    return false;
+  }
+};
+#define PSG_SEGMENTS(p) SegmentIter segs((p).sk_units, (p).sk_ctas, (p).sk_tiles, (p).num_tiles, (p).num_kb, blockIdx.x, gridDim.x)
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+// Bounded spin on a stream-K flag (see mbar_wait: a protocol bug must not hang the box).
+__device__ __forceinline__ void wait_flag(const int* flag) {
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v != 0) return;
+    __nanosleep(64);
+  }
+  atomicExch(&g_timeout_flag, 1);
+}
+
 // ---------------------------------------------------------------------------------------------
-// the kernel: persistent CTAs, static round-robin over (tile, split) work items
+// the kernel: persistent CTAs, one contiguous stream-K range of (tile, k-block) units each
 // ---------------------------------------------------------------------------------------------
 template <int kBlockN, int kStages, int kMode, int kMT>
 __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_constant__ KernelParams p) {
@@ -306,18 +425,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_work = p.num_m_tiles * p.num_n_tiles * p.splits;
-
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      uint32_t it = 0;   // global k-block counter: smem ring position and phase carry across work items
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int split = work % p.splits;
-        const int tile = work / p.splits;
+      uint32_t it = 0;   // global k-block counter: smem ring position and phase carry across segments
+      PSG_SEGMENTS(p);
+      Segment sg;
+      while (segs.next(sg)) {
+        const int tile = sg.tile;
         const int tile_n = tile % p.num_n_tiles, tile_m = tile / p.num_n_tiles;
         const int m0 = tile_m * BM;
-        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int kb0 = sg.kb0, kb1 = sg.kb1;
         int w0[kMT], h0[kMT], img0[kMT];
         if (kMode == 0 && p.a_im2col) {
           const int pq = p.P * p.Q;
@@ -387,10 +505,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc(kBlockN, kMode, kMode);
       uint32_t it = 0;
-      int wi = 0;   // local work counter -> accumulator stage and phase
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++wi) {
-        const int split = work % p.splits;
-        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      int wi = 0;   // local segment counter -> accumulator stage and phase
+      PSG_SEGMENTS(p);
+      Segment sg;
+      for (; segs.next(sg); ++wi) {
+        const int kb0 = sg.kb0, kb1 = sg.kb1;
         const int acc = wi % kAcc;
         const uint32_t aph = (wi / kAcc) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1);       // epilogue has drained this accumulator
@@ -426,35 +545,84 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
     // ===== epilogue warps =====
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int chalf = (warp - 2) >> 2;       // the two warps of a quarter take alternate 32-column chunks
+    const int row = q * 32 + lane;           // row of the 128-row MMA tile this thread drains
+    uint8_t* stage = smem_raw + (smem - smem_u32(smem_raw)) + L::EPI_OFFSET + (warp - 2) * 4096;   // this warp's staging tile
+    constexpr int kChunks = kBlockN / 32;
+    constexpr long long kSlotFloats = (long long)kMT * BLOCK_M * kBlockN;
     int wi = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++wi) {
-      const int split = work % p.splits;
-      const int tile = work / p.splits;
+    PSG_SEGMENTS(p);
+    Segment sg;
+    for (; segs.next(sg); ++wi) {
+      const int tile = sg.tile;
       const int tile_n = tile % p.num_n_tiles, tile_m = tile / p.num_n_tiles;
       const int acc = wi % kAcc;
       const uint32_t aph = (wi / kAcc) & 1;
+      const bool contributor = sg.kb0 > 0;                      // someone else owns this tile: park the partial sums
+      const bool shared_owner = sg.kb0 == 0 && sg.kb1 < p.num_kb;
+      // CTAs blockIdx.x+1 .. last_contrib hold the rest of this tile (their ranges start inside it)
+      int last_contrib = blockIdx.x;
+      if (shared_owner) {
+        const long long tile_end = (long long)(tile + 1) * p.num_kb;
+        while (last_contrib + 1 < p.sk_ctas && sk_begin(p.sk_units, last_contrib + 1, p.sk_ctas) < tile_end) ++last_contrib;
+        if (warp == 2 && lane == 0)
+          for (int c = blockIdx.x + 1; c <= last_contrib; ++c) wait_flag(p.sk_flags + c);
+        __syncwarp();
+        epi_bar_sync();
+      }
       mbar_wait(bar_tfull + 8 * acc, aph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * (kMT * kBlockN);
-      float* out_override = nullptr;
-      if (p.splits > 1) out_override = reinterpret_cast<float*>(p.epi.out) + (long long)split * p.split_stride;
       const long long col_base = (long long)tile_n * kBlockN;
       const int col_limit = p.N - tile_n * kBlockN;
 #pragma unroll 1
       for (int t = 0; t < kMT; ++t) {
-        const long long m = (long long)tile_m * BM + t * BLOCK_M + q * 32 + lane;
+        const long long m_base = (long long)tile_m * BM + t * BLOCK_M + q * 32;
 #pragma unroll 1
-        for (int ch = chalf; ch < kBlockN / 32; ch += 2) {
+        for (int ch = chalf; ch < kChunks; ch += 2) {
           uint32_t accv[32];
           tmem_ld32(tmem_acc + t * kBlockN + ((uint32_t)(q * 32) << 16) + ch * 32, accv);
+          // slot layout: [chunk][float4 index j][row] -> a warp's 16-byte accesses are contiguous
+          const long long chunk_off = (long long)(t * kChunks + ch) * (BLOCK_M * 32) + row * 4;
+          if (contributor) {
+            float* dst = p.sk_slots + (long long)blockIdx.x * kSlotFloats + chunk_off;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              __stcg(reinterpret_cast<float4*>(dst + j * (BLOCK_M * 4)),
+                     make_float4(__uint_as_float(accv[4 * j]), __uint_as_float(accv[4 * j + 1]), __uint_as_float(accv[4 * j + 2]),
+                                 __uint_as_float(accv[4 * j + 3])));
+            continue;
+          }
+          for (int c = blockIdx.x + 1; c <= last_contrib; ++c) {       // fixed CTA order: deterministic sums
+            const float* src = p.sk_slots + (long long)c * kSlotFloats + chunk_off;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j * (BLOCK_M * 4)));
+              accv[4 * j] = __float_as_uint(__uint_as_float(accv[4 * j]) + v.x);
+              accv[4 * j + 1] = __float_as_uint(__uint_as_float(accv[4 * j + 1]) + v.y);
+              accv[4 * j + 2] = __float_as_uint(__uint_as_float(accv[4 * j + 2]) + v.z);
+              accv[4 * j + 3] = __float_as_uint(__uint_as_float(accv[4 * j + 3]) + v.w);
+            }
+          }
           int nvalid = col_limit - ch * 32;
           nvalid = nvalid > 32 ? 32 : nvalid;
-          if (m < p.M && nvalid > 0) epilogue_chunk(p.epi, accv, m, col_base + ch * 32, nvalid, p.N, out_override);
+          if (m_base < p.M && nvalid > 0) epilogue_chunk(p.epi, accv, m_base, lane, p.M, col_base + ch * 32, nvalid, p.N, stage);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (contributor) {
+        __threadfence();                     // partial sums visible device-wide before the flag
+        epi_bar_sync();
+        if (warp == 2 && lane == 0) {
+          int one = 1;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + blockIdx.x), "r"(one) : "memory");
+        }
+      } else if (shared_owner) {
+        epi_bar_sync();                      // every epilogue thread has read the slots: hand them back
+        if (warp == 2 && lane == 0)
+          for (int c = blockIdx.x + 1; c <= last_contrib; ++c) p.sk_flags[c] = 0;
+      }
     }
   }
   tc_fence_before();
@@ -552,9 +720,24 @@ static int launch(const KernelParams& kp, dim3 grid, cudaStream_t stream) {
 
 extern "C" {
 
-// Tile-shape heuristic shared by the auto path and psg_umma_plan (the host needs the tile counts to pick split-K).
+// Stream-K workspace (caller-owned, registered once per process): [kMaxCtas] flags (zeroed by the caller) followed by
+// [kMaxCtas] slots of 2*128*256 fp32 partial accumulators.
+static constexpr int kMaxCtas = 160;
+static constexpr size_t kSlotBytes = (size_t)2 * 128 * 256 * sizeof(float);
+static void* g_sk_ws = nullptr;
+
+size_t psg_umma_workspace_bytes() { return 1024 + (size_t)kMaxCtas * kSlotBytes; }
+
+int psg_umma_set_workspace(void* ws, size_t bytes) {
+  PSG_CHECK_ARG(ws == nullptr || bytes >= psg_umma_workspace_bytes(), "psg_umma_set_workspace: need %zu bytes, got %zu",
+                psg_umma_workspace_bytes(), bytes);
+  PSG_CHECK_ARG(((uintptr_t)ws % 256) == 0, "psg_umma_set_workspace: workspace must be 256B aligned");
+  g_sk_ws = ws;
+  return PSG_OK;
+}
+
+// Tile-shape heuristic shared by the auto path and psg_umma_plan.
 static void plan_tiles(int mode, long long M, long long N, long long K, int* block_n, int* m_tiles) {
-  const int sms = psg_num_sms();
   int bn = *block_n;
   if (bn == 0) {
     if (mode == 0) {
@@ -567,13 +750,12 @@ static void plan_tiles(int mode, long long M, long long N, long long K, int* blo
   }
   int mt = *m_tiles;
   if (mt == 0) {
-    const long long n_tiles = (N + bn - 1) / bn;
-    const long long tiles2 = ((M + 255) / 256) * n_tiles;
     const long long pad1 = (M + 127) / 128 * 128, pad2 = (M + 255) / 256 * 256;
     mt = 1;
-    // 256-row CTA tiles (two MMAs share the B tile) pay off for long reductions with at least a full wave of tiles and
-    // no extra row padding; short-K GEMMs prefer 128-row tiles with double-buffered TMEM (epilogue overlap).
-    if (M > 128 && tiles2 >= sms && pad2 == pad1 && (mode == 1 || K >= 2048)) mt = 2;
+    // 256-row CTA tiles (two MMAs share the B tile) pay off for long reductions with no extra row padding; short-K
+    // GEMMs prefer 128-row tiles with double-buffered TMEM (epilogue overlap).  Stream-K balances any tile count.
+    // The NT (wgrad) mode runs ~1.6x faster per MMA row with 256-row tiles, so it takes them even with padded rows.
+    if (M > 128 && ((mode == 1 && pad2 * 2 <= pad1 * 3) || (pad2 == pad1 && K >= 2048))) mt = 2;
   }
   *block_n = bn;
   *m_tiles = mt;
@@ -609,7 +791,7 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   kp.M = (int)d->M;
   kp.N = (int)d->N;
   kp.epi = d->epi;
-  const int split = d->split_k > 1 ? d->split_k : 1;
+  PSG_CHECK_ARG(d->split_k <= 1, "psg_umma_gemm: split-K is gone (stream-K scheduling balances the k-range itself)");
   plan_tiles(mode, d->M, d->N, d->K, &block_n, &m_tiles);
 
   long long n_tiles;
@@ -654,21 +836,35 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
     }
     kp.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
   }
-  kp.kb_per_split = (kp.num_kb + split - 1) / split;
-  const int eff_split = (kp.num_kb + kp.kb_per_split - 1) / kp.kb_per_split;
-  if (split > 1) {
-    PSG_CHECK_ARG(d->epi.out_dtype == PSG_DTYPE_F32, "psg_umma_gemm: split-K needs fp32 output");
-    PSG_CHECK_ARG(eff_split == split, "psg_umma_gemm: split_k=%d does not divide %d k-blocks evenly enough", split, kp.num_kb);
-    kp.split_stride = d->M * d->epi.ldc;
-  }
   const long long m_tiles_n = (d->M + BLOCK_M * m_tiles - 1) / (BLOCK_M * m_tiles);
-  const long long work = m_tiles_n * n_tiles * split;
-  PSG_CHECK_ARG(work < 2147483647LL, "psg_umma_gemm: too many tiles");
+  const long long tiles = m_tiles_n * n_tiles;
+  PSG_CHECK_ARG(tiles < 2147483647LL / 2, "psg_umma_gemm: too many tiles");
   kp.num_m_tiles = (int)m_tiles_n;
   kp.num_n_tiles = (int)n_tiles;
-  kp.splits = split;
-  const int sms = psg_num_sms();
-  dim3 grid((unsigned)(work < sms ? work : sms));
+  kp.num_tiles = (int)tiles;
+  // whole waves of tiles are dealt round-robin; the remainder is the stream-K region, each CTA's share of it being at
+  // least max(8, num_kb / 8) k-blocks (at most ~8 CTAs per tile: the owner adds their partials serially)
+  int sms = psg_num_sms();
+  if (sms > kMaxCtas) sms = kMaxCtas;
+  const long long sk_tiles = tiles % sms;
+  long long ctas = tiles >= sms ? sms : 0, sk_ctas = 0;
+  if (sk_tiles > 0) {
+    const long long sk_units = sk_tiles * kp.num_kb;
+    const long long min_share = kp.num_kb / 8 > 8 ? kp.num_kb / 8 : 8;
+    sk_ctas = sk_units / min_share;
+    if (sk_ctas < sk_tiles) sk_ctas = sk_tiles;
+    if (sk_ctas > sms) sk_ctas = sms;
+    if (ctas < sk_ctas) ctas = sk_ctas;
+    kp.sk_tiles = (int)sk_tiles;
+    kp.sk_ctas = (int)sk_ctas;
+    kp.sk_units = sk_units;
+    if (sk_ctas != sk_tiles) {     // some tile is shared between CTAs
+      PSG_CHECK_ARG(g_sk_ws != nullptr, "psg_umma_gemm: stream-K workspace not registered (psg_umma_set_workspace)");
+      kp.sk_flags = reinterpret_cast<int*>(g_sk_ws);
+      kp.sk_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(g_sk_ws) + 1024);
+    }
+  }
+  dim3 grid((unsigned)ctas);
   cudaStream_t s = (cudaStream_t)stream;
 
 #define PSG_LAUNCH(BN, ST1, ST2, MODE)                              \
@@ -676,14 +872,14 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   else return launch<BN, ST2, MODE, 2>(kp, grid, s)
   if (mode == 0) {
     switch (block_n) {
-      case 64: PSG_LAUNCH(64, 6, 5, 0);
+      case 64: PSG_LAUNCH(64, 6, 4, 0);
       case 128: PSG_LAUNCH(128, 6, 4, 0);
-      case 160: PSG_LAUNCH(160, 5, 4, 0);
+      case 160: PSG_LAUNCH(160, 5, 3, 0);
       case 256: PSG_LAUNCH(256, 4, 3, 0);
     }
   } else {
     switch (block_n) {
-      case 64: PSG_LAUNCH(64, 6, 5, 1);
+      case 64: PSG_LAUNCH(64, 6, 4, 1);
       case 128: PSG_LAUNCH(128, 6, 4, 1);
       case 256: PSG_LAUNCH(256, 4, 3, 1);
     }

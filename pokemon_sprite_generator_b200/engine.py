@@ -336,25 +336,6 @@ class UNetEngine:
     def _engine_for(self, t: torch.Tensor, edge: bool = False) -> str:
         return "umma" if (t.dtype == torch.bfloat16 and not edge) else "simt"
 
-    @staticmethod
-    def _pick_split(tiles: int, num_kb: int) -> int:
-        """Split-K factor for reduction-heavy GEMMs (wgrad): fill the persistent grid's waves, prefer fewer splits."""
-        if tiles >= 2 * NUM_SMS or num_kb < 16:
-            return 1
-        best, best_eff = 1, 0.0
-        for s in range(1, 17):
-            per = -(-num_kb // s)
-            if per < 8:
-                break
-            s_eff = -(-num_kb // per)
-            if s_eff != s:
-                continue
-            work = tiles * s
-            eff = work / (-(-work // NUM_SMS) * NUM_SMS)
-            if eff > best_eff + 0.04:
-                best, best_eff = s, eff
-        return best
-
     def _seed(self, site: int) -> int:
         return ((self.seed * 0x9E3779B1 + self.step_counter) * 0x85EBCA77 + site * 0xC2B2AE3D) & 0xFFFFFFFFFFFFFFFF
 
@@ -404,16 +385,10 @@ class UNetEngine:
         kk = cw.k * cw.k
         ncols = kk * cw.cin_p
         a_op, b_op = G.mnmajor(dy), G.im2col_t(x.nhwc(), cw.k, cw.stride, cw.pad)
-        bn = mt = 0
-        if eng == "umma":
-            bn, mt, tiles = G.plan(a_op, b_op)
-            split = self._pick_split(tiles, (dy.shape[0] + 63) // 64)
-        else:
-            split = 1
-        nel = split * cw.cout_p * ncols
-        part = K.workspace(self.device, nel, "wgrad").narrow(0, 0, nel).view(split, cw.cout_p, ncols)
-        G.run_gemm(a_op, b_op, G.Epilogue(out=part[0]), engine=eng, split_k=split, block_n=bn, m_tiles=mt)
-        K.wgrad_finalize(part, split, cw.cout_p * ncols, gw, cin_p=cw.cin_p)
+        nel = cw.cout_p * ncols
+        part = K.workspace(self.device, nel, "wgrad").narrow(0, 0, nel).view(1, cw.cout_p, ncols)
+        G.run_gemm(a_op, b_op, G.Epilogue(out=part[0]), engine=eng)      # stream-K balances the long pixel reduction
+        K.wgrad_finalize(part, 1, nel, gw, cin_p=cw.cin_p)
         if not x_needs_grad:
             return
         # dgrad
@@ -490,19 +465,7 @@ class UNetEngine:
         if gb is not None:
             K.colsum(dy, 1, None, gb, scale=scale)
         # wgrad: dW[n][k] = scale * sum_m dY[m, n] X[m, k]
-        a_op, b_op = G.mnmajor(dy), G.mnmajor(x.t)
-        bn = mt = 0
-        if eng == "umma":
-            bn, mt, tiles = G.plan(a_op, b_op)
-            split = self._pick_split(tiles, (dy.shape[0] + 63) // 64)
-        else:
-            split = 1
-        if split == 1:
-            G.run_gemm(a_op, b_op, G.Epilogue(out=gw2, alpha=scale), engine=eng, block_n=bn, m_tiles=mt)
-        else:
-            part = K.workspace(self.device, split * N * Kd, "wgrad").narrow(0, 0, split * N * Kd).view(split, N, Kd)
-            G.run_gemm(a_op, b_op, G.Epilogue(out=part[0], alpha=scale), engine=eng, split_k=split, block_n=bn, m_tiles=mt)
-            K.sum_partials(part, split, N * Kd, gw2)
+        G.run_gemm(G.mnmajor(dy), G.mnmajor(x.t), G.Epilogue(out=gw2, alpha=scale), engine=eng)
         if not x_needs_grad:
             return
         tgt, acc = self._grad_target(x) if x.parent is None else (x.g(), False)

@@ -148,6 +148,22 @@ def plan(a: Operand, b: Operand, block_n: int = 0, m_tiles: int = 0):
     return bn, mt, mtiles * ntiles
 
 
+_umma_ws = {}
+
+
+def _ensure_umma_workspace(device) -> None:
+    """Registers the stream-K partial-accumulator workspace of the tcgen05 engine (once per process/device)."""
+    if device in _umma_ws:
+        return
+    lib = L.load()
+    lib.psg_umma_workspace_bytes.restype = C.c_size_t
+    n = lib.psg_umma_workspace_bytes()
+    ws = torch.zeros(n, dtype=torch.uint8, device=device)
+    L.check(lib.psg_umma_set_workspace(C.c_void_p(ws.data_ptr()), C.c_size_t(n)), "psg_umma_set_workspace")
+    _umma_ws.clear()
+    _umma_ws[device] = ws
+
+
 # When set to a list, every launch appends (start_event, end_event, algorithmic_flops, engine): bench.py uses it to time
 # the tensor-core kernel on its own stream inside the timed region (roofline numerator and denominator).
 PROFILE = None
@@ -174,6 +190,7 @@ def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", spl
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     if engine == "umma":
+        _ensure_umma_workspace(a.t.device)
         L.check(lib.psg_umma_gemm_ex(C.byref(d), C.c_int(block_n), C.c_int(m_tiles), L.stream_ptr()), "psg_umma_gemm")
     elif engine == "simt":
         L.check(lib.psg_simt_gemm(C.byref(d), L.stream_ptr()), "psg_simt_gemm")

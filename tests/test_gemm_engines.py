@@ -98,20 +98,55 @@ def test_gemm_nt(cuda_device, engine, M, N, K):
     _close(out, ref, 1e-4, f"nt {engine} {M}x{N}x{K}")
 
 
-@pytest.mark.parametrize("engine", ["simt", "umma"])
-def test_gemm_nt_split_k(cuda_device, engine):
-    if engine == "simt":
-        pytest.skip("split-K is a tcgen05-engine feature")
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64 * 1200), (640, 1280, 64 * 333), (128, 64, 64 * 2000), (384, 320, 64 * 257)])
+def test_gemm_nt_stream_k(cuda_device, M, N, K):
+    """Few tiles, long reduction: stream-K shares every tile between several CTAs (fp32 partials through the workspace);
+    the result must match, twice in a row bit-identically (fixed summation order), and leave the flags clean."""
+    L, G = _mods()
+    g = torch.Generator(device="cuda").manual_seed(11 + M)
+    a = torch.randn(K, M, device="cuda", generator=g).bfloat16()
+    b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+    outs = []
+    for _ in range(2):
+        out = torch.full((M, N), float("nan"), device="cuda")
+        G.run_gemm(G.mnmajor(a), G.mnmajor(b), G.Epilogue(out=out), engine="umma")
+        torch.cuda.synchronize()
+        _check_timeout(L)
+        outs.append(out)
+    ref = (a.double().t() @ b.double()).float()
+    _close(outs[0], ref, 1e-4, f"nt stream-k {M}x{N}x{K}")
+    assert torch.equal(outs[0], outs[1]), "stream-K result is not run-to-run deterministic"
+    flags = next(iter(G._umma_ws.values()))[:1024].view(torch.int32)
+    assert int(flags.abs().sum()) == 0, "stream-K flags not handed back"
+
+
+def test_gemm_simt_split_k(cuda_device):
     L, G = _mods()
     M, N, K, S = 256, 128, 64 * 12, 4
     g = torch.Generator(device="cuda").manual_seed(11)
-    a = torch.randn(K, M, device="cuda", generator=g).bfloat16()
-    b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(K, N, device="cuda", generator=g)
     part = torch.full((S, M, N), float("nan"), device="cuda")
-    G.run_gemm(G.mnmajor(a), G.mnmajor(b), G.Epilogue(out=part[0]), engine=engine, split_k=S)
+    G.run_gemm(G.kmajor(a), G.mnmajor(b), G.Epilogue(out=part[0]), engine="simt", split_k=S)
+    torch.cuda.synchronize()
+    _close(part.sum(0), a @ b, 1e-5, "simt split-k")
+
+
+@pytest.mark.parametrize("M,N,K,bn,mt", [(128 * 37 + 5, 1280, 640, 0, 0), (12544, 1280, 11520, 256, 2), (4096, 1280, 2560, 256, 1),
+                                         (3000, 320, 2880, 160, 1), (50176, 640, 640, 0, 0)])
+def test_gemm_tn_stream_k(cuda_device, M, N, K, bn, mt):
+    """Tile counts that do not divide the SM count: stream-K ranges cross tile boundaries with a fused bf16 epilogue."""
+    L, G = _mods()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out, bias=bias, residual=res, alpha=0.7), engine="umma", block_n=bn, m_tiles=mt)
     torch.cuda.synchronize()
     _check_timeout(L)
-    _close(part.sum(0), a.float().t() @ b.float(), 1e-4, "nt split-k")
+    _close(out, 0.7 * (a.float() @ b.float().t() + bias) + res.float(), 6e-3, f"tn stream-k {M}x{N}x{K}")
 
 
 def _conv_inputs(n, h, w, cin, cout, seed, dtype):
@@ -175,11 +210,9 @@ def test_conv_dgrad_stride2_gather(cuda_device, h, cin, cout):
 
 @pytest.mark.parametrize("engine,dtype", [("simt", torch.float32), ("umma", torch.bfloat16)])
 @pytest.mark.parametrize("n,h,cin,cout,stride,split", [(2, 27, 64, 128, 1, 1), (3, 14, 128, 64, 1, 1), (8, 4, 320, 128, 1, 1),
-                                                       (2, 27, 64, 64, 2, 1), (4, 27, 64, 128, 1, 3)])
+                                                       (2, 27, 64, 64, 2, 1), (40, 27, 64, 128, 1, 1)])
 def test_conv_wgrad(cuda_device, engine, dtype, n, h, cin, cout, stride, split):
     L, G = _mods()
-    if engine == "simt" and split > 1:
-        pytest.skip("split-K is a tcgen05-engine feature")
     x, wt = _conv_inputs(n, h, h, cin, cout, 31 + h + cin, dtype)
     b = G.im2col_t(x, 3, stride, 1)
     p = (h + 2 - 3) // stride + 1
@@ -230,11 +263,11 @@ def test_umma_tile_shapes_tn(cuda_device, mt, bn):
 @pytest.mark.parametrize("bn", [64, 128, 256])
 def test_umma_tile_shapes_wgrad(cuda_device, mt, bn):
     L, G = _mods()
-    n, h, cin, cout, split = 6, 14, 320, 384, 3
+    n, h, cin, cout, split = 6, 14, 320, 384, 1
     x, wt = _conv_inputs(n, h, h, cin, cout, 77 + bn + mt, torch.bfloat16)
     dy = torch.randn(n * h * h, cout, device="cuda").bfloat16()
     part = torch.full((split, cout, 9 * cin), float("nan"), device="cuda")
-    G.run_gemm(G.mnmajor(dy), G.im2col_t(x, 3, 1, 1), G.Epilogue(out=part[0]), engine="umma", split_k=split, block_n=bn, m_tiles=mt)
+    G.run_gemm(G.mnmajor(dy), G.im2col_t(x, 3, 1, 1), G.Epilogue(out=part[0]), engine="umma", block_n=bn, m_tiles=mt)
     torch.cuda.synchronize()
     _check_timeout(L)
     dw = part.sum(0).reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)

@@ -37,7 +37,7 @@ def conv(B, H, cin, cout, bn=0, mt=0):
 def wgrad(B, H, cin, cout, split=1, bn=128, mt=0):
     x = torch.randn(B, H, H, cin, device=dev).bfloat16(); dy = torch.randn(B * H * H, cout, device=dev).bfloat16()
     part = torch.empty(split, cout, 9 * cin, device=dev)
-    timeit(lambda: G.run_gemm(G.mnmajor(dy), G.im2col_t(x, 3, 1, 1), G.Epilogue(out=part[0]), engine="umma", split_k=split, block_n=bn, m_tiles=mt),
+    timeit(lambda: G.run_gemm(G.mnmajor(dy), G.im2col_t(x, 3, 1, 1), G.Epilogue(out=part[0]), engine="umma", block_n=bn, m_tiles=mt),
            2.0 * B * H * H * cout * 9 * cin, f"wgrad  B={B} H={H} {cin}->{cout} split={split} bn={bn} mt={mt}")
 
 

@@ -30,6 +30,7 @@ extern "C" {
 #define PSG_ACT_NONE 0
 #define PSG_ACT_GELU 1
 #define PSG_ACT_SILU 2
+#define PSG_ACT_MUL 3   /* aux_in only: multiply by the stored value (a derivative saved by the forward epilogue) */
 #define PSG_OP_KMAJOR 0
 #define PSG_OP_MNMAJOR 1
 #define PSG_OP_IM2COL 2
@@ -83,6 +84,7 @@ int psg_umma_plan(const PsgGemmDesc* desc, int* block_n, int* m_tiles);
  * caller-owned workspace (psg_umma_workspace_bytes() bytes, 256B aligned, first 1 KiB zeroed), registered once. */
 size_t psg_umma_workspace_bytes(void);
 int psg_umma_set_workspace(void* workspace, size_t bytes);
+int psg_umma_debug(int flags);                 /* profiling aid: 1 = skip the epilogue body (mainloop time alone); 0 = normal */
 /* CUDA-core fp32-accumulate engine (fp32 parity mode, edge shapes, general-stride dgrad gather). */
 int psg_simt_gemm(const PsgGemmDesc* desc, void* stream);
 

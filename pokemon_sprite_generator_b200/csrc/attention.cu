@@ -54,7 +54,7 @@ struct Params {
 __device__ __forceinline__ bool keep(const Params& p, int b, int h, int i, int j) {
   if (p.drop_threshold == 0) return true;
   uint64_t idx = (((uint64_t)(b * p.H + h) * p.Lq + i) * p.Lk + j);
-  return psg_hash32(p.drop_seed, idx) >= p.drop_threshold;
+  return psg_drop_keep(p.drop_seed, idx, p.drop_threshold);
 }
 
 // copy rows [r0, r0+nr) x hd of a token-major matrix into smem words with row pitch `pitch`

@@ -196,7 +196,7 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, __nv_bfloat16* _
     const float pr = (j < Lk) ? v[i] * inv : 0.f;
     P[row * ldp + j] = __float2bfloat16_rn(pr);
     if (Pd != nullptr) {
-      const bool kp = thr == 0 || psg_hash32(seed, (uint64_t)(row * Lk + j)) >= thr;
+      const bool kp = thr == 0 || psg_drop_keep(seed, (uint64_t)(row * Lk + j), thr);
       Pd[row * ldp + j] = __float2bfloat16_rn(kp ? pr * keep_scale : 0.f);
     }
   }
@@ -217,7 +217,7 @@ __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const fl
     pr[i] = 0.f; g[i] = 0.f;
     if (j < Lk) {
       pr[i] = __bfloat162float(P[row * ldp + j]);
-      const bool kp = thr == 0 || psg_hash32(seed, (uint64_t)(row * Lk + j)) >= thr;
+      const bool kp = thr == 0 || psg_drop_keep(seed, (uint64_t)(row * Lk + j), thr);
       g[i] = kp ? dPd[row * ldp + j] * keep_scale : 0.f;
       if (Pd != nullptr) Pd[row * ldp + j] = __float2bfloat16_rn(kp ? pr[i] * keep_scale : 0.f);
       d = fmaf(pr[i], g[i], d);

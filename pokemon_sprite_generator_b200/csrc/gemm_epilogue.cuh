@@ -2,9 +2,10 @@
 // (simt_gemm.cu).  One definition so that both engines produce the same function of the accumulator:
 //
 //   v   = acc + bias[n] + rowbias[(m / rows_per_group) * ld_rowbias + n]
-//   (aux_out[m,n] = v)                       -- optional pre-activation store, activation dtype
+//   (aux_out[m,n] = v)                       -- optional pre-activation store, activation dtype            [aux_act == NONE]
+//   (aux_out[m,n] = act'(v) * dropmask * keep_scale)  -- or the saved local derivative of act+dropout     [aux_act != NONE]
 //   v   = act(v)                             -- none | gelu(erf) | silu
-//   v  *= act'(aux_in[m,n])                  -- optional, backward of a fused activation
+//   v  *= act'(aux_in[m,n])                  -- optional, backward of a fused activation; aux_act == PSG_ACT_MUL: v *= aux_in
 //   v   = dropout(v; seed, threshold) * keep_scale
 //   v   = alpha * v + residual[m,n]          -- residual in activation dtype, may alias out
 //   out[m,n] (+)= v                          -- fp32 or bf16; accumulate only for fp32
@@ -18,6 +19,7 @@
 #define PSG_ACT_NONE 0
 #define PSG_ACT_GELU 1
 #define PSG_ACT_SILU 2
+#define PSG_ACT_MUL 3      // aux_in only: multiply by the stored value itself (a derivative saved by the forward epilogue)
 
 struct PsgEpilogue {
   void* out;               // [M, ldc]
@@ -56,17 +58,20 @@ __device__ __forceinline__ void psg_epilogue_scalar(const PsgEpilogue& e, float 
   float v = acc;
   if (e.bias) v += e.bias[n];
   if (e.rowbias) v += e.rowbias[(m / e.rows_per_group) * e.ld_rowbias + n];
-  if (e.aux_out) psg_epi_store(e.aux_out, e.act_dtype, m * e.ld_aux + n, v);
+  const float keep = (!e.drop_threshold || psg_drop_keep(e.drop_seed, (uint64_t)(m * N + n), e.drop_threshold)) ? e.drop_scale : 0.f;
+  if (e.aux_out) {
+    float s = v;
+    if (e.aux_act != PSG_ACT_NONE)
+      s = keep * ((e.act == PSG_ACT_GELU) ? psg_gelu_grad(v) : (e.act == PSG_ACT_SILU ? psg_silu_grad(v) : 1.f));
+    psg_epi_store(e.aux_out, e.act_dtype, m * e.ld_aux + n, s);
+  }
   if (e.act == PSG_ACT_GELU) v = psg_gelu(v);
   else if (e.act == PSG_ACT_SILU) v = psg_silu(v);
   if (e.aux_in) {
     float a = psg_epi_load_act(e.aux_in, e.act_dtype, m * e.ld_aux + n);
-    v *= (e.aux_act == PSG_ACT_GELU) ? psg_gelu_grad(a) : (e.aux_act == PSG_ACT_SILU ? psg_silu_grad(a) : 1.f);
+    v *= (e.aux_act == PSG_ACT_GELU) ? psg_gelu_grad(a) : (e.aux_act == PSG_ACT_SILU ? psg_silu_grad(a) : (e.aux_act == PSG_ACT_MUL ? a : 1.f));
   }
-  if (e.drop_threshold) {
-    uint32_t h = psg_hash32(e.drop_seed, (uint64_t)(m * N + n));
-    v = (h >= e.drop_threshold) ? v * e.drop_scale : 0.f;
-  }
+  if (e.drop_threshold) v *= keep;
   v *= e.alpha;
   if (e.residual) v += psg_epi_load_act(e.residual, e.act_dtype, m * e.ldr + n);
   long long o = m * e.ldc + n;

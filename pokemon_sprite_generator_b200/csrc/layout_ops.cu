@@ -273,7 +273,7 @@ __global__ void dropout_scale_kernel(const T* __restrict__ x, long long ldx, T* 
     a.load(x + r * ldx + v * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const bool kp = threshold == 0 || psg_hash32(seed, (uint64_t)(r * C + v * 8 + j)) >= threshold;
+      const bool kp = threshold == 0 || psg_drop_keep(seed, (uint64_t)(r * C + v * 8 + j), threshold);
       a.v[j] = kp ? a.v[j] * keep_scale * alpha : 0.f;
     }
     a.store(out + r * ldo + v * 8);

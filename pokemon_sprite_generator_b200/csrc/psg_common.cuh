@@ -110,6 +110,35 @@ __device__ __forceinline__ float psg_gelu_grad(float x) {
   return cdf + x * pdf;
 }
 
+__device__ __forceinline__ float psg_rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float psg_ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Fast forms for the bf16 tensor-core epilogues (|error| < 2e-7, far below bf16 rounding): Abramowitz-Stegun 7.1.26
+// for the normal CDF, evaluated on the tail side so that there is no cancellation; two MUFU ops (rcp, ex2) per value.
+__device__ __forceinline__ void psg_gelu_parts(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = psg_rcp_approx(fmaf(0.3275911f, z, 1.f));
+  e = psg_ex2_approx(-1.4426950408889634f * z * z);               // exp(-x^2/2)
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float tail = 0.5f * poly * e;                             // 1 - Phi(|x|)
+  cdf = x < 0.f ? tail : 1.f - tail;
+}
+__device__ __forceinline__ float psg_gelu_fast(float x) {
+  float cdf, e;
+  psg_gelu_parts(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float psg_gelu_grad_fast(float x) {
+  float cdf, e;
+  psg_gelu_parts(x, cdf, e);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+__device__ __forceinline__ float psg_silu_fast(float x) { return x * psg_rcp_approx(1.f + psg_ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float psg_silu_grad_fast(float x) {
+  const float s = psg_rcp_approx(1.f + psg_ex2_approx(-1.4426950408889634f * x));
+  return s * fmaf(x, 1.f - s, 1.f);
+}
+
 // Stateless counter-based dropout mask: keep iff hash(seed, idx) >= threshold (threshold = p * 2^32).  32-bit mixer
 // (two multiply/xorshift rounds): it runs once per element inside GEMM epilogues, where a 64-bit mixer was the bottleneck.
 __device__ __forceinline__ uint32_t psg_hash32(uint64_t seed, uint64_t idx) {
@@ -120,4 +149,13 @@ __device__ __forceinline__ uint32_t psg_hash32(uint64_t seed, uint64_t idx) {
   x *= 0x846CA68Bu;
   x ^= x >> 16;
   return x;
+}
+// One hash decides two neighbouring elements (16 bits each): keep element idx iff its half of hash(seed, idx / 2) is
+// >= threshold / 65536.  Every dropout site (GEMM epilogues, softmax, dropout_scale) and its backward use this one rule.
+__device__ __forceinline__ bool psg_drop_keep2(uint32_t pair_hash, int odd, uint32_t threshold) {
+  const uint32_t field = odd ? (pair_hash >> 16) : (pair_hash & 0xFFFFu);
+  return field >= (threshold >> 16);
+}
+__device__ __forceinline__ bool psg_drop_keep(uint64_t seed, uint64_t idx, uint32_t threshold) {
+  return psg_drop_keep2(psg_hash32(seed, idx >> 1), (int)(idx & 1), threshold);
 }

@@ -27,7 +27,8 @@ namespace umma {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+constexpr int kEpiWarps = 8;       // two warps per TMEM lane quarter (16 were measured: no faster, and they spill)
+constexpr int kNumThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
 
 struct alignas(64) KernelParams {
@@ -41,6 +42,7 @@ struct alignas(64) KernelParams {
   long long sk_units;        // sk_tiles * num_kb
   float* sk_slots;           // [gridDim.x][kMT*128*kBlockN] fp32 partial accumulators of shared tiles
   int* sk_flags;             // [gridDim.x] 1 = slot holds a partial that has not been consumed yet
+  int debug;                 // profiling aid (psg_umma_debug): 1 = skip the epilogue body, 2 = epilogue math without global I/O
   // mode 0, A im2col
   int a_im2col, cblks, ksize, conv_stride, pad, flip, P, Q;
   // mode 1, B im2col (wgrad): columns are (tap, cin)
@@ -161,90 +163,94 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
 // take consecutive 16-byte pieces of a row, 64 or 128 contiguous bytes per row and instruction -- and each thread
 // picks up / drops off its own row on the shared-memory side.
 // ---------------------------------------------------------------------------------------------
-template <int kElemBytes>      // 2 (bf16) or 4 (fp32): a 32 x 32 tile has rows of 64 or 128 bytes
+// One staging tile = 32 rows x 64 bytes (32 bf16 columns, or 16 fp32 columns: fp32 tensors move in two halves).
 struct WarpTile {
-  static constexpr int kCpr = 32 * kElemBytes / 16;     // 16-byte pieces per row: 4 or 8
-  static constexpr int kPerLane = kCpr;                 // pieces each lane moves: 32 rows * kCpr / 32 lanes
-  __device__ static __forceinline__ uint32_t off(int r, int c) {
-    return (uint32_t)(r * (kCpr * 16) + ((kCpr == 8 ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3))) << 4));
-  }
+  __device__ static __forceinline__ uint32_t off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
   // global tile (row pitch ld_bytes) -> staging; rows >= rows_valid are skipped
   __device__ static __forceinline__ void load(uint8_t* stage, const uint8_t* g, long long ld_bytes, int rows_valid, int lane) {
-    uint4 v[kPerLane];
+    uint4 v[4];
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
-      const int pc = lane + 32 * i, r = pc / kCpr, c = pc % kCpr;
-      v[i] = (r < rows_valid) ? *reinterpret_cast<const uint4*>(g + (long long)r * ld_bytes + c * 16) : make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < 4; ++i) {
+      const int pc = lane + 32 * i, r = pc >> 2, c = pc & 3;
+      v[i] = (r < rows_valid) ? __ldcg(reinterpret_cast<const uint4*>(g + (long long)r * ld_bytes + c * 16)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
-      const int pc = lane + 32 * i, r = pc / kCpr, c = pc % kCpr;
+    for (int i = 0; i < 4; ++i) {
+      const int pc = lane + 32 * i, r = pc >> 2, c = pc & 3;
       *reinterpret_cast<uint4*>(stage + off(r, c)) = v[i];
     }
   }
   __device__ static __forceinline__ void store(const uint8_t* stage, uint8_t* g, long long ld_bytes, int rows_valid, int lane) {
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
-      const int pc = lane + 32 * i, r = pc / kCpr, c = pc % kCpr;
-      if (r < rows_valid) *reinterpret_cast<uint4*>(g + (long long)r * ld_bytes + c * 16) = *reinterpret_cast<const uint4*>(stage + off(r, c));
+    for (int i = 0; i < 4; ++i) {
+      const int pc = lane + 32 * i, r = pc >> 2, c = pc & 3;
+      if (r < rows_valid) __stcg(reinterpret_cast<uint4*>(g + (long long)r * ld_bytes + c * 16), *reinterpret_cast<const uint4*>(stage + off(r, c)));
     }
   }
 };
 
-// staging <-> this thread's row, as 32 floats
-__device__ __forceinline__ void row_get(const uint8_t* stage, int dtype, int lane, float (&a)[32]) {
+// whole-warp: fetch the [32 x 32] tile at (m_base, n0) of a row-pitched tensor and hand every thread its row
+__device__ __forceinline__ void tile_in(uint8_t* stage, const void* base, long long ld, int dtype, long long m_base, long long n0,
+                                        int rows_valid, int lane, float (&a)[32]) {
   if (dtype == PSG_DTYPE_BF16) {
+    __syncwarp();
+    WarpTile::load(stage, reinterpret_cast<const uint8_t*>(base) + (m_base * ld + n0) * 2, ld * 2, rows_valid, lane);
+    __syncwarp();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const uint4 r = *reinterpret_cast<const uint4*>(stage + WarpTile<2>::off(lane, c));
+      const uint4 r = *reinterpret_cast<const uint4*>(stage + WarpTile::off(lane, c));
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); a[8 * c + 2 * i] = f.x; a[8 * c + 2 * i + 1] = f.y; }
     }
   } else {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 r = *reinterpret_cast<const float4*>(stage + WarpTile<4>::off(lane, c));
-      a[4 * c] = r.x; a[4 * c + 1] = r.y; a[4 * c + 2] = r.z; a[4 * c + 3] = r.w;
+    for (int half = 0; half < 2; ++half) {
+      __syncwarp();
+      WarpTile::load(stage, reinterpret_cast<const uint8_t*>(base) + (m_base * ld + n0 + 16 * half) * 4, ld * 4, rows_valid, lane);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 r = *reinterpret_cast<const float4*>(stage + WarpTile::off(lane, c));
+        a[16 * half + 4 * c] = r.x; a[16 * half + 4 * c + 1] = r.y; a[16 * half + 4 * c + 2] = r.z; a[16 * half + 4 * c + 3] = r.w;
+      }
     }
   }
 }
-__device__ __forceinline__ void row_put(uint8_t* stage, int dtype, int lane, const float (&v)[32]) {
+__device__ __forceinline__ void tile_out(uint8_t* stage, void* base, long long ld, int dtype, long long m_base, long long n0,
+                                         int rows_valid, int lane, const float (&v)[32]) {
   if (dtype == PSG_DTYPE_BF16) {
+    __syncwarp();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint4 r;
       __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
 #pragma unroll
       for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
-      *reinterpret_cast<uint4*>(stage + WarpTile<2>::off(lane, c)) = r;
+      *reinterpret_cast<uint4*>(stage + WarpTile::off(lane, c)) = r;
     }
+    __syncwarp();
+    WarpTile::store(stage, reinterpret_cast<uint8_t*>(base) + (m_base * ld + n0) * 2, ld * 2, rows_valid, lane);
   } else {
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<float4*>(stage + WarpTile<4>::off(lane, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    for (int half = 0; half < 2; ++half) {
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(stage + WarpTile::off(lane, c)) =
+            make_float4(v[16 * half + 4 * c], v[16 * half + 4 * c + 1], v[16 * half + 4 * c + 2], v[16 * half + 4 * c + 3]);
+      __syncwarp();
+      WarpTile::store(stage, reinterpret_cast<uint8_t*>(base) + (m_base * ld + n0 + 16 * half) * 4, ld * 4, rows_valid, lane);
+    }
   }
 }
-// whole-warp: fetch the [32 x 32] tile at (m_base, n0) of a row-pitched tensor and hand every thread its row
-__device__ __forceinline__ void tile_in(uint8_t* stage, const void* base, long long ld, int dtype, long long m_base, long long n0,
-                                        int rows_valid, int lane, float (&a)[32]) {
-  __syncwarp();
-  if (dtype == PSG_DTYPE_BF16)
-    WarpTile<2>::load(stage, reinterpret_cast<const uint8_t*>(base) + (m_base * ld + n0) * 2, ld * 2, rows_valid, lane);
-  else
-    WarpTile<4>::load(stage, reinterpret_cast<const uint8_t*>(base) + (m_base * ld + n0) * 4, ld * 4, rows_valid, lane);
-  __syncwarp();
-  row_get(stage, dtype, lane, a);
-}
-__device__ __forceinline__ void tile_out(uint8_t* stage, void* base, long long ld, int dtype, long long m_base, long long n0,
-                                         int rows_valid, int lane, const float (&v)[32]) {
-  __syncwarp();
-  row_put(stage, dtype, lane, v);
-  __syncwarp();
-  if (dtype == PSG_DTYPE_BF16)
-    WarpTile<2>::store(stage, reinterpret_cast<uint8_t*>(base) + (m_base * ld + n0) * 2, ld * 2, rows_valid, lane);
-  else
-    WarpTile<4>::store(stage, reinterpret_cast<uint8_t*>(base) + (m_base * ld + n0) * 4, ld * 4, rows_valid, lane);
+
+// L2 prefetch of this thread's row segment (64 B bf16 / 128 B fp32) of an epilogue input tile: issued before the wait
+// for the accumulator, so that the tile_in loads that follow find their lines in L2.
+__device__ __forceinline__ void prefetch_row(const void* base, long long ld, int dtype, long long m, long long n0) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(base) + (m * ld + n0) * (dtype == PSG_DTYPE_BF16 ? 2 : 4);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  if (dtype != PSG_DTYPE_BF16) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 64));
 }
 
 // Called by the whole warp (rows m_base .. m_base+31, this thread's row m = m_base + lane; rows >= M are dead).
@@ -254,7 +260,7 @@ __device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint3
   const int rows_valid = (M - m_base) < 32 ? (int)(M - m_base) : 32;
   // fast path: whole chunk valid and 16B-aligned everywhere (warp-uniform condition)
   const bool vec = (nvalid == 32) && ((n0 & 7) == 0) && ((e.ldc & 7) == 0) && ((e.ldr & 7) == 0) && ((e.ld_aux & 7) == 0) &&
-                   ((e.ld_rowbias & 3) == 0);
+                   ((e.ld_rowbias & 3) == 0) && (((N & 1) == 0) || !e.drop_threshold);
   if (!vec) {
     if (m < M) {
 #pragma unroll
@@ -277,27 +283,68 @@ __device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint3
 #pragma unroll
     for (int j = 0; j < 8; ++j) { float4 b = __ldg(b4 + j); v[4*j] += b.x; v[4*j+1] += b.y; v[4*j+2] += b.z; v[4*j+3] += b.w; }
   }
-  if (e.aux_out) tile_out(stage, e.aux_out, e.ld_aux, e.act_dtype, m_base, n0, rows_valid, lane, v);
-  if (e.act == PSG_ACT_GELU) {
+  // dropout decisions of this thread's 32 elements, one bit each (one hash per neighbouring pair)
+  uint32_t keep = 0xFFFFFFFFu;
+  if (e.drop_threshold) {
+    keep = 0u;
+    const uint64_t pair0 = (uint64_t)(m * N + n0) >> 1;      // N and n0 are even here: (m*N + n0) is even
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = psg_gelu(v[j]);
+    for (int j = 0; j < 32; j += 2) {
+      const uint32_t h = psg_hash32(e.drop_seed, pair0 + (j >> 1));
+      keep |= (psg_drop_keep2(h, 0, e.drop_threshold) ? 1u : 0u) << j;
+      keep |= (psg_drop_keep2(h, 1, e.drop_threshold) ? 1u : 0u) << (j + 1);
+    }
+  }
+  const bool save_grad = e.aux_out && e.aux_act != PSG_ACT_NONE;   // save act'(pre) * dropmask instead of pre
+  if (e.aux_out && !save_grad) tile_out(stage, e.aux_out, e.ld_aux, e.act_dtype, m_base, n0, rows_valid, lane, v);
+  if (save_grad) {
+    float d[32];
+    if (e.act == PSG_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float cdf, ex;
+        psg_gelu_parts(v[j], cdf, ex);
+        d[j] = fmaf(v[j] * 0.3989422804014327f, ex, cdf);
+        v[j] *= cdf;
+      }
+    } else if (e.act == PSG_ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float sg = psg_rcp_approx(1.f + psg_ex2_approx(-1.4426950408889634f * v[j]));
+        d[j] = sg * fmaf(v[j], 1.f - sg, 1.f);
+        v[j] *= sg;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = 1.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d[j] = ((keep >> j) & 1u) ? d[j] * e.drop_scale : 0.f;
+    tile_out(stage, e.aux_out, e.ld_aux, e.act_dtype, m_base, n0, rows_valid, lane, d);
+  } else if (e.act == PSG_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = psg_gelu_fast(v[j]);
   } else if (e.act == PSG_ACT_SILU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = psg_silu(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = psg_silu_fast(v[j]);
   }
   if (e.aux_in) {
     float a[32];
     tile_in(stage, e.aux_in, e.ld_aux, e.act_dtype, m_base, n0, rows_valid, lane, a);
+    if (e.aux_act == PSG_ACT_MUL) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      v[j] *= (e.aux_act == PSG_ACT_GELU) ? psg_gelu_grad(a[j]) : (e.aux_act == PSG_ACT_SILU ? psg_silu_grad(a[j]) : 1.f);
+      for (int j = 0; j < 32; ++j) v[j] *= a[j];
+    } else if (e.aux_act == PSG_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= psg_gelu_grad_fast(a[j]);
+    } else if (e.aux_act == PSG_ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= psg_silu_grad_fast(a[j]);
+    }
   }
   if (e.drop_threshold) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      uint32_t h = psg_hash32(e.drop_seed, (uint64_t)(m * N + n0 + j));
-      v[j] = (h >= e.drop_threshold) ? v[j] * e.drop_scale : 0.f;
-    }
+    for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * e.drop_scale : 0.f;
   }
   if (e.alpha != 1.f) {
 #pragma unroll
@@ -330,8 +377,8 @@ struct SmemLayout {
   static constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_BYTES;
   static constexpr int kAcc = (2 * kMT * kBlockN <= 512) ? 2 : 1;          // TMEM accumulator stages
   static constexpr uint32_t TMEM_COLS = tmem_cols_for(kAcc * kMT * kBlockN);
-  static constexpr uint32_t EPI_OFFSET = STAGE_BYTES * kStages;         // 8 epilogue warps x 4 KiB staging tiles
-  static constexpr uint32_t EPI_BYTES = 8 * 4096;
+  static constexpr uint32_t EPI_OFFSET = STAGE_BYTES * kStages;         // one 2 KiB staging tile per epilogue warp
+  static constexpr uint32_t EPI_BYTES = kEpiWarps * 2048;
   static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * kStages + 4) * 8 + 16 + 1024;  // + alignment slack
 };
@@ -376,7 +423,7 @@ struct SegmentIter {
 };
 #define PSG_SEGMENTS(p) SegmentIter segs((p).sk_units, (p).sk_ctas, (p).sk_tiles, (p).num_tiles, (p).num_kb, blockIdx.x, gridDim.x)
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }   // the epilogue warps
 
 // Bounded spin on a stream-K flag (see mbar_wait: a protocol bug must not hang the box).
 __device__ __forceinline__ void wait_flag(const int* flag) {
@@ -416,7 +463,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
     prefetch_tmap(&p.tm_a);
     prefetch_tmap(&p.tm_b);
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < kAcc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+    for (int a = 0; a < kAcc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -544,9 +591,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
   } else {
     // ===== epilogue warps =====
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int chalf = (warp - 2) >> 2;       // the two warps of a quarter take alternate 32-column chunks
+    const int cslot = (warp - 2) >> 2;       // the warps of a quarter take every (kEpiWarps/4)-th 32-column chunk
     const int row = q * 32 + lane;           // row of the 128-row MMA tile this thread drains
-    uint8_t* stage = smem_raw + (smem - smem_u32(smem_raw)) + L::EPI_OFFSET + (warp - 2) * 4096;   // this warp's staging tile
+    uint8_t* stage = smem_raw + (smem - smem_u32(smem_raw)) + L::EPI_OFFSET + (warp - 2) * 2048;   // this warp's staging tile
     constexpr int kChunks = kBlockN / 32;
     constexpr long long kSlotFloats = (long long)kMT * BLOCK_M * kBlockN;
     int wi = 0;
@@ -569,16 +616,32 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
         __syncwarp();
         epi_bar_sync();
       }
+      const long long col_base = (long long)tile_n * kBlockN;
+      const int col_limit = p.N - tile_n * kBlockN;
+      if (!contributor && (p.epi.residual || p.epi.aux_in || p.epi.accumulate)) {
+        // while the MMAs of this tile are still running: pull the epilogue's input tiles towards L2
+#pragma unroll 1
+        for (int t = 0; t < kMT; ++t) {
+          const long long m = (long long)tile_m * BM + t * BLOCK_M + row;
+          if (m >= p.M) continue;
+#pragma unroll 1
+          for (int ch = cslot; ch < kChunks; ch += kEpiWarps / 4) {
+            if (col_limit - ch * 32 <= 0) break;
+            const long long n0 = col_base + ch * 32;
+            if (p.epi.residual) prefetch_row(p.epi.residual, p.epi.ldr, p.epi.act_dtype, m, n0);
+            if (p.epi.aux_in) prefetch_row(p.epi.aux_in, p.epi.ld_aux, p.epi.act_dtype, m, n0);
+            if (p.epi.accumulate && p.epi.out_dtype == PSG_DTYPE_F32) prefetch_row(p.epi.out, p.epi.ldc, PSG_DTYPE_F32, m, n0);
+          }
+        }
+      }
       mbar_wait(bar_tfull + 8 * acc, aph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * (kMT * kBlockN);
-      const long long col_base = (long long)tile_n * kBlockN;
-      const int col_limit = p.N - tile_n * kBlockN;
 #pragma unroll 1
       for (int t = 0; t < kMT; ++t) {
         const long long m_base = (long long)tile_m * BM + t * BLOCK_M + q * 32;
 #pragma unroll 1
-        for (int ch = chalf; ch < kChunks; ch += 2) {
+        for (int ch = cslot; ch < kChunks; ch += kEpiWarps / 4) {
           uint32_t accv[32];
           tmem_ld32(tmem_acc + t * kBlockN + ((uint32_t)(q * 32) << 16) + ch * 32, accv);
           // slot layout: [chunk][float4 index j][row] -> a warp's 16-byte accesses are contiguous
@@ -605,6 +668,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
           }
           int nvalid = col_limit - ch * 32;
           nvalid = nvalid > 32 ? 32 : nvalid;
+          if (p.debug == 1) continue;
           if (m_base < p.M && nvalid > 0) epilogue_chunk(p.epi, accv, m_base, lane, p.M, col_base + ch * 32, nvalid, p.N, stage);
         }
       }
@@ -725,6 +789,10 @@ extern "C" {
 static constexpr int kMaxCtas = 160;
 static constexpr size_t kSlotBytes = (size_t)2 * 128 * 256 * sizeof(float);
 static void* g_sk_ws = nullptr;
+static int g_debug = 0;
+
+// Profiling aid for tools/bench_shapes.py: 1 = drain TMEM but skip the epilogue body (mainloop time alone).
+int psg_umma_debug(int flags) { g_debug = flags; return PSG_OK; }
 
 size_t psg_umma_workspace_bytes() { return 1024 + (size_t)kMaxCtas * kSlotBytes; }
 
@@ -842,6 +910,7 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   kp.num_m_tiles = (int)m_tiles_n;
   kp.num_n_tiles = (int)n_tiles;
   kp.num_tiles = (int)tiles;
+  kp.debug = g_debug;
   // whole waves of tiles are dealt round-robin; the remainder is the stream-K region, each CTA's share of it being at
   // least max(8, num_kb / 8) k-blocks (at most ~8 CTAs per tile: the owner adds their partials serially)
   int sms = psg_num_sms();

@@ -35,9 +35,9 @@ class Act:
         self.t, self.B, self.H, self.W = t, B, H, W
         self.grad: Optional[torch.Tensor] = None
         self.parent, self.col = parent, col
-        self.pre: Optional[torch.Tensor] = None   # saved pre-activation when this is act(pre) [+dropout]
+        self.pre: Optional[torch.Tensor] = None   # when this is drop(act(pre)): the saved local derivative act'(pre) * dropmask
         self.pre_act = L.ACT_NONE
-        self.drop = None                          # (seed, p) of an epilogue dropout applied after the activation
+        self.drop = None                          # (unused: the dropout mask is folded into `pre`)
         self.sink = None                          # (rowbias Act, bias grad) fed by the column sums of this conv output's gradient
         self.colsum_done = False                  # ... already produced by the consumer's fused GroupNorm backward
 
@@ -409,12 +409,11 @@ class UNetEngine:
             self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng, algo_flops=2.0 * dy.shape[0] * cw.cin_p * cw.k * cw.k * cw.cout_p)
 
     def _dgrad_gemm(self, a, b, tgt, res, x: Act, eng: str, alpha: float = 1.0, algo_flops=None):
-        """tgt (+)= alpha * (A B^T) [* act'(x.pre) * dropmask]  -- gradient w.r.t. the pre-activation when x carries one."""
+        """tgt (+)= alpha * (A B^T) [* act'(pre) * dropmask]  -- gradient w.r.t. the pre-activation when x carries one
+        (the forward epilogue saved that local derivative in x.pre)."""
         epi = G.Epilogue(out=tgt, residual=res, alpha=alpha)
         if x.pre is not None:
             epi.aux_in, epi.aux_act = x.pre, x.pre_act
-            if x.drop is not None:
-                epi.drop_seed, epi.drop_p = x.drop
         G.run_gemm(a, b, epi, engine=eng, algo_flops=algo_flops)
 
     # ---- linear ------------------------------------------------------------------------------------------------
@@ -437,12 +436,11 @@ class UNetEngine:
         epi.residual = res_t
         if act != L.ACT_NONE and self.taping:
             out.pre = torch.empty(x.M, N, dtype=x.t.dtype, device=self.device)
-            out.pre_act = act
+            out.pre_act = L.ACT_MUL
             epi.aux_out = out.pre
+            epi.aux_act = act          # forward side: store act'(pre) * dropmask, so that backward is one multiply
         if drop is not None:
             epi.drop_seed, epi.drop_p = drop
-            if act != L.ACT_NONE:
-                out.drop = drop
         G.run_gemm(G.kmajor(x.t), G.kmajor(bmat), epi, engine=eng)
         if self.taping:
             self.tape.append(lambda: self._linear_bwd(x, lw, out, act, alpha, residual, into, drop, x_needs_grad, eng))

@@ -149,6 +149,43 @@ def test_gemm_tn_stream_k(cuda_device, M, N, K, bn, mt):
     _close(out, 0.7 * (a.float() @ b.float().t() + bias) + res.float(), 6e-3, f"tn stream-k {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("engine", ["simt", "umma"])
+@pytest.mark.parametrize("act", ["gelu", "silu"])
+def test_epilogue_saved_derivative(cuda_device, engine, act):
+    """Forward epilogue stores act'(pre) * dropmask / (1-p) (aux_act set on the forward side); backward multiplies by it
+    (PSG_ACT_MUL).  Same rule on both engines, same dropout mask in both passes."""
+    L, G = _mods()
+    M, N, K, p = 392, 640, 320, 0.25
+    g = torch.Generator(device="cuda").manual_seed(17)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    code = L.ACT_GELU if act == "gelu" else L.ACT_SILU
+    fn = F.gelu if act == "gelu" else F.silu
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out, bias=bias, act=code, aux_out=aux, aux_act=code, drop_seed=99, drop_p=p),
+               engine=engine)
+    torch.cuda.synchronize()
+    x = (a.float() @ b.float().t() + bias).requires_grad_(True)
+    y = fn(x)
+    y.sum().backward()
+    mask = (out.float() != 0) | (y.detach().abs() < 1e-3)
+    frac = 1.0 - (out.float() != 0).float().mean().item()
+    assert abs(frac - p) < 0.02, f"dropout rate {frac}"
+    _close(out.float(), torch.where(out.float() != 0, y.detach() / (1 - p), torch.zeros_like(y)), 8e-3, f"saved-grad out {engine} {act}")
+    keep = (out.float() != 0).float()
+    sel = y.detach().abs() > 1e-3            # where the mask can be read off the output
+    _close(aux.float()[sel], (x.grad * keep / (1 - p))[sel], 8e-3, f"saved-grad aux {engine} {act}")
+    # backward: dX-like product times the saved derivative
+    o2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=o2, aux_in=aux, aux_act=L.ACT_MUL), engine=engine)
+    torch.cuda.synchronize()
+    _close(o2.float(), (a.float() @ b.float().t()) * aux.float(), 8e-3, f"saved-grad bwd {engine} {act}")
+    if engine == "umma":
+        _check_timeout(L)
+
+
 def _conv_inputs(n, h, w, cin, cout, seed, dtype):
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(dtype)            # NHWC

@@ -47,6 +47,34 @@ def wgrad(B, H, cin, cout, bn=0, mt=0):
            2.0 * B * H * H * cout * 9 * cin, f"wgrad  B={B} H={H} {cin}->{cout} bn={bn} mt={mt}")
 
 
+def epi_sweep(M=50176, N=1280, K=640):
+    from pokemon_sprite_generator_b200 import _lib as L
+    a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    res = torch.randn(M, N, device=dev).bfloat16()
+    bias = torch.randn(N, device=dev)
+    variants = {
+        "plain": dict(),
+        "bias": dict(bias=bias),
+        "bias+gelu": dict(bias=bias, act=L.ACT_GELU),
+        "bias+aux_out": dict(bias=bias, aux_out=pre),
+        "bias+gelu+aux_out": dict(bias=bias, act=L.ACT_GELU, aux_out=pre),
+        "bias+gelu+aux_out+drop": dict(bias=bias, act=L.ACT_GELU, aux_out=pre, drop_seed=123, drop_p=0.05),
+        "bias+drop": dict(bias=bias, drop_seed=123, drop_p=0.05),
+        "bias+residual": dict(bias=bias, residual=res, alpha=0.7),
+        "aux_in(gelu')+drop": dict(aux_in=pre, aux_act=L.ACT_GELU, drop_seed=123, drop_p=0.05),
+        "aux_in(gelu')": dict(aux_in=pre, aux_act=L.ACT_GELU),
+    }
+    from pokemon_sprite_generator_b200 import _lib as L2
+    L2.load().psg_umma_debug(1)
+    timeit(lambda: G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out), engine="umma"), 2.0 * M * N * K, f"EPI {M}x{N}x{K} (no epilogue: mainloop alone)")
+    timeit(lambda: G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out), engine="umma", m_tiles=2), 2.0 * M * N * K, f"EPI {M}x{N}x{K} (no epilogue, mt=2)")
+    L2.load().psg_umma_debug(0)
+    for name, kw in variants.items():
+        timeit(lambda: G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out, **kw), engine="umma"), 2.0 * M * N * K, f"EPI {M}x{N}x{K} {name}")
+
+
 B = 256
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "wgrad"):
@@ -66,3 +94,6 @@ if which in ("all", "nt"):
     for mt in (1, 2):
         nt(640, 640, 50176, 256, mt); nt(1280, 1280, 12544, 256, mt); nt(1280, 1280, 4096, 256, mt); nt(1280, 256, 8192, 256, mt)
         nt(640, 1280, 50176, 256, mt); nt(1280, 1280, 4096, 128, mt)
+if which in ("all", "epi"):
+    epi_sweep()
+    epi_sweep(50176, 640, 640)

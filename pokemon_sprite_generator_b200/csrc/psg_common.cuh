@@ -116,11 +116,11 @@ __device__ __forceinline__ float psg_ex2_approx(float x) { float r; asm("ex2.app
 // Fast forms for the bf16 tensor-core epilogues (|error| < 2e-7, far below bf16 rounding): Abramowitz-Stegun 7.1.26
 // for the normal CDF, evaluated on the tail side so that there is no cancellation; two MUFU ops (rcp, ex2) per value.
 __device__ __forceinline__ void psg_gelu_parts(float x, float& cdf, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = psg_rcp_approx(fmaf(0.3275911f, z, 1.f));
-  e = psg_ex2_approx(-1.4426950408889634f * z * z);               // exp(-x^2/2)
-  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  const float tail = 0.5f * poly * e;                             // 1 - Phi(|x|)
+  // z = |x|/sqrt(2); t = 1/(1 + p z); tail = 1 - Phi(|x|) = (poly(t)/2) * exp(-z^2), constants folded
+  const float t = psg_rcp_approx(fmaf(0.23164189f, fabsf(x), 1.f));
+  e = psg_ex2_approx(x * x * -0.72134752f);                       // exp(-x^2/2)
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.5307027145f, -0.7265760135f), 0.7107068705f), -0.142248368f), 0.127414796f);
+  const float tail = poly * e;
   cdf = x < 0.f ? tail : 1.f - tail;
 }
 __device__ __forceinline__ float psg_gelu_fast(float x) {

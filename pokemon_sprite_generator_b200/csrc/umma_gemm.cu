@@ -264,7 +264,7 @@ __device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint3
   if (!vec) {
     if (m < M) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < 32; ++j)       // (fully unrolled on purpose: a runtime index would push acc[] into local memory)
         if (j < nvalid) psg_epilogue_scalar(e, __uint_as_float(acc[j]), m, n0 + j, N);
     }
     return;

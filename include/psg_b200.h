@@ -36,6 +36,7 @@ extern "C" {
 #define PSG_OP_IM2COL 2
 #define PSG_OP_IM2COL_T 3
 #define PSG_OP_DGRAD 4
+#define PSG_OP_CONVW_T 5   /* conv weight [Cout][tap][Cin] read as B(n = cin, k = tap*Cout + cout): dgrad without a transposed copy */
 
 /* ---- library ------------------------------------------------------------------------------------------------- */
 int psg_version(void);
@@ -173,7 +174,9 @@ int psg_sum_partials(const float* partial, int splits, long long split_stride, f
 int psg_sumsq(const float* x, long long n, float* out_sumsq, int accumulate, void* workspace, void* stream);
 int psg_clip_coef(const float* sumsq, float max_norm, float* state /* [3]: norm, coef, finite */, void* stream);
 int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, long long step, const float* state, void* stream);
+                   float weight_decay, long long step, const float* state, void* bf16_shadow /* nullable: bf16 copy of p */,
+                   void* stream);
+int psg_cast_bf16(const float* x, void* y_bf16, long long n, void* stream);
 int psg_scale_inplace(float* x, long long n, const float* state, float extra, void* stream);
 
 #ifdef __cplusplus

@@ -10,6 +10,8 @@
 //   PSG_OP_IM2COL   i = output pixel (n,p,q), k = tap*C + c         (conv fprop / stride-1 dgrad, NHWC input)
 //   PSG_OP_IM2COL_T i = tap*C + c,            k = output pixel      (conv wgrad "B" operand)
 //   PSG_OP_DGRAD    i = input pixel (n,h,w),  k = tap*C + c over dY (general-stride dgrad gather; SIMT only)
+//   PSG_OP_CONVW_T  i = cin,                  k = tap*Cout + cout     (conv weight [Cout][tap][Cin] read transposed: the
+//                                                                      dgrad "B" operand; n = Cout, c = Cin; tcgen05 only)
 #pragma once
 #include "gemm_epilogue.cuh"
 
@@ -18,6 +20,7 @@
 #define PSG_OP_IM2COL 2
 #define PSG_OP_IM2COL_T 3
 #define PSG_OP_DGRAD 4
+#define PSG_OP_CONVW_T 5
 
 struct PsgOperand {
   const void* ptr;

@@ -69,10 +69,10 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
 __global__ void __launch_bounds__(kThreads)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
              float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
-             const float* __restrict__ state) {
+             const float* __restrict__ state, __nv_bfloat16* __restrict__ shadow) {
   float gscale = 1.f;
   if (state != nullptr) {
-    if (state[2] == 0.f) return;  // non-finite gradients: skip the whole step
+    if (state[2] == 0.f) return;  // non-finite gradients: skip the whole step (the bf16 shadow stays valid)
     gscale = state[1];
   }
   const float step = lr / bc1;
@@ -94,9 +94,34 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
     upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    if (shadow) {   // bf16 copy of the updated parameters in the same layout: what the tensor-core GEMMs read
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(shadow)[i] = pk;
+    }
   }
   for (size_t i = (n4 << 2) + (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
+  {
     upd(p[i], g[i], m[i], v[i]);
+    if (shadow) shadow[i] = __float2bfloat16_rn(p[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  const size_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads) {
+    const float4 v = x4[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(y)[i] = pk;
+  }
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
+    y[i] = __float2bfloat16_rn(x[i]);
 }
 
 __global__ void __launch_bounds__(kThreads) scale_kernel(float* __restrict__ x, size_t n, const float* __restrict__ state, float extra) {
@@ -135,7 +160,7 @@ int psg_clip_coef(const float* sumsq, float max_norm, float* state, void* stream
 // torch.optim.AdamW (no amsgrad) over flat buffers; `step` is the 1-based step count (bias corrections computed
 // on the host in double, as PyTorch does); state may be null (no clipping / skipping).
 int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, long long step, const float* state, void* stream) {
+                   float weight_decay, long long step, const float* state, void* bf16_shadow, void* stream) {
   PSG_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "psg_adamw_step: bad args");
   PSG_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0),
                 "psg_adamw_step: buffers must be 16B aligned");
@@ -146,8 +171,21 @@ int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, fl
   if (g_ > cap) g_ = cap;
   if (g_ < 1) g_ = 1;
   adamw_kernel<<<(int)g_, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                              (float)sqrt(bc2), state);
+                                                              (float)sqrt(bc2), state, (__nv_bfloat16*)bf16_shadow);
   PSG_CHECK_LAUNCH("psg_adamw_step");
+  return PSG_OK;
+}
+
+// y = bf16(x): refreshes the bf16 shadow of the flat parameter buffer after the parameters changed outside psg_adamw_step.
+int psg_cast_bf16(const float* x, void* y, long long n, void* stream) {
+  PSG_CHECK_ARG(x && y && n > 0, "psg_cast_bf16: bad args");
+  PSG_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 8 == 0), "psg_cast_bf16: buffers must be 16B / 8B aligned");
+  long long g_ = (n / 4 + kThreads - 1) / kThreads;
+  long long cap = (long long)psg_num_sms() * 16;
+  if (g_ > cap) g_ = cap;
+  if (g_ < 1) g_ = 1;
+  cast_bf16_kernel<<<(int)g_, kThreads, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, (size_t)n);
+  PSG_CHECK_LAUNCH("psg_cast_bf16");
   return PSG_OK;
 }
 

@@ -7,6 +7,8 @@
 //
 // kMode 0 ("TN"):  A K-major (tiled matrix or im2col pixels), B K-major matrix.   fprop / dgrad / linears.
 // kMode 1 ("NT"):  A MN-major matrix, B MN-major (tiled matrix or im2col pixels). wgrad (reduction over rows).
+// kMode 2 ("TT"):  A as kMode 0, B MN-major: the weight matrix as stored ([N_w, K_w] row-major, conv weights
+//                  [Cout][tap][Cin]) read transposed -- dgrad needs no transposed weight copy.
 //
 // Scheduling is "data-parallel + stream-K": whole waves of tiles are dealt round-robin to the persistent CTAs; the
 // remainder tiles (all tiles, when there are fewer tiles than SMs) form a stream-K region whose (tile, k-block)
@@ -47,6 +49,8 @@ struct alignas(64) KernelParams {
   int a_im2col, cblks, ksize, conv_stride, pad, flip, P, Q;
   // mode 1, B im2col (wgrad): columns are (tap, cin)
   int b_im2col, cin, tiles_per_tap;
+  // mode 2, B = conv weight [Cout][tap*Cin] read as B(n = cin, k = (tap, cout)): k-block -> (tap, 64-row block of Cout)
+  int b_tapped, b_cblks, b_tap_cols;
   PsgEpilogue epi;
 };
 
@@ -446,6 +450,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
   constexpr int BM = BLOCK_M * kMT;
   static_assert(kBlockN % 32 == 0 && kBlockN <= 256, "BLOCK_N must be a multiple of 32 (epilogue chunk) and <= 256");
   static_assert(kMode == 0 || kBlockN % 64 == 0, "MN-major B tiles are built from 64-wide TMA boxes");
+  constexpr bool kAMn = (kMode == 1), kBMn = (kMode >= 1);
   static_assert(kMT * kBlockN <= 512, "accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
         const int m0 = tile_m * BM;
         const int kb0 = sg.kb0, kb1 = sg.kb1;
         int w0[kMT], h0[kMT], img0[kMT];
-        if (kMode == 0 && p.a_im2col) {
+        if (!kAMn && p.a_im2col) {
           const int pq = p.P * p.Q;
 #pragma unroll
           for (int t = 0; t < kMT; ++t) {
@@ -504,7 +509,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
           mbar_expect_tx(full, L::STAGE_BYTES);
           const uint32_t sa = smem + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_TILE_BYTES;
-          if (kMode == 0) {
+          if (!kAMn) {
             if (p.a_im2col) {
               const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
               int r = tap / p.ksize, ss = tap - r * p.ksize;
@@ -516,32 +521,38 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
               for (int t = 0; t < kMT; ++t) tma_load_2d(sa + t * A_BYTES, &p.tm_a, full, kb * BLOCK_K, m0 + t * BLOCK_M);
             }
-            tma_load_2d(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &p.tm_a, full, m0 + 64 * j, kb * BLOCK_K);
-            if (p.b_im2col) {
-              const int pix = kb * BLOCK_K;
-              const int pq = p.P * p.Q;
-              const int img = pix / pq;
-              const int rem = pix - img * pq;
-              const int pp = rem / p.Q, qq = rem - pp * p.Q;
-              // columns are the flat (tap, cin) index; cin % 64 == 0, so every 64-wide box lies inside one tap
+          }
+          if (!kBMn) {
+            tma_load_2d(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN);
+          } else if (p.b_im2col) {
+            const int pix = kb * BLOCK_K;
+            const int pq = p.P * p.Q;
+            const int img = pix / pq;
+            const int rem = pix - img * pq;
+            const int pp = rem / p.Q, qq = rem - pp * p.Q;
+            // columns are the flat (tap, cin) index; cin % 64 == 0, so every 64-wide box lies inside one tap
 #pragma unroll
-              for (int j = 0; j < kBlockN / 64; ++j) {
-                const int col = tile_n * kBlockN + 64 * j;
-                int tap = col / p.cin;
-                int c0 = col - tap * p.cin;
-                if (tap >= p.ksize * p.ksize) { tap = 0; c0 = p.cin; }     // past the last tap: channel OOB -> zero fill
-                const int r = tap / p.ksize, ss = tap - r * p.ksize;
-                tma_load_im2col_4d(sb + j * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
-                                   (uint16_t)ss, (uint16_t)r);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < kBlockN / 64; ++j)
-                tma_load_2d(sb + j * 8192, &p.tm_b, full, tile_n * kBlockN + 64 * j, kb * BLOCK_K);
+            for (int j = 0; j < kBlockN / 64; ++j) {
+              const int col = tile_n * kBlockN + 64 * j;
+              int tap = col / p.cin;
+              int c0 = col - tap * p.cin;
+              if (tap >= p.ksize * p.ksize) { tap = 0; c0 = p.cin; }     // past the last tap: channel OOB -> zero fill
+              const int r = tap / p.ksize, ss = tap - r * p.ksize;
+              tma_load_im2col_4d(sb + j * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
+                                 (uint16_t)ss, (uint16_t)r);
             }
+          } else {
+            int row = kb * BLOCK_K, col0 = tile_n * kBlockN;
+            if (p.b_tapped) {          // k-block = (tap, 64 rows of Cout); the tap selects a column band of the weight matrix
+              const int tap = kb / p.b_cblks;
+              row = (kb - tap * p.b_cblks) * BLOCK_K;
+              col0 += tap * p.b_tap_cols;
+            }
+#pragma unroll
+            for (int j = 0; j < kBlockN / 64; ++j) tma_load_2d(sb + j * 8192, &p.tm_b, full, col0 + 64 * j, row);
           }
         }
       }
@@ -550,7 +561,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(kBlockN, kMode, kMode);
+      constexpr uint32_t idesc = make_idesc(kBlockN, kAMn ? 1 : 0, kBMn ? 1 : 0);
       uint32_t it = 0;
       int wi = 0;   // local segment counter -> accumulator stage and phase
       PSG_SEGMENTS(p);
@@ -572,13 +583,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             uint64_t bd;
-            if (kMode == 0) bd = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            else            bd = make_desc(sb + k * (UMMA_K * 128), 8192, 1024);
+            if (!kBMn) bd = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            else       bd = make_desc(sb + k * (UMMA_K * 128), 8192, 1024);
 #pragma unroll
             for (int t = 0; t < kMT; ++t) {
               uint64_t ad;
-              if (kMode == 0) ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 2), 16, 1024);
-              else            ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 128), 8192, 1024);
+              if (!kAMn) ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 2), 16, 1024);
+              else       ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 128), 8192, 1024);
               umma_bf16(tmem_acc + t * kBlockN, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
@@ -813,7 +824,7 @@ static void plan_tiles(int mode, long long M, long long N, long long K, int* blo
       else if (N % 160 == 0) bn = 160;
       else bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
     } else {
-      bn = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+      bn = N > 128 ? 256 : (N > 64 ? 128 : 64);      // MN-major B: tiles are built from 64-wide boxes
     }
   }
   int mt = *m_tiles;
@@ -832,7 +843,7 @@ static void plan_tiles(int mode, long long M, long long N, long long K, int* blo
 // Reports the tile shape psg_umma_gemm would use for this problem (block_n / m_tiles: in = request or 0, out = choice).
 int psg_umma_plan(const PsgGemmDesc* d, int* block_n, int* m_tiles) {
   PSG_CHECK_ARG(d && block_n && m_tiles, "psg_umma_plan: null pointer");
-  const int mode = (d->a.mode == PSG_OP_MNMAJOR) ? 1 : 0;
+  const int mode = (d->a.mode == PSG_OP_MNMAJOR) ? 1 : ((d->b.mode == PSG_OP_MNMAJOR || d->b.mode == PSG_OP_CONVW_T) ? 2 : 0);
   plan_tiles(mode, d->M, d->N, d->K, block_n, m_tiles);
   return PSG_OK;
 }
@@ -847,6 +858,7 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   int mode;
   if ((am == PSG_OP_KMAJOR || am == PSG_OP_IM2COL) && bm == PSG_OP_KMAJOR) mode = 0;
   else if (am == PSG_OP_MNMAJOR && (bm == PSG_OP_MNMAJOR || bm == PSG_OP_IM2COL_T)) mode = 1;
+  else if ((am == PSG_OP_KMAJOR || am == PSG_OP_IM2COL) && (bm == PSG_OP_MNMAJOR || bm == PSG_OP_CONVW_T)) mode = 2;
   else { psg_set_error("psg_umma_gemm: unsupported operand modes a=%d b=%d", am, bm); return PSG_ERR_UNSUPPORTED; }
   PSG_CHECK_ARG(((uintptr_t)d->a.ptr % 16 == 0) && ((uintptr_t)d->b.ptr % 16 == 0), "psg_umma_gemm: operands must be 16B aligned");
   PSG_CHECK_ARG((d->a.ld % 8 == 0) && (d->b.ld % 8 == 0), "psg_umma_gemm: pitches must be multiples of 8 elements");
@@ -862,8 +874,10 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   PSG_CHECK_ARG(d->split_k <= 1, "psg_umma_gemm: split-K is gone (stream-K scheduling balances the k-range itself)");
   plan_tiles(mode, d->M, d->N, d->K, &block_n, &m_tiles);
 
-  long long n_tiles;
-  if (mode == 0) {
+  long long n_tiles = (d->N + block_n - 1) / block_n;
+  kp.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
+  // ---- A operand ----
+  if (mode != 1) {
     if (am == PSG_OP_IM2COL) {
       const PsgOperand& a = d->a;
       PSG_CHECK_ARG(a.c % 64 == 0, "psg_umma_gemm: im2col needs C %% 64 == 0 (C=%d)", a.c);
@@ -878,15 +892,16 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
       rc = make_tiled_map(&kp.tm_a, d->a.ptr, d->M, d->K, d->a.ld, 64, BLOCK_M);
       if (rc) return rc;
     }
+  } else {
+    rc = make_tiled_map(&kp.tm_a, d->a.ptr, d->K, d->M, d->a.ld, 64, 64);     // A: [K rows][M cols]
+    if (rc) return rc;
+  }
+  // ---- B operand ----
+  if (mode == 0) {
     rc = make_tiled_map(&kp.tm_b, d->b.ptr, d->N, d->K, d->b.ld, 64, block_n);
     if (rc) return rc;
-    kp.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
-    n_tiles = (d->N + block_n - 1) / block_n;
   } else {
     PSG_CHECK_ARG(block_n % 64 == 0, "psg_umma_gemm: MN-major B needs block_n %% 64 == 0");
-    // A: [K rows][M cols]
-    rc = make_tiled_map(&kp.tm_a, d->a.ptr, d->K, d->M, d->a.ld, 64, 64);
-    if (rc) return rc;
     if (bm == PSG_OP_IM2COL_T) {
       const PsgOperand& b = d->b;
       PSG_CHECK_ARG(d->N == (long long)b.ksize * b.ksize * b.c, "psg_umma_gemm: N != ksize^2*C");
@@ -896,13 +911,21 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
       if (rc) return rc;
       kp.b_im2col = 1; kp.cin = b.c; kp.tiles_per_tap = 0;
       kp.ksize = b.ksize; kp.conv_stride = b.stride; kp.pad = b.pad; kp.P = b.p; kp.Q = b.q;
-      n_tiles = (d->N + block_n - 1) / block_n;
-    } else {
-      rc = make_tiled_map(&kp.tm_b, d->b.ptr, d->K, d->N, d->b.ld, 64, 64);
+    } else if (bm == PSG_OP_CONVW_T) {
+      // conv weight [Cout = b.n][taps * Cin], Cin = b.c: B(n = cin, k = tap * Cout + cout)
+      const PsgOperand& b = d->b;
+      const int taps = b.ksize * b.ksize;
+      PSG_CHECK_ARG(b.n % 64 == 0, "psg_umma_gemm: transposed conv weight needs Cout %% 64 == 0 (Cout=%d)", b.n);
+      PSG_CHECK_ARG(d->N == b.c && d->K == (long long)taps * b.n, "psg_umma_gemm: transposed conv weight: N != Cin or K != taps*Cout");
+      PSG_CHECK_ARG(mode == 2 && am == PSG_OP_IM2COL && d->a.c == b.n && d->a.ksize == b.ksize,
+                    "psg_umma_gemm: transposed conv weight pairs with an im2col A over Cout channels");
+      rc = make_tiled_map(&kp.tm_b, b.ptr, b.n, (long long)taps * b.c, b.ld, 64, 64);
       if (rc) return rc;
-      n_tiles = (d->N + block_n - 1) / block_n;
+      kp.b_tapped = 1; kp.b_cblks = b.n / 64; kp.b_tap_cols = b.c;
+    } else {
+      rc = make_tiled_map(&kp.tm_b, d->b.ptr, d->K, d->N, d->b.ld, 64, 64);   // B: [K rows][N cols]
+      if (rc) return rc;
     }
-    kp.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
   }
   const long long m_tiles_n = (d->M + BLOCK_M * m_tiles - 1) / (BLOCK_M * m_tiles);
   const long long tiles = m_tiles_n * n_tiles;
@@ -946,11 +969,17 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
       case 160: PSG_LAUNCH(160, 5, 3, 0);
       case 256: PSG_LAUNCH(256, 4, 3, 0);
     }
-  } else {
+  } else if (mode == 1) {
     switch (block_n) {
       case 64: PSG_LAUNCH(64, 6, 4, 1);
       case 128: PSG_LAUNCH(128, 6, 4, 1);
       case 256: PSG_LAUNCH(256, 4, 3, 1);
+    }
+  } else {
+    switch (block_n) {
+      case 64: PSG_LAUNCH(64, 6, 4, 2);
+      case 128: PSG_LAUNCH(128, 6, 4, 2);
+      case 256: PSG_LAUNCH(256, 4, 3, 2);
     }
   }
 #undef PSG_LAUNCH

@@ -79,6 +79,10 @@ class ConvW:
         self.cin_p = (self.cin + 63) // 64 * 64 if pad_channels else self.cin
         self.cout_p = (self.cout + 63) // 64 * 64 if pad_channels else self.cout
         self.padded = (self.cin_p != self.cin) or (self.cout_p != self.cout)
+        # tensor-core mode, tileable channels: the weight lives tap-major in the flat buffers and the GEMMs read its bf16
+        # shadow in place (fprop: K-major [Cout, taps*Cin]; dgrad: the same matrix read transposed; wgrad writes the
+        # gradient matrix directly) -- no packing pass, no transposed copy, no finalize pass
+        self.in_place = pad_channels and not self.padded and self.k > 1
 
 
 class LinW:
@@ -123,11 +127,19 @@ class NormW:
 class ParamStore:
     """Flat fp32 parameter / gradient buffers; every nn.Parameter's .data is a view into `flat`."""
 
-    def __init__(self, module: nn.Module, front: Optional[List[nn.Parameter]] = None):
+    def __init__(self, module: nn.Module, front: Optional[List[nn.Parameter]] = None,
+                 tap_major: Optional[List[nn.Parameter]] = None, shadow: bool = False):
         """`front`: parameters laid out first, contiguously and in the given order (the ResBlock conditioning
         projections, so that all time_proj / text_proj weights form one [sum C, K] matrix each); every other parameter
-        follows in registration order."""
+        follows in registration order.
+        `tap_major`: conv weights stored physically as [Cout][kh][kw][Cin] (channels-last memory format): `.data` keeps
+        the logical OIHW shape through a permuted view, so state_dict / optimisers / autograd see the reference layout
+        while the implicit-GEMM kernels read (and write gradients to) the buffer as a [Cout, taps*Cin] matrix in place.
+        `shadow`: keep a bf16 copy of the flat buffer (same offsets) for the tensor-core GEMMs."""
         self.module = module
+        self.tap_major = {id(p) for p in (tap_major or [])}
+        self.want_shadow = shadow
+        self.shadow: Optional[torch.Tensor] = None
         named = list(module.named_parameters())
         name_of = {id(p): n for n, p in named}
         front = list(front or [])
@@ -159,21 +171,34 @@ class ParamStore:
         flat = torch.zeros(self.total, dtype=torch.float32, device=device)
         with torch.no_grad():
             for name, p in self.named:
-                off, n = self.offsets[name], p.numel()
-                view = flat[off:off + n].view(p.shape)
+                view = self._view(flat, p, self.offsets[name])
                 view.copy_(p.data.to(device=device, dtype=torch.float32))
                 p.data = view
         self.flat = flat
+        self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=device) if self.want_shadow else None
         self.grads = torch.zeros(self.total, dtype=torch.float32, device=device)
         self._index_grads()
         self.generation += 1
         return True
 
+    def _view(self, buf: torch.Tensor, p: nn.Parameter, off: int) -> torch.Tensor:
+        """The view of `buf` that is parameter p (logical shape; tap-major conv weights through a permute)."""
+        n = p.numel()
+        if id(p) in self.tap_major:
+            co, ci, kh, kw = p.shape
+            return buf[off:off + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        return buf[off:off + n].view(p.shape)
+
+    def matrix(self, buf: torch.Tensor, p: nn.Parameter) -> torch.Tensor:
+        """Physical [rows, cols] matrix of p inside `buf` (flat / grads / shadow): [Cout, taps*Cin] for tap-major conv
+        weights, [shape[0], rest] otherwise."""
+        off = self.offset_of(p)
+        return buf[off:off + p.numel()].view(p.shape[0], -1)
+
     def _index_grads(self):
         self._by_id = {}
         for name, p in self.named:
-            off, n = self.offsets[name], p.numel()
-            self._by_id[id(p)] = self.grads[off:off + n].view(p.shape)
+            self._by_id[id(p)] = self._view(self.grads, p, self.offsets[name])
 
     def fresh_grads(self):
         """Detach the current gradient buffer (it may be referenced by p.grad) and start a new one."""
@@ -203,6 +228,7 @@ class UNetEngine:
         self.bf16 = compute_dtype == torch.bfloat16
         self._packed_version = None
         self._packed_generation = None
+        self._edges_dirty = False
         self._build_descriptors()
         self.step_counter = 0
         self.dropout_enabled = True      # honoured only in train() mode
@@ -269,7 +295,7 @@ class UNetEngine:
                  [rb.time_proj.bias for rb in res_blocks] + [rb.text_proj.bias for rb in res_blocks])
         for p in front:
             assert p.numel() % ALIGN == 0, "conditioning projections must tile the flat buffer without padding"
-        self.store = ParamStore(u, front=front)
+        self.store = ParamStore(u, front=front, tap_major=[c.mod.weight for c in self.convs if c.in_place], shadow=self.bf16)
         self.cond_width = sum(rb.out_channels for rb in res_blocks)
         rb0 = res_blocks[0]
         self.d_cond_time = FlatLinW(rb0.time_proj.weight, rb0.time_proj.bias, self.cond_width, rb0.time_proj.in_features)
@@ -279,12 +305,23 @@ class UNetEngine:
     # weights
     # ------------------------------------------------------------------------------------------------------------
     def prepare(self, device) -> None:
-        """Flatten parameters if needed and refresh the packed kernel-layout weight copies if they changed."""
-        rebuilt = self.store.ensure_flat(device)
-        ver = self.store.version()
-        if not rebuilt and self._packed_version == ver and self._packed_generation == self.store.generation:
+        """Flatten parameters if needed and refresh the kernel-side weight copies if they changed.
+        bf16 mode: one cast pass flat fp32 -> bf16 shadow (skipped when the fused AdamW already wrote it) plus a re-pack
+        of the two channel-padded edge convs; fp32 parity mode: re-pack every conv (fprop / dgrad layouts)."""
+        store = self.store
+        rebuilt = store.ensure_flat(device)
+        ver = store.version()
+        stale = rebuilt or self._packed_version != ver or self._packed_generation != store.generation
+        if not stale and not self._edges_dirty:
             return
+        if self.bf16 and stale:
+            K.cast_bf16(store.flat, store.shadow)
         for c in self.convs:
+            if c.in_place:
+                if stale:
+                    c.wp = store.matrix(store.shadow, c.mod.weight)
+                    c.wd = None
+                continue
             w = c.mod.weight.data
             if c.wp is None or c.wp.device != device:
                 c.wp = torch.zeros(c.cout_p, c.k * c.k * c.cin_p, dtype=self.dtype, device=device)
@@ -293,31 +330,24 @@ class UNetEngine:
             K.pack_conv_weight(w, c.wp, c.wd, c.cin_p, c.cout_p)
             if c.bias_p is not None:
                 K.copy_strided(c.mod.bias.data.view(1, c.cout), c.bias_p[:, :c.cout])
-        if self.bf16:
-            done = {}
+        if self.bf16 and stale:
             for l in self.lins:
-                key = id(l.weight)
-                if key not in done:
-                    w = l.weight.data
-                    w2 = w.view(w.shape[0], -1)
-                    cached = getattr(l.weight, "_psg_pack", None)
-                    if cached is None or cached[0].device != device:
-                        cached = (torch.empty(w2.shape, dtype=self.dtype, device=device),
-                                  torch.empty(w2.shape[1], w2.shape[0], dtype=self.dtype, device=device))
-                        l.weight._psg_pack = cached
-                    K.pack_linear_weight(w2, cached[0], cached[1])
-                    done[key] = cached
-                wk, wt = done[key]
+                wk = store.matrix(store.shadow, l.weight)
                 if l.rows is not None:
                     a, e = l.rows
-                    wk, wt = wk[a:e], wt[:, a:e]
-                l.wk, l.wt = wk, wt
-        self._packed_version = self.store.version()
-        self._packed_generation = self.store.generation
+                    wk = wk[a:e]
+                l.wk, l.wt = wk, None
+        self._edges_dirty = False
+        self._packed_version = store.version()
+        self._packed_generation = store.generation
 
     def mark_params_dirty(self) -> None:
-        """Call after updating the flat parameter buffer outside of torch (fused optimiser): forces a re-pack."""
+        """Call after updating the flat parameter buffer outside of torch: forces a full refresh of the kernel-side copies."""
         self._packed_version = None
+
+    def mark_shadow_fresh(self) -> None:
+        """Call after a fused optimiser step that rewrote the bf16 shadow itself: only the edge convs need re-packing."""
+        self._edges_dirty = True
 
     # ------------------------------------------------------------------------------------------------------------
     # primitive ops (forward + tape entry)
@@ -385,19 +415,23 @@ class UNetEngine:
         kk = cw.k * cw.k
         ncols = kk * cw.cin_p
         a_op, b_op = G.mnmajor(dy), G.im2col_t(x.nhwc(), cw.k, cw.stride, cw.pad)
-        nel = cw.cout_p * ncols
-        part = K.workspace(self.device, nel, "wgrad").narrow(0, 0, nel).view(1, cw.cout_p, ncols)
-        G.run_gemm(a_op, b_op, G.Epilogue(out=part[0]), engine=eng)      # stream-K balances the long pixel reduction
-        K.wgrad_finalize(part, 1, nel, gw, cin_p=cw.cin_p)
+        if cw.in_place:     # the gradient buffer IS the [Cout, taps*Cin] matrix the GEMM produces (stream-K: no split pass)
+            G.run_gemm(a_op, b_op, G.Epilogue(out=self.store.matrix(self.store.grads, cw.mod.weight)), engine=eng)
+        else:
+            nel = cw.cout_p * ncols
+            part = K.workspace(self.device, nel, "wgrad").narrow(0, 0, nel).view(1, cw.cout_p, ncols)
+            G.run_gemm(a_op, b_op, G.Epilogue(out=part[0]), engine=eng)
+            K.wgrad_finalize(part, 1, nel, gw, cin_p=cw.cin_p)
         if not x_needs_grad:
             return
         # dgrad
         tgt, acc = self._grad_target(x) if x.parent is None else (x.g(), False)
         res = tgt if acc else None
         dy4 = Act.nhwc_of(dy, out.B, out.H, out.W)
+        wd_op = G.convw_t(cw.wp, cw.cin, cw.k) if cw.in_place else G.kmajor(cw.wd)
         if cw.stride == 1:
             a = G.im2col(dy4, cw.k, 1, cw.pad, flip=True)
-            self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng)
+            self._dgrad_gemm(a, wd_op, tgt, res, x, eng)
         elif eng == "simt":
             a = G.dgrad_gather(dy4, x.H, x.W, cw.k, cw.stride, cw.pad)
             self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng)
@@ -406,7 +440,7 @@ class UNetEngine:
             dil = torch.empty(x.B * x.H * x.W, cw.cout_p, dtype=dy.dtype, device=dy.device)
             K.dilate2(dy, dil, x.B, out.H, out.W, x.H, x.W)
             a = G.im2col(Act.nhwc_of(dil, x.B, x.H, x.W), cw.k, 1, cw.pad, flip=True)
-            self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng, algo_flops=2.0 * dy.shape[0] * cw.cin_p * cw.k * cw.k * cw.cout_p)
+            self._dgrad_gemm(a, wd_op, tgt, res, x, eng, algo_flops=2.0 * dy.shape[0] * cw.cin_p * cw.k * cw.k * cw.cout_p)
 
     def _dgrad_gemm(self, a, b, tgt, res, x: Act, eng: str, alpha: float = 1.0, algo_flops=None):
         """tgt (+)= alpha * (A B^T) [* act'(pre) * dropmask]  -- gradient w.r.t. the pre-activation when x carries one
@@ -467,7 +501,7 @@ class UNetEngine:
         if not x_needs_grad:
             return
         tgt, acc = self._grad_target(x) if x.parent is None else (x.g(), False)
-        bop = G.mnmajor(w2) if fp32 else G.kmajor(lw.wt)
+        bop = G.mnmajor(w2) if fp32 else G.mnmajor(lw.wk)      # the [N, K] weight read transposed in place
         if eng == "simt" and x.pre is None and scale == 1.0 and tgt.dtype == torch.float32 and tgt.is_contiguous() \
                 and N >= 2048 and x.M * Kd <= 256 * 512:
             # skinny dgrad with a long reduction (the all-blocks conditioning projection): split-K over the CUDA-core engine

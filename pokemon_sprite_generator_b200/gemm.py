@@ -66,6 +66,14 @@ def im2col_t(x: torch.Tensor, ksize: int, stride: int, pad: int) -> Operand:
     return Operand(x, L.OP_IM2COL_T, ld, ksize * ksize * c, n * p * q, (n, h, w, c, p, q, stride, pad, ksize, 0))
 
 
+def convw_t(w2: torch.Tensor, cin: int, ksize: int) -> Operand:
+    """Conv weight stored [Cout, ksize^2 * Cin] (tap-major, channels innermost) read transposed: rows = cin,
+    K = (tap, cout) -- the dgrad "B" operand, no transposed copy needed (tcgen05 engine only)."""
+    assert w2.dim() == 2 and w2.stride(1) == 1 and w2.shape[1] == ksize * ksize * cin, (w2.shape, cin, ksize)
+    cout = w2.shape[0]
+    return Operand(w2, L.OP_CONVW_T, w2.stride(0), cin, ksize * ksize * cout, (cout, 0, 0, cin, 0, 0, 1, 0, ksize, 0))
+
+
 def dgrad_gather(dy: torch.Tensor, in_h: int, in_w: int, ksize: int, stride: int, pad: int) -> Operand:
     """rows = conv input pixels; K = ksize^2 * Cout gathered from NHWC `dy` (general stride; SIMT engine only)."""
     n, h, w, c, ld = _nhwc_geom(dy)

@@ -248,9 +248,17 @@ def clip_coef(sumsq_t: torch.Tensor, max_norm: float, state: torch.Tensor) -> No
     L.call("psg_clip_coef", L.ptr(sumsq_t), C.c_float(max_norm), L.ptr(state), L.stream_ptr())
 
 
-def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step: int, state: torch.Tensor | None) -> None:
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step: int, state: torch.Tensor | None,
+               shadow: torch.Tensor | None = None) -> None:
+    """shadow: optional bf16 buffer of p's size, rewritten with the updated parameters (what the tensor-core GEMMs read)."""
+    assert shadow is None or (shadow.dtype == torch.bfloat16 and shadow.numel() == p.numel())
     L.call("psg_adamw_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), C.c_longlong(p.numel()), C.c_float(lr), C.c_float(beta1),
-           C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), L.ptr(state), L.stream_ptr())
+           C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), L.ptr(state), L.ptr(shadow), L.stream_ptr())
+
+
+def cast_bf16(x: torch.Tensor, y: torch.Tensor) -> None:
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.numel() == y.numel() and x.is_contiguous() and y.is_contiguous()
+    L.call("psg_cast_bf16", L.ptr(x), L.ptr(y), C.c_longlong(x.numel()), L.stream_ptr())
 
 
 def scale_inplace(x: torch.Tensor, state: torch.Tensor | None, extra: float = 1.0) -> None:

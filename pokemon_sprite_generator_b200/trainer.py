@@ -76,8 +76,11 @@ class FusedAdamW(torch.optim.Optimizer):
         if not self.decoupled and wd != 0.0:
             raise L.PsgError("FusedAdamW: coupled (Adam-style) weight decay is not implemented; use adamw=True")
         K.adamw_step(store.flat, store.grads, self._m, self._v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], wd,
-                     self.step_count, self.clip_state)
-        eng.mark_params_dirty()
+                     self.step_count, self.clip_state, shadow=store.shadow)
+        if store.shadow is not None:
+            eng.mark_shadow_fresh()     # the kernel rewrote the bf16 shadow the GEMMs read
+        else:
+            eng.mark_params_dirty()
         return None
 
     def zero_grad(self, set_to_none: bool = True):

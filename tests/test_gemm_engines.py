@@ -265,6 +265,35 @@ def test_conv_wgrad(cuda_device, engine, dtype, n, h, cin, cout, stride, split):
     _close(dw, ref, 1e-4, f"wgrad {engine} h{h} {cin}->{cout} s{stride} split{split}")
 
 
+@pytest.mark.parametrize("M,N,K,bn,mt", [(392, 640, 1280, 0, 0), (12544, 1280, 2560, 256, 2), (1000, 320, 640, 0, 0), (300, 96, 128, 0, 0)])
+def test_gemm_tt_weight_in_place(cuda_device, M, N, K, bn, mt):
+    """dgrad of a Linear with the [N_w, K_w] weight read transposed in place (A K-major, B MN-major)."""
+    L, G = _mods()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    dy = torch.randn(M, K, device="cuda", generator=g).bfloat16()                       # K = N_w
+    w = (torch.randn(K, N, device="cuda", generator=g) / K ** 0.5).bfloat16()           # weight [N_w, K_w]: here [K, N]
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.kmajor(dy), G.mnmajor(w), G.Epilogue(out=out), engine="umma", block_n=bn, m_tiles=mt)
+    torch.cuda.synchronize()
+    _check_timeout(L)
+    _close(out, dy.float() @ w.float(), 6e-3, f"tt {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("n,h,cin,cout", [(2, 27, 320, 320), (3, 14, 640, 320), (8, 7, 1280, 1280), (5, 4, 128, 64), (2, 14, 64, 640)])
+def test_conv_dgrad_weight_in_place(cuda_device, n, h, cin, cout):
+    """Stride-1 dgrad with the fprop weight matrix [Cout][tap][Cin] read transposed in place (PSG_OP_CONVW_T)."""
+    L, G = _mods()
+    x, wt = _conv_inputs(n, h, h, cin, cout, 91 + h + cin, torch.bfloat16)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    dy = torch.randn(n, h, h, cout, device="cuda").bfloat16()
+    dx = torch.full((n * h * h, cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.run_gemm(G.im2col(dy, 3, 1, 1, flip=True), G.convw_t(wp, cin, 3), G.Epilogue(out=dx), engine="umma")
+    torch.cuda.synchronize()
+    _check_timeout(L)
+    ref = torch.nn.grad.conv2d_input((n, cin, h, h), wt.float(), dy.float().permute(0, 3, 1, 2), stride=1, padding=1)
+    _close(dx, ref.permute(0, 2, 3, 1).reshape(-1, cin), 6e-3, f"dgrad in place h{h} {cin}<-{cout}")
+
+
 def test_strided_views(cuda_device):
     """Operands and outputs that are channel slices of wider (concat) buffers."""
     L, G = _mods()

@@ -46,7 +46,7 @@ agg = collections.defaultdict(lambda: [0.0, 0])
 for name, a, b in calls:
     agg[name][0] += a.elapsed_time(b)
     agg[name][1] += 1
-MODE = {0: "K", 1: "MN", 2: "im2col", 3: "im2colT", 4: "dgrad"}
+MODE = {0: "K", 1: "MN", 2: "im2col", 3: "im2colT", 4: "dgrad", 5: "convwT"}
 gagg = collections.defaultdict(lambda: [0.0, 0, 0.0])
 for a, b, fl, eng, (am, bm, M, N, Kd, sp) in gemms:
     key = f"gemm:{eng}:{MODE[am]}x{MODE[bm]}"

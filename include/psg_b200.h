@@ -102,6 +102,17 @@ int psg_smooth_l1_fwd_bwd(const float* pred, const float* target, float* dpred, 
 int psg_ddpm_step(const float* x, const float* eps, const float* z, float* out, long long n, int mode, const float* tab0,
                   const float* tab1, const float* tab2, const float* tab3, int t, int num_t, void* stream);
 
+/* ---- fused tensor-core attention (bf16): scores stay on chip, forward saves only the row log-sum-exp ------------------
+ * replaces the nn.MultiheadAttention core, src/models/unet.py:160-173,217,235 (softmax over keys, dropout on probabilities) */
+int psg_attn_fused_ok(int B, int H, int Lq, int Lk, int hd);
+int psg_attn_fused_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                       float* lse, int B, int H, int Lq, int Lk, int hd, float scale, unsigned long long drop_seed, float drop_p,
+                       void* stream);
+int psg_attn_fused_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,
+                       long long ldo, const void* dout, long long lddo, const float* lse, float* delta, void* dq, long long lddq,
+                       void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Lq, int Lk, int hd, float scale,
+                       unsigned long long drop_seed, float drop_p, void* stream);
+
 /* ---- GroupNorm (+SiLU)  nn.GroupNorm + F.silu, src/models/unet.py:79,89,115,127,156-157,214,231,397-398 ---------- */
 int psg_groupnorm_slices(int B, int HW);
 int psg_groupnorm_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,

@@ -560,7 +560,11 @@ class UNetEngine:
         p = drop_p if (self.training and self.dropout_enabled) else 0.0
         seed = self._seed(site)
         tensor_core = q.t.dtype == torch.bfloat16 and lk <= 1024
-        if tensor_core:
+        fused = q.t.dtype == torch.bfloat16 and K.attn_fused_ok(q.B, heads, lq, lk, hd)
+        if fused:
+            lse = torch.empty(q.B, heads, lq, dtype=torch.float32, device=self.device) if self.taping else None
+            K.attn_fused_fwd(q.t, k.t, v.t, o.t, lse, q.B, heads, lq, lk, hd, seed, p)
+        elif tensor_core:
             P = K.attn_tc_fwd(q.t, k.t, v.t, o.t, q.B, heads, lq, lk, hd, seed, p)
             lse = None
         else:
@@ -572,7 +576,9 @@ class UNetEngine:
                     par = a.parent if a.parent is not None else a
                     if par.grad is None:
                         par.grad = torch.empty(par.M, par.C, dtype=par.t.dtype, device=self.device)
-                if tensor_core:
+                if fused:
+                    K.attn_fused_bwd(q.t, k.t, v.t, o.t, o.g(), lse, q.g(), k.g(), v.g(), q.B, heads, lq, lk, hd, seed, p)
+                elif tensor_core:
                     K.attn_tc_bwd(q.t, k.t, v.t, o.g(), P, q.g(), k.g(), v.g(), q.B, heads, lq, lk, hd, seed, p)
                 else:
                     K.attn_bwd(q.t, k.t, v.t, o.t, o.g(), lse, q.g(), k.g(), v.g(), q.B, heads, lq, lk, hd, seed, p)

@@ -195,6 +195,34 @@ def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, b: int, heads: int, lq: int, lk: i
            C.c_float(1.0 / (hd ** 0.5)), C.c_int(L.dt(q)), C.c_ulonglong(drop_seed), C.c_float(drop_p), L.stream_ptr())
 
 
+# ---- fused tensor-core attention (bf16): scores never leave the chip --------------------------------------------------
+_attn_fused_cache = {}
+
+
+def attn_fused_ok(b: int, heads: int, lq: int, lk: int, hd: int) -> bool:
+    key = (b, heads, lq, lk, hd)
+    ok = _attn_fused_cache.get(key)
+    if ok is None:
+        ok = bool(L.load().psg_attn_fused_ok(C.c_int(b), C.c_int(heads), C.c_int(lq), C.c_int(lk), C.c_int(hd)))
+        _attn_fused_cache[key] = ok
+    return ok
+
+
+def attn_fused_fwd(q, k, v, o, lse, b: int, heads: int, lq: int, lk: int, hd: int, drop_seed: int = 0, drop_p: float = 0.0) -> None:
+    L.call("psg_attn_fused_fwd", L.ptr(q), C.c_longlong(_ld(q)), L.ptr(k), C.c_longlong(_ld(k)), L.ptr(v), C.c_longlong(_ld(v)), L.ptr(o),
+           C.c_longlong(_ld(o)), L.ptr(lse), C.c_int(b), C.c_int(heads), C.c_int(lq), C.c_int(lk), C.c_int(hd),
+           C.c_float(1.0 / (hd ** 0.5)), C.c_ulonglong(drop_seed), C.c_float(drop_p), L.stream_ptr())
+
+
+def attn_fused_bwd(q, k, v, o, do, lse, dq, dk, dv, b: int, heads: int, lq: int, lk: int, hd: int, drop_seed: int = 0,
+                   drop_p: float = 0.0) -> None:
+    delta = workspace(q.device, b * heads * lq, "attn_dsum")
+    L.call("psg_attn_fused_bwd", L.ptr(q), C.c_longlong(_ld(q)), L.ptr(k), C.c_longlong(_ld(k)), L.ptr(v), C.c_longlong(_ld(v)), L.ptr(o),
+           C.c_longlong(_ld(o)), L.ptr(do), C.c_longlong(_ld(do)), L.ptr(lse), L.ptr(delta), L.ptr(dq), C.c_longlong(_ld(dq)), L.ptr(dk),
+           C.c_longlong(_ld(dk)), L.ptr(dv), C.c_longlong(_ld(dv)), C.c_int(b), C.c_int(heads), C.c_int(lq), C.c_int(lk), C.c_int(hd),
+           C.c_float(1.0 / (hd ** 0.5)), C.c_ulonglong(drop_seed), C.c_float(drop_p), L.stream_ptr())
+
+
 # ---- tensor-core attention (bf16): batched mma.sync GEMMs + row softmax ------------------------------------------
 def _bmm(a, a_sb, a_sh, lda, ta, b, b_sb, b_sh, ldb, tb, c, c_sb, c_sh, ldc, batch, heads, m, n, k, alpha):
     L.call("psg_bmm_bf16", L.ptr(a), C.c_longlong(a_sb), C.c_longlong(a_sh), C.c_longlong(lda), C.c_int(ta), L.ptr(b),

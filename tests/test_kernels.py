@@ -322,3 +322,52 @@ def test_attention_tensor_core(cuda_device, B, H, Lq, Lk, hd, p):
     _cmp(dkv[:, :C_], k.grad.transpose(1, 2).reshape(B * Lk, C_), dtype, "tc dk", 2.0)
     _cmp(dkv[:, C_:], v.grad.transpose(1, 2).reshape(B * Lk, C_), dtype, "tc dv", 2.0)
     assert dqkv[:, C_:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,hd,p", [(2, 4, 196, 196, 160, 0.0), (2, 8, 196, 196, 80, 0.0), (3, 4, 196, 32, 160, 0.0), (3, 4, 49, 49, 320, 0.0),
+                                            (2, 8, 49, 77, 160, 0.0), (2, 4, 16, 16, 320, 0.0), (2, 4, 16, 7, 320, 0.0), (5, 8, 100, 70, 48, 0.0),
+                                            (2, 4, 49, 32, 320, 0.25), (2, 8, 196, 64, 80, 0.25)])
+def test_attention_fused(cuda_device, B, H, Lq, Lk, hd, p):
+    """Fused bf16 attention (scores on chip, LSE saved, probabilities recomputed in backward) vs an fp32 PyTorch reference."""
+    K = _ops()
+    dtype = torch.bfloat16
+    assert K.attn_fused_ok(B, H, Lq, Lk, hd)
+    C_ = H * hd
+    g = torch.Generator(device="cuda").manual_seed(Lq * Lk + hd + 2)
+    qkv = torch.randn(B * Lq, 3 * C_, device="cuda", generator=g).to(dtype)          # self-attention style packed buffer
+    kvb = torch.randn(B * Lk, 2 * C_, device="cuda", generator=g).to(dtype)
+    qb = qkv[:, :C_]
+    do = torch.randn(B * Lq, C_, device="cuda", generator=g).to(dtype)
+    o = torch.empty(B * Lq, C_, device="cuda", dtype=dtype)
+    lse = torch.empty(B, H, Lq, device="cuda")
+    seed = 987654321
+    K.attn_fused_fwd(qb, kvb[:, :C_], kvb[:, C_:], o, lse, B, H, Lq, Lk, hd, seed, p)
+    q = qb.float().reshape(B, Lq, H, hd).transpose(1, 2).requires_grad_(True)
+    k = kvb[:, :C_].float().reshape(B, Lk, H, hd).transpose(1, 2).requires_grad_(True)
+    v = kvb[:, C_:].float().reshape(B, Lk, H, hd).transpose(1, 2).requires_grad_(True)
+    s = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    pr = torch.softmax(s, dim=-1)
+    _cmp(lse, torch.logsumexp(s, dim=-1).detach(), torch.float32, "fused lse", 100.0)
+    if p > 0:
+        assert Lk <= hd
+        eye = torch.zeros(B * Lk, 2 * C_, device="cuda", dtype=dtype)
+        for h in range(H):
+            eye[:, C_ + h * hd: C_ + h * hd + Lk] = torch.eye(Lk, device="cuda", dtype=dtype).repeat(B, 1)
+        om = torch.empty_like(o)
+        K.attn_fused_fwd(qb, kvb[:, :C_], eye[:, C_:], om, None, B, H, Lq, Lk, hd, seed, p)
+        pm = om.float().view(B, Lq, H, hd).transpose(1, 2)[..., :Lk]
+        mask = (pm > 0).float()
+        assert abs((1.0 - mask.mean().item()) - p) < 0.03
+        pr_used = pr * mask / (1.0 - p)
+    else:
+        pr_used = pr
+    oref = pr_used @ v
+    oref.backward(do.float().view(B, Lq, H, hd).transpose(1, 2))
+    _cmp(o, oref.detach().transpose(1, 2).reshape(B * Lq, C_), dtype, "fused fwd")
+    dqkv = torch.zeros_like(qkv)
+    dkv = torch.empty_like(kvb)
+    K.attn_fused_bwd(qb, kvb[:, :C_], kvb[:, C_:], o, do, lse, dqkv[:, :C_], dkv[:, :C_], dkv[:, C_:], B, H, Lq, Lk, hd, seed, p)
+    _cmp(dqkv[:, :C_], q.grad.transpose(1, 2).reshape(B * Lq, C_), dtype, "fused dq", 2.0)
+    _cmp(dkv[:, :C_], k.grad.transpose(1, 2).reshape(B * Lk, C_), dtype, "fused dk", 2.0)
+    _cmp(dkv[:, C_:], v.grad.transpose(1, 2).reshape(B * Lk, C_), dtype, "fused dv", 2.0)
+    assert dqkv[:, C_:].abs().max().item() == 0.0

@@ -9,16 +9,17 @@
 // global memory: the forward saves only the row log-sum-exp, the backward recomputes the probabilities.
 //
 //   forward  (q-block 64): S = scale Q K^T -> softmax -> LSE, Pd = drop(P) -> O = Pd V
-//   backward (q-block 32): delta = rowsum(dO o O); S; dPd = dO V^T; dS = P o (drop(dPd) - delta); dQ = scale dS K
-//   backward (k-block 32): S^T = scale K Q^T; dPd^T = V dO^T; Pd^T, dS^T; dV = Pd^T dO; dK = scale dS^T Q
+//   backward (q-block 64): delta = rowsum(dO o O); {S, dPd = dO V^T} per tile in registers -> dS = P o (drop(dPd) - delta)
+//                          -> shared memory (bf16) -> dQ = scale dS K
+//   backward (k-block 64): S^T -> Pd^T (bf16) -> dV = Pd^T dO; then {S^T, dPd^T = V dO^T} -> dS^T (same buffer) -> dK = scale dS^T Q
+//                          (S^T is computed twice: FLOPs are free here, shared memory is not)
 //
 // The dropout mask is the library-wide stateless rule psg_drop_keep(seed, ((b*H + h)*Lq + i)*Lk + j).
 #include "psg_common.cuh"
 
 namespace fattn {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+constexpr int kThreads = 512;      // big problems (one CTA per SM by shared memory): 16 warps; small ones launch 256 threads
 constexpr int kMaxLk = 256;          // softmax keeps a row in registers: Lk16 / 32 <= 8 values per lane
 constexpr size_t kSmemLimit = 225 * 1024;
 
@@ -36,12 +37,11 @@ struct Params {
   float ks;                           // 1 / (1 - p)
 };
 
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t a) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t a) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -55,14 +55,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
-// rows [r0, r0 + nrows) of a token-major [*, hd] matrix -> smem tile [rows_padded][hp]; rows >= rmax are zero-filled
+// rows [r0, r0 + rows_padded) of a token-major [*, hd] matrix -> smem tile [rows_padded][hp]; rows >= rmax are zero-filled.
+// One warp per row, lanes over the row's 16-byte pieces: no integer division in the copy loop.
 __device__ __forceinline__ void load_rows(__nv_bfloat16* dst, int hp, const __nv_bfloat16* src, long long ld, int r0, int rmax,
                                           int rows_padded, int hd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int vpr = hd >> 3;
-  for (int idx = threadIdx.x; idx < rows_padded * vpr; idx += kThreads) {
-    const int r = idx / vpr, v = idx - r * vpr;
+  for (int r = warp; r < rows_padded; r += nwarps) {
     const bool ok = r0 + r < rmax;
-    cp_async16(dst + r * hp + v * 8, ok ? src + (long long)(r0 + r) * ld + v * 8 : src, ok ? 16 : 0);
+    const __nv_bfloat16* srow = ok ? src + (long long)(r0 + r) * ld : src;
+    __nv_bfloat16* drow = dst + r * hp;
+    for (int v = lane; v < vpr; v += 32) cp_async16(drow + v * 8, ok ? srow + v * 8 : src, ok ? 16 : 0);
   }
 }
 
@@ -76,24 +79,46 @@ __device__ __forceinline__ void warp_mma_16x32(float (&acc)[4][4], const __nv_bf
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
   const int j = lane >> 3, r = lane & 7;
+  // shared-space byte addresses of this lane's ldmatrix rows, advanced by a constant per 16-deep k step: the loop body
+  // is 3 LDSM + 4 HMMA + 3 adds (recomputing generic addresses per step made the integer pipe, not the tensor pipe, the limit)
+  uint32_t a_addr = smem_u32(A + (m0 + r + 8 * (j & 1)) * lda + 8 * (j >> 1));
+  uint32_t b_addr0, b_addr1, b_step;
+  if (kBT) {
+    b_addr0 = smem_u32(Bm + (r + 8 * (j & 1)) * ldb + n0 + 8 * (j >> 1));
+    b_addr1 = b_addr0 + 32;                 // n0 + 16
+    b_step = (uint32_t)ldb * 32u;           // 16 k rows
+  } else {
+    b_addr0 = smem_u32(Bm + (n0 + r + 8 * (j >> 1)) * ldb + 8 * (j & 1));
+    b_addr1 = b_addr0 + (uint32_t)ldb * 32u;  // n0 + 16
+    b_step = 32u;                           // 16 k elements
+  }
+#pragma unroll 2
   for (int kk = 0; kk < K; kk += 16) {
-    uint32_t af[4];
-    ldsm_x4(af, A + (m0 + r + 8 * (j & 1)) * lda + kk + 8 * (j >> 1));
-#pragma unroll
-    for (int jn = 0; jn < 4; jn += 2) {
-      uint32_t bf[4];
-      const int nt = n0 + jn * 8;
-      if (kBT) ldsm_x4_t(bf, Bm + (kk + r + 8 * (j & 1)) * ldb + nt + 8 * (j >> 1));
-      else     ldsm_x4(bf, Bm + (nt + r + 8 * (j >> 1)) * ldb + kk + 8 * (j & 1));
-      mma16816(acc[jn], af, bf[0], bf[1]);
-      mma16816(acc[jn + 1], af, bf[2], bf[3]);
-    }
+    uint32_t af[4], b0[4], b1[4];
+    ldsm_x4(af, a_addr);
+    if (kBT) { ldsm_x4_t(b0, b_addr0); ldsm_x4_t(b1, b_addr1); }
+    else     { ldsm_x4(b0, b_addr0);   ldsm_x4(b1, b_addr1); }
+    a_addr += 32u;
+    b_addr0 += b_step;
+    b_addr1 += b_step;
+    mma16816(acc[0], af, b0[0], b0[1]);
+    mma16816(acc[1], af, b0[2], b0[3]);
+    mma16816(acc[2], af, b1[0], b1[1]);
+    mma16816(acc[3], af, b1[2], b1[3]);
   }
 }
 // element (e) of acc[jn] sits at row m0 + (lane >> 2) + 8 * (e >> 1), column n0 + jn * 8 + (lane & 3) * 2 + (e & 1)
 
 __device__ __forceinline__ bool keep_ij(const Params& p, long long row_global, int j) {
   return p.thr == 0 || psg_drop_keep(p.seed, (uint64_t)(row_global * p.Lk + j), p.thr);
+}
+// keep flags of the two neighbouring scores (row, j) and (row, j + 1) from at most two hashes (one when row*Lk + j is even)
+__device__ __forceinline__ void keep_pair(const Params& p, uint64_t row_base, int j, bool& k0, bool& k1) {
+  const uint64_t idx = row_base + (uint64_t)j;
+  const uint32_t h0 = psg_hash32(p.seed, idx >> 1);
+  k0 = psg_drop_keep2(h0, (int)(idx & 1), p.thr);
+  const uint32_t h1 = (idx & 1) ? psg_hash32(p.seed, (idx + 1) >> 1) : h0;
+  k1 = psg_drop_keep2(h1, (int)((idx + 1) & 1), p.thr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -111,7 +136,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Params p) {
   __nv_bfloat16* Vs = Ks + (size_t)p.Lk16 * hp;
   __nv_bfloat16* Qs = Vs + (size_t)p.Lk16 * hp;
   float* Sf = reinterpret_cast<float*>(Qs + (size_t)kQB * hp);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kWarps = blockDim.x >> 5;
+  const int mtl = min(kQB / 16, (p.Lq - q0 + 15) >> 4);      // live 16-row tiles of this block
 
   load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, 0, p.Lk, p.Lk16, p.hd);
   load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, 0, p.Lk, p.Lk16, p.hd);
@@ -121,8 +147,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Params p) {
 
   // S = scale * Q K^T
   const int nchunks = (p.Lk16 + 31) / 32;
-  for (int item = warp; item < 4 * nchunks; item += kWarps) {
-    const int mt = item & 3, nc = item >> 2;
+  for (int item = warp; item < mtl * nchunks; item += kWarps) {
+    const int nc = item / mtl, mt = item - nc * mtl;
     float acc[4][4];
     // the last chunk may run 16 columns past Lk16: those B rows belong to the V tile (finite data), results are dropped
     warp_mma_16x32<false>(acc, Qs, hp, mt * 16, Ks, hp, nc * 32, p.hd, lane);
@@ -136,24 +162,28 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Params p) {
   }
   __syncthreads();
 
-  // row softmax (one warp per row), LSE out, dropout, bf16 Pd written over the row's own fp32 storage
-  for (int r = warp; r < kQB; r += kWarps) {
-    float v[kMaxLk / 32];
+  // row softmax (one warp per row; lane l owns the column pairs 2l + 64 i), LSE out, dropout (one hash per pair), bf16 Pd
+  // written over the row's own fp32 storage
+  for (int r = warp; r < mtl * 16; r += kWarps) {
+    float2 v[kMaxLk / 64];
     float mx = -INFINITY;
     float* srow = Sf + r * sp;
 #pragma unroll
-    for (int i = 0; i < kMaxLk / 32; ++i) {
-      const int jx = lane + 32 * i;
-      v[i] = (jx < p.Lk) ? srow[jx] : -INFINITY;
-      mx = fmaxf(mx, v[i]);
+    for (int i = 0; i < kMaxLk / 64; ++i) {
+      const int jx = 2 * lane + 64 * i;
+      v[i] = (jx < p.Lk16) ? *reinterpret_cast<const float2*>(srow + jx) : make_float2(-INFINITY, -INFINITY);
+      if (jx >= p.Lk) v[i].x = -INFINITY;
+      if (jx + 1 >= p.Lk) v[i].y = -INFINITY;
+      mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxLk / 32; ++i) {
-      v[i] = (lane + 32 * i < p.Lk) ? __expf(v[i] - mx) : 0.f;
-      sum += v[i];
+    for (int i = 0; i < kMaxLk / 64; ++i) {
+      v[i].x = __expf(v[i].x - mx);       // exp(-inf) = 0 on the padding
+      v[i].y = __expf(v[i].y - mx);
+      sum += v[i].x + v[i].y;
     }
     sum = psg_warp_sum(sum);
     const float inv = 1.f / sum;
@@ -162,13 +192,20 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Params p) {
     if (valid && lane == 0 && p.lse) p.lse[row_global] = mx + __logf(sum);
     __syncwarp();
     __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(srow);
+    const uint64_t row_base = (uint64_t)row_global * (uint64_t)p.Lk;
+    const float live = valid ? inv : 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxLk / 32; ++i) {
-      const int jx = lane + 32 * i;
+    for (int i = 0; i < kMaxLk / 64; ++i) {
+      const int jx = 2 * lane + 64 * i;
       if (jx < p.Lk16) {
-        float pv = v[i] * inv;
-        if (p.thr) pv = (valid && jx < p.Lk && keep_ij(p, row_global, jx)) ? pv * p.ks : 0.f;
-        prow[jx] = __float2bfloat16_rn(valid ? pv : 0.f);
+        float p0 = v[i].x * live, p1 = v[i].y * live;
+        if (p.thr) {
+          bool k0, k1;
+          keep_pair(p, row_base, jx, k0, k1);
+          p0 = k0 ? p0 * p.ks : 0.f;
+          p1 = k1 ? p1 * p.ks : 0.f;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(prow + jx) = __floats2bfloat162_rn(p0, p1);
       }
     }
   }
@@ -179,8 +216,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Params p) {
   const int ldp = 2 * sp;
   __nv_bfloat16* obase = p.out + (long long)b * p.Lq * p.ldo + h * p.hd;
   const int ochunks = (p.hd + 31) / 32;      // head_dim % 32 == 16: the last chunk's upper half is dropped
-  for (int item = warp; item < 4 * ochunks; item += kWarps) {
-    const int mt = item & 3, nc = item >> 2;
+  for (int item = warp; item < mtl * ochunks; item += kWarps) {
+    const int nc = item / mtl, mt = item - nc * mtl;
     float acc[4][4];
     warp_mma_16x32<true>(acc, Pd, ldp, mt * 16, Vs, hp, nc * 32, p.Lk16, lane);
 #pragma unroll
@@ -194,25 +231,25 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward, dQ: grid (ceil(Lq / 32), B * H)
-//   smem: K [Lk16][hp] | V [Lk16][hp] | Q [32][hp] | dO [32][hp] | S fp32 [32][sp] | dS bf16 [32][dp] | lse[32] | delta[32]
+// backward, dQ: grid (ceil(Lq / 64), B * H)
+//   smem: K [Lk16][hp] | V [Lk16][hp] | Q [64][hp] | dO [64][hp] | dS bf16 [64][dp] | lse[64] | delta[64]
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kBB = 32;
+constexpr int kBB = 64;
 
 __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
   const int q0 = blockIdx.x * kBB;
-  const int hp = p.hp, sp = p.Lk16 + 4, dp = p.Lk16 + 8;
+  const int hp = p.hp, dp = p.Lk16 + 8;
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* Vs = Ks + (size_t)p.Lk16 * hp;
   __nv_bfloat16* Qs = Vs + (size_t)p.Lk16 * hp;
   __nv_bfloat16* dOs = Qs + (size_t)kBB * hp;
-  float* Sf = reinterpret_cast<float*>(dOs + (size_t)kBB * hp);
-  __nv_bfloat16* dSs = reinterpret_cast<__nv_bfloat16*>(Sf + (size_t)kBB * sp);
+  __nv_bfloat16* dSs = dOs + (size_t)kBB * hp;
   float* lse_s = reinterpret_cast<float*>(dSs + (size_t)kBB * dp);
   float* del_s = lse_s + kBB;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kWarps = blockDim.x >> 5;
+  const int mtl = min(kBB / 16, (p.Lq - q0 + 15) >> 4);      // live 16-row tiles of this block
 
   load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, 0, p.Lk, p.Lk16, p.hd);
   load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, 0, p.Lk, p.Lk16, p.hd);
@@ -244,48 +281,41 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Params p) {
   cp_async_wait_all();
   __syncthreads();
 
+  // per 16 x 32 tile: S = Q K^T and dPd = dO V^T in registers -> dS = P o (drop(dPd) - delta) -> shared memory
   const int nchunks = (p.Lk16 + 31) / 32;
-  // S = scale * Q K^T -> smem
-  for (int item = warp; item < 2 * nchunks; item += kWarps) {
-    const int mt = item & 1, nc = item >> 1;
-    float acc[4][4];
-    warp_mma_16x32<false>(acc, Qs, hp, mt * 16, Ks, hp, nc * 32, p.hd, lane);
+  for (int item = warp; item < mtl * nchunks; item += kWarps) {
+    const int nc = item / mtl, mt = item - nc * mtl;
+    float sa[4][4], da[4][4];
+    warp_mma_16x32<false>(sa, Qs, hp, mt * 16, Ks, hp, nc * 32, p.hd, lane);
+    warp_mma_16x32<false>(da, dOs, hp, mt * 16, Vs, hp, nc * 32, p.hd, lane);
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
+    for (int half = 0; half < 2; ++half) {
+      const int m = mt * 16 + (lane >> 2) + 8 * half;
+      const bool row_ok = q0 + m < p.Lq;
+      const float lse_m = lse_s[m], del_m = del_s[m];
+      const uint64_t row_base = (uint64_t)((long long)bh * p.Lq + q0 + m) * (uint64_t)p.Lk;
+      __nv_bfloat16* drow = dSs + m * dp;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = mt * 16 + (lane >> 2) + 8 * (e >> 1), n = nc * 32 + jn * 8 + (lane & 3) * 2 + (e & 1);
-        if (n < p.Lk16) Sf[m * sp + n] = acc[jn][e] * p.scale;
-      }
-  }
-  __syncthreads();
-  // dPd = dO V^T ; dS = P o (drop(dPd) - delta)
-  for (int item = warp; item < 2 * nchunks; item += kWarps) {
-    const int mt = item & 1, nc = item >> 1;
-    float acc[4][4];
-    warp_mma_16x32<false>(acc, dOs, hp, mt * 16, Vs, hp, nc * 32, p.hd, lane);
-#pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = mt * 16 + (lane >> 2) + 8 * (e >> 1), n = nc * 32 + jn * 8 + (lane & 3) * 2 + (e & 1);
+      for (int jn = 0; jn < 4; ++jn) {
+        const int n = nc * 32 + jn * 8 + (lane & 3) * 2;          // columns n, n + 1
         if (n >= p.Lk16) continue;
-        float ds = 0.f;
-        if (n < p.Lk && q0 + m < p.Lq) {
-          const float pr = __expf(Sf[m * sp + n] - lse_s[m]);
-          float dpv = acc[jn][e];
-          if (p.thr) dpv = keep_ij(p, (long long)bh * p.Lq + q0 + m, n) ? dpv * p.ks : 0.f;
-          ds = pr * (dpv - del_s[m]);
+        float d0 = 0.f, d1 = 0.f;
+        if (row_ok) {
+          bool k0 = true, k1 = true;
+          if (p.thr) keep_pair(p, row_base, n, k0, k1);
+          if (n < p.Lk) d0 = __expf(sa[jn][2 * half] * p.scale - lse_m) * ((k0 ? da[jn][2 * half] * p.ks : 0.f) - del_m);
+          if (n + 1 < p.Lk) d1 = __expf(sa[jn][2 * half + 1] * p.scale - lse_m) * ((k1 ? da[jn][2 * half + 1] * p.ks : 0.f) - del_m);
         }
-        dSs[m * dp + n] = __float2bfloat16_rn(ds);
+        *reinterpret_cast<__nv_bfloat162*>(drow + n) = __floats2bfloat162_rn(d0, d1);
       }
+    }
   }
   __syncthreads();
   // dQ = scale * dS K
   __nv_bfloat16* qbase = p.dq + (long long)b * p.Lq * p.lddq + h * p.hd;
   const int ochunks = (p.hd + 31) / 32;      // head_dim % 32 == 16: the last chunk's upper half is dropped
-  for (int item = warp; item < 2 * ochunks; item += kWarps) {
-    const int mt = item & 1, nc = item >> 1;
+  for (int item = warp; item < mtl * ochunks; item += kWarps) {
+    const int nc = item / mtl, mt = item - nc * mtl;
     float acc[4][4];
     warp_mma_16x32<true>(acc, dSs, dp, mt * 16, Ks, hp, nc * 32, p.Lk16, lane);
 #pragma unroll
@@ -301,31 +331,29 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward, dK / dV: grid (ceil(Lk / 32), B * H)
-//   smem: Q [Lq16][hp] | dO [Lq16][hp] | K [32][hp] | V [32][hp] | S^T fp32 [32][sp] | Pd^T bf16 [32][dp] | dS^T bf16 [32][dp]
-//         | lse[Lq16] | delta[Lq16]
+// backward, dK / dV: grid (ceil(Lk / 64), B * H)
+//   smem: Q [Lq16][hp] | dO [Lq16][hp] | K [64][hp] | V [64][hp] | T bf16 [64][dp] (Pd^T, then dS^T) | lse[Lq16] | delta[Lq16]
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
   const int k0 = blockIdx.x * kBB;
-  const int hp = p.hp, sp = p.Lq16 + 4, dp = p.Lq16 + 8;
+  const int hp = p.hp, dp = p.Lq16 + 8;
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* dOs = Qs + (size_t)p.Lq16 * hp;
   __nv_bfloat16* Ks = dOs + (size_t)p.Lq16 * hp;
   __nv_bfloat16* Vs = Ks + (size_t)kBB * hp;
-  float* Sf = reinterpret_cast<float*>(Vs + (size_t)kBB * hp);
-  __nv_bfloat16* Pt = reinterpret_cast<__nv_bfloat16*>(Sf + (size_t)kBB * sp);
-  __nv_bfloat16* dSt = Pt + (size_t)kBB * dp;
-  float* lse_s = reinterpret_cast<float*>(dSt + (size_t)kBB * dp);
+  __nv_bfloat16* Ts = Vs + (size_t)kBB * hp;
+  float* lse_s = reinterpret_cast<float*>(Ts + (size_t)kBB * dp);
   float* del_s = lse_s + p.Lq16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kWarps = blockDim.x >> 5;
+  const int mtl = min(kBB / 16, (p.Lk - k0 + 15) >> 4);      // live 16-key tiles of this block
 
   load_rows(Qs, hp, p.q + (long long)b * p.Lq * p.ldq + h * p.hd, p.ldq, 0, p.Lq, p.Lq16, p.hd);
   load_rows(dOs, hp, p.dout + (long long)b * p.Lq * p.lddo + h * p.hd, p.lddo, 0, p.Lq, p.Lq16, p.hd);
   load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, k0, p.Lk, kBB, p.hd);
   load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, k0, p.Lk, kBB, p.hd);
-  for (int i = threadIdx.x; i < p.Lq16; i += kThreads) {
+  for (int i = threadIdx.x; i < p.Lq16; i += blockDim.x) {
     const bool ok = i < p.Lq;
     lse_s[i] = ok ? p.lse[(long long)bh * p.Lq + i] : 0.f;
     del_s[i] = ok ? p.delta[(long long)bh * p.Lq + i] : 0.f;
@@ -334,67 +362,80 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Params p) 
   __syncthreads();
 
   const int nchunks = (p.Lq16 + 31) / 32;
-  // S^T = scale * K Q^T (rows = keys of this block, columns = queries)
-  for (int item = warp; item < 2 * nchunks; item += kWarps) {
-    const int mt = item & 1, nc = item >> 1;
-    float acc[4][4];
-    warp_mma_16x32<false>(acc, Ks, hp, mt * 16, Qs, hp, nc * 32, p.hd, lane);
-#pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = mt * 16 + (lane >> 2) + 8 * (e >> 1), n = nc * 32 + jn * 8 + (lane & 3) * 2 + (e & 1);
-        if (n < p.Lq16) Sf[m * sp + n] = acc[jn][e] * p.scale;
-      }
-  }
-  __syncthreads();
-  // dPd^T = V dO^T ; Pd^T and dS^T
-  for (int item = warp; item < 2 * nchunks; item += kWarps) {
-    const int mt = item & 1, nc = item >> 1;
-    float acc[4][4];
-    warp_mma_16x32<false>(acc, Vs, hp, mt * 16, dOs, hp, nc * 32, p.hd, lane);
+  const int ochunks = (p.hd + 31) / 32;
+  // pass A: Pd^T = drop(exp(scale K Q^T - lse)) -> T (rows = keys of this block, columns = queries)
+  for (int item = warp; item < mtl * nchunks; item += kWarps) {
+    const int nc = item / mtl, mt = item - nc * mtl;
+    float sa[4][4];
+    warp_mma_16x32<false>(sa, Ks, hp, mt * 16, Qs, hp, nc * 32, p.hd, lane);
 #pragma unroll
     for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int m = mt * 16 + (lane >> 2) + 8 * (e >> 1), n = nc * 32 + jn * 8 + (lane & 3) * 2 + (e & 1);
         if (n >= p.Lq16) continue;
-        float pd = 0.f, ds = 0.f;
+        float pd = 0.f;
         if (n < p.Lq && k0 + m < p.Lk) {
-          const float pr = __expf(Sf[m * sp + n] - lse_s[n]);
-          float dpv = acc[jn][e];
-          pd = pr;
-          if (p.thr) {
-            const bool kp = keep_ij(p, (long long)bh * p.Lq + n, k0 + m);
-            pd = kp ? pr * p.ks : 0.f;
-            dpv = kp ? dpv * p.ks : 0.f;
-          }
-          ds = pr * (dpv - del_s[n]);
+          pd = __expf(sa[jn][e] * p.scale - lse_s[n]);
+          if (p.thr) pd = keep_ij(p, (long long)bh * p.Lq + n, k0 + m) ? pd * p.ks : 0.f;
         }
-        Pt[m * dp + n] = __float2bfloat16_rn(pd);
-        dSt[m * dp + n] = __float2bfloat16_rn(ds);
+        Ts[m * dp + n] = __float2bfloat16_rn(pd);
       }
   }
   __syncthreads();
-  // dV = Pd^T dO ; dK = scale * dS^T Q
+  // dV = Pd^T dO
   __nv_bfloat16* vbase = p.dv + (long long)b * p.Lk * p.lddv + h * p.hd;
-  __nv_bfloat16* kbase = p.dk + (long long)b * p.Lk * p.lddk + h * p.hd;
-  const int ochunks = (p.hd + 31) / 32;      // head_dim % 32 == 16: the last chunk's upper half is dropped
-  for (int item = warp; item < 4 * ochunks; item += kWarps) {
-    const int which = item & 1, mt = (item >> 1) & 1, nc = item >> 2;
+  for (int item = warp; item < mtl * ochunks; item += kWarps) {
+    const int nc = item / mtl, mt = item - nc * mtl;
     float acc[4][4];
-    if (which == 0) warp_mma_16x32<true>(acc, Pt, dp, mt * 16, dOs, hp, nc * 32, p.Lq16, lane);
-    else            warp_mma_16x32<true>(acc, dSt, dp, mt * 16, Qs, hp, nc * 32, p.Lq16, lane);
-    const float sc = which == 0 ? 1.f : p.scale;
-    __nv_bfloat16* base = which == 0 ? vbase : kbase;
-    const long long ld = which == 0 ? p.lddv : p.lddk;
+    warp_mma_16x32<true>(acc, Ts, dp, mt * 16, dOs, hp, nc * 32, p.Lq16, lane);
 #pragma unroll
     for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int m = k0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
         if (m < p.Lk && n < p.hd)
-          *reinterpret_cast<__nv_bfloat162*>(base + (long long)m * ld + n) = __floats2bfloat162_rn(acc[jn][2 * half] * sc, acc[jn][2 * half + 1] * sc);
+          *reinterpret_cast<__nv_bfloat162*>(vbase + (long long)m * p.lddv + n) = __floats2bfloat162_rn(acc[jn][2 * half], acc[jn][2 * half + 1]);
+      }
+  }
+  __syncthreads();
+  // pass B: dS^T = P^T o (drop(V dO^T) - delta) -> T
+  for (int item = warp; item < mtl * nchunks; item += kWarps) {
+    const int nc = item / mtl, mt = item - nc * mtl;
+    float sa[4][4], da[4][4];
+    warp_mma_16x32<false>(sa, Ks, hp, mt * 16, Qs, hp, nc * 32, p.hd, lane);
+    warp_mma_16x32<false>(da, Vs, hp, mt * 16, dOs, hp, nc * 32, p.hd, lane);
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int m = mt * 16 + (lane >> 2) + 8 * (e >> 1), n = nc * 32 + jn * 8 + (lane & 3) * 2 + (e & 1);
+        if (n >= p.Lq16) continue;
+        float ds = 0.f;
+        if (n < p.Lq && k0 + m < p.Lk) {
+          const float pr = __expf(sa[jn][e] * p.scale - lse_s[n]);
+          float dpv = da[jn][e];
+          if (p.thr) dpv = keep_ij(p, (long long)bh * p.Lq + n, k0 + m) ? dpv * p.ks : 0.f;
+          ds = pr * (dpv - del_s[n]);
+        }
+        Ts[m * dp + n] = __float2bfloat16_rn(ds);
+      }
+  }
+  __syncthreads();
+  // dK = scale * dS^T Q
+  __nv_bfloat16* kbase = p.dk + (long long)b * p.Lk * p.lddk + h * p.hd;
+  for (int item = warp; item < mtl * ochunks; item += kWarps) {
+    const int nc = item / mtl, mt = item - nc * mtl;
+    float acc[4][4];
+    warp_mma_16x32<true>(acc, Ts, dp, mt * 16, Qs, hp, nc * 32, p.Lq16, lane);
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int m = k0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
+        if (m < p.Lk && n < p.hd)
+          *reinterpret_cast<__nv_bfloat162*>(kbase + (long long)m * p.lddk + n) =
+              __floats2bfloat162_rn(acc[jn][2 * half] * p.scale, acc[jn][2 * half + 1] * p.scale);
       }
   }
 }
@@ -403,13 +444,14 @@ static size_t fwd_smem(const Params& p) {
   return ((size_t)2 * p.Lk16 * p.hp + (size_t)kQB * p.hp) * 2 + (size_t)kQB * (p.Lk16 + 4) * 4 + 64;
 }
 static size_t dq_smem(const Params& p) {
-  return ((size_t)2 * p.Lk16 * p.hp + (size_t)2 * kBB * p.hp) * 2 + (size_t)kBB * (p.Lk16 + 4) * 4 + (size_t)kBB * (p.Lk16 + 8) * 2 +
-         2 * kBB * 4 + 64;
+  return ((size_t)2 * p.Lk16 * p.hp + (size_t)2 * kBB * p.hp) * 2 + (size_t)kBB * (p.Lk16 + 8) * 2 + 2 * kBB * 4 + 64;
 }
 static size_t dkv_smem(const Params& p) {
-  return ((size_t)2 * p.Lq16 * p.hp + (size_t)2 * kBB * p.hp) * 2 + (size_t)kBB * (p.Lq16 + 4) * 4 + (size_t)2 * kBB * (p.Lq16 + 8) * 2 +
-         (size_t)2 * p.Lq16 * 4 + 64;
+  return ((size_t)2 * p.Lq16 * p.hp + (size_t)2 * kBB * p.hp) * 2 + (size_t)kBB * (p.Lq16 + 8) * 2 + (size_t)2 * p.Lq16 * 4 + 64;
 }
+
+// one CTA per SM anyway (shared memory): 16 warps; otherwise 8 warps so that two or three CTAs share an SM
+static int threads_for(size_t smem) { return smem > 110 * 1024 ? kThreads : 256; }
 
 static int fill(Params& p, int B, int H, int Lq, int Lk, int hd, float scale, unsigned long long seed, float drop_p) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || hd <= 0 || hd % 16 != 0 || Lk > kMaxLk || Lq > 1024) return -1;
@@ -465,7 +507,7 @@ int psg_attn_fused_fwd(const void* q, long long ldq, const void* k, long long ld
   int rc = configure(attn_fwd_kernel, done, "psg_attn_fused_fwd");
   if (rc) return rc;
   dim3 grid((Lq + kQB - 1) / kQB, B * H);
-  attn_fwd_kernel<<<grid, kThreads, fwd_smem(p), (cudaStream_t)stream>>>(p);
+  attn_fwd_kernel<<<grid, threads_for(fwd_smem(p)), fwd_smem(p), (cudaStream_t)stream>>>(p);
   PSG_CHECK_LAUNCH("psg_attn_fused_fwd");
   return PSG_OK;
 }
@@ -495,8 +537,8 @@ int psg_attn_fused_bwd(const void* q, long long ldq, const void* k, long long ld
   rc = configure(attn_bwd_dkv_kernel, done2, "psg_attn_fused_bwd");
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  attn_bwd_dq_kernel<<<dim3((Lq + kBB - 1) / kBB, B * H), kThreads, dq_smem(p), st>>>(p);
-  attn_bwd_dkv_kernel<<<dim3((Lk + kBB - 1) / kBB, B * H), kThreads, dkv_smem(p), st>>>(p);
+  attn_bwd_dq_kernel<<<dim3((Lq + kBB - 1) / kBB, B * H), threads_for(dq_smem(p)), dq_smem(p), st>>>(p);
+  attn_bwd_dkv_kernel<<<dim3((Lk + kBB - 1) / kBB, B * H), threads_for(dkv_smem(p)), dkv_smem(p), st>>>(p);
   PSG_CHECK_LAUNCH("psg_attn_fused_bwd");
   g_psg_launch_count += 1;  // two kernels
   return PSG_OK;

@@ -41,6 +41,7 @@ struct alignas(64) KernelParams {
   int num_m_tiles, num_n_tiles;
   int num_tiles;             // num_m_tiles * num_n_tiles
   int sk_tiles, sk_ctas;     // stream-K region: tiles [0, sk_tiles) shared by CTAs [0, sk_ctas)
+  int sk_split;              // > 0: aligned mode, every stream-K tile is cut into sk_split equal k-ranges (one per CTA)
   long long sk_units;        // sk_tiles * num_kb
   float* sk_slots;           // [gridDim.x][kMT*128*kBlockN] fp32 partial accumulators of shared tiles
   int* sk_flags;             // [gridDim.x] 1 = slot holds a partial that has not been consumed yet
@@ -393,8 +394,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // Work decomposition.  Stream-K region: unit u = tile * num_kb + kb over tiles [0, sk_tiles); CTA c < sk_ctas owns units
 // [sk_begin(c), sk_begin(c+1)).  Data-parallel region: CTA c then takes tiles sk_tiles + c, sk_tiles + c + gridDim.x, ...
-__device__ __forceinline__ long long sk_begin(long long sk_units, int c, int sk_ctas) {
-  return c >= sk_ctas ? sk_units : sk_units * c / sk_ctas;
+// Aligned mode (sk_split > 0): CTA c takes the (c % split)-th k-range of tile c / split, so that the CTAs of all tiles
+// walk the SAME k positions at the same time and share every operand slab in L2 (wgrad over activations larger than L2:
+// with unaligned ranges each tile re-read its operands from DRAM, 60 GB per step).
+__device__ __forceinline__ long long sk_begin(long long sk_units, int c, int sk_ctas, int split, int num_kb) {
+  if (c >= sk_ctas) return sk_units;
+  if (split > 0) {
+    const int tile = c / split, s = c - tile * split;
+    return (long long)tile * num_kb + (long long)s * num_kb / split;
+  }
+  return sk_units * c / sk_ctas;
 }
 
 struct Segment {          // a maximal run of one CTA's k-blocks inside one tile
@@ -403,9 +412,10 @@ struct Segment {          // a maximal run of one CTA's k-blocks inside one tile
 struct SegmentIter {
   long long cur, end;
   int num_kb, dp_tile, num_tiles, stride;
-  __device__ __forceinline__ SegmentIter(const long long sk_units, int sk_ctas, int sk_tiles, int num_tiles_, int num_kb_, int c, int ctas)
-      : cur(sk_begin(sk_units, c, sk_ctas)), end(sk_begin(sk_units, c + 1, sk_ctas)), num_kb(num_kb_), dp_tile(sk_tiles + c),
-        num_tiles(num_tiles_), stride(ctas) {}
+  __device__ __forceinline__ SegmentIter(const long long sk_units, int sk_ctas, int sk_split, int sk_tiles, int num_tiles_, int num_kb_,
+                                         int c, int ctas)
+      : cur(sk_begin(sk_units, c, sk_ctas, sk_split, num_kb_)), end(sk_begin(sk_units, c + 1, sk_ctas, sk_split, num_kb_)),
+        num_kb(num_kb_), dp_tile(sk_tiles + c), num_tiles(num_tiles_), stride(ctas) {}
   __device__ __forceinline__ bool next(Segment& s) {
     if (cur < end) {
       s.tile = (int)(cur / num_kb);
@@ -425,7 +435,7 @@ struct SegmentIter {
     return false;
   }
 };
-#define PSG_SEGMENTS(p) SegmentIter segs((p).sk_units, (p).sk_ctas, (p).sk_tiles, (p).num_tiles, (p).num_kb, blockIdx.x, gridDim.x)
+#define PSG_SEGMENTS(p) SegmentIter segs((p).sk_units, (p).sk_ctas, (p).sk_split, (p).sk_tiles, (p).num_tiles, (p).num_kb, blockIdx.x, gridDim.x)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }   // the epilogue warps
 
@@ -621,7 +631,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       int last_contrib = blockIdx.x;
       if (shared_owner) {
         const long long tile_end = (long long)(tile + 1) * p.num_kb;
-        while (last_contrib + 1 < p.sk_ctas && sk_begin(p.sk_units, last_contrib + 1, p.sk_ctas) < tile_end) ++last_contrib;
+        while (last_contrib + 1 < p.sk_ctas && sk_begin(p.sk_units, last_contrib + 1, p.sk_ctas, p.sk_split, p.num_kb) < tile_end) ++last_contrib;
         if (warp == 2 && lane == 0)
           for (int c = blockIdx.x + 1; c <= last_contrib; ++c) wait_flag(p.sk_flags + c);
         __syncwarp();
@@ -940,12 +950,22 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   if (sms > kMaxCtas) sms = kMaxCtas;
   const long long sk_tiles = tiles % sms;
   long long ctas = tiles >= sms ? sms : 0, sk_ctas = 0;
+  // reduction over activations (NT mode) bigger than the L2 can hold next to everything else: keep the k-ranges of all
+  // tiles aligned (see sk_begin); all such problems of this model have fewer tiles than SMs
+  const bool aligned_split = mode == 1 && tiles < sms && (double)d->K * (double)(d->M + d->N) * 2.0 > 48e6;
   if (sk_tiles > 0) {
     const long long sk_units = sk_tiles * kp.num_kb;
     const long long min_share = kp.num_kb / 8 > 8 ? kp.num_kb / 8 : 8;
     sk_ctas = sk_units / min_share;
     if (sk_ctas < sk_tiles) sk_ctas = sk_tiles;
     if (sk_ctas > sms) sk_ctas = sms;
+    if (aligned_split) {
+      long long split = sms / sk_tiles;
+      if (split > kp.num_kb / 8) split = kp.num_kb / 8;
+      if (split < 1) split = 1;
+      kp.sk_split = (int)split;
+      sk_ctas = sk_tiles * split;
+    }
     if (ctas < sk_ctas) ctas = sk_ctas;
     kp.sk_tiles = (int)sk_tiles;
     kp.sk_ctas = (int)sk_ctas;

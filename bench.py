@@ -32,6 +32,16 @@ TRAIN_GFLOP_PER_SAMPLE = 3 * FWD_GFLOP_PER_SAMPLE
 METRIC = "unet_train_latent_samples_per_s"
 
 
+def _umma_traffic():
+    """DRAM read+write bytes per tcgen05 launch (mean over one step's launches), from the committed ncu launch list
+    (tools/summarize_launches.py --json over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); None if absent."""
+    p = ROOT / "profiles" / "umma_traffic.json"
+    try:
+        return json.loads(p.read_text())["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -237,7 +247,8 @@ def main():
     achieved = um_flops / (um_ms / 1e3) / 1e12 if um_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "umma_gemm_kernel (tcgen05 implicit-GEMM conv + GEMM, fwd/dgrad/wgrad)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "peak_source": f"{peaks['src']} sustained cuBLAS bf16", "traffic": None,
+                "peak_source": f"{peaks['src']} sustained cuBLAS bf16", "traffic": _umma_traffic(),
+                "algorithmic_bytes_note": "tensor-bound kernel: achieved/peak are TFLOP/s; traffic = mean DRAM bytes per launch (ncu)",
                 "launches_per_step": len(um) / Ksteps, "share_of_step": um_ms / ms if ms > 0 else None,
                 "algorithmic_tflop_per_step": um_flops / Ksteps / 1e12,
                 "step_model_tflops": B * TRAIN_GFLOP_PER_SAMPLE / 1e3 / (ms_per_step / 1e3)}

@@ -37,3 +37,12 @@ print("|---|---:|---:|---:|---:|---:|")
 for name, d in sorted(per.items(), key=lambda kv: -kv[1]["ns"]):
     print(f"| `{name}` | {len(d['n'])} | {d['ns'] / 1e6:.3f} | {100 * d['ns'] / tot:.1f}% | {d['rd'] / 1e9:.3f} | {d['wr'] / 1e9:.3f} |")
 print(f"| **total** | {sum(len(d['n']) for d in per.values())} | {tot / 1e6:.3f} | 100% | {sum(d['rd'] for d in per.values()) / 1e9:.2f} | {sum(d['wr'] for d in per.values()) / 1e9:.2f} |")
+
+if len(sys.argv) > 3:      # third argument: write the mean DRAM bytes per launch of the kernels matching argv[4] (default umma)
+    import json
+    pat = sys.argv[4] if len(sys.argv) > 4 else "umma"
+    sel = [d for n, d in per.items() if pat in n]
+    launches = sum(len(d["n"]) for d in sel)
+    total = sum(d["rd"] + d["wr"] for d in sel)
+    json.dump({"kernel_pattern": pat, "launches": launches, "dram_bytes_total": total, "dram_bytes_per_launch": total / max(launches, 1),
+               "source": path}, open(sys.argv[3], "w"), indent=1)

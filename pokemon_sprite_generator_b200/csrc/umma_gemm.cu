@@ -10,6 +10,12 @@
 // kMode 2 ("TT"):  A as kMode 0, B MN-major: the weight matrix as stored ([N_w, K_w] row-major, conv weights
 //                  [Cout][tap][Cin]) read transposed -- dgrad needs no transposed weight copy.
 //
+// kCl == 2 ("B-multicast pairs"): two CTAs of a thread-block cluster take vertically adjacent 128*kMT-row tiles of the
+// same column block; each loads only HALF of the B tile and TMA-multicasts it into both CTAs' shared memory, so a CTA
+// pulls 32 KB instead of 48 KB through L2 per 128x256x64 block (the mainloop is L2->SM bound, not tensor-pipe bound) while
+// keeping its own double-buffered TMEM accumulators and its own cta_group::1 MMAs.  A stage is refilled only after BOTH
+// CTAs' MMAs have drained it (tcgen05.commit multicast onto both empty barriers).
+//
 // Scheduling is "data-parallel + stream-K": whole waves of tiles are dealt round-robin to the persistent CTAs; the
 // remainder tiles (all tiles, when there are fewer tiles than SMs) form a stream-K region whose (tile, k-block)
 // iteration space is cut into one contiguous range per CTA, done BEFORE the CTA's whole tiles -- every SM gets the same
@@ -101,6 +107,28 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h, int n,
+                                                      uint16_t off_w, uint16_t off_h, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -125,6 +153,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -435,7 +468,7 @@ struct SegmentIter {
     return false;
   }
 };
-#define PSG_SEGMENTS(p) SegmentIter segs((p).sk_units, (p).sk_ctas, (p).sk_split, (p).sk_tiles, (p).num_tiles, (p).num_kb, blockIdx.x, gridDim.x)
+#define PSG_SEGMENTS(p) SegmentIter segs((p).sk_units, (p).sk_ctas, (p).sk_split, (p).sk_tiles, (p).num_tiles, (p).num_kb, vcta, vctas)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }   // the epilogue warps
 
@@ -453,7 +486,7 @@ __device__ __forceinline__ void wait_flag(const int* flag) {
 // ---------------------------------------------------------------------------------------------
 // the kernel: persistent CTAs, one contiguous stream-K range of (tile, k-block) units each
 // ---------------------------------------------------------------------------------------------
-template <int kBlockN, int kStages, int kMode, int kMT>
+template <int kBlockN, int kStages, int kMode, int kMT, int kCl>
 __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_constant__ KernelParams p) {
   using L = SmemLayout<kBlockN, kStages, kMT>;
   constexpr int kAcc = L::kAcc;
@@ -461,6 +494,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
   static_assert(kBlockN % 32 == 0 && kBlockN <= 256, "BLOCK_N must be a multiple of 32 (epilogue chunk) and <= 256");
   static_assert(kMode == 0 || kBlockN % 64 == 0, "MN-major B tiles are built from 64-wide TMA boxes");
   constexpr bool kAMn = (kMode == 1), kBMn = (kMode >= 1);
+  static_assert(kCl == 1 || (kCl == 2 && kBlockN % 128 == 0), "B-multicast pairs split the B tile in two halves of whole 64-wide boxes");
+  const uint32_t cta_rank = (kCl == 2) ? cluster_ctarank() : 0u;     // which half of B this CTA fetches, which row tile it owns
+  const int vcta = blockIdx.x / kCl, vctas = gridDim.x / kCl;        // scheduling unit: a CTA, or a CTA pair
   static_assert(kMT * kBlockN <= 512, "accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -477,13 +513,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tm_a);
     prefetch_tmap(&p.tm_b);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, kCl); }   // empty: every CTA's MMAs
     for (int a = 0; a < kAcc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (kCl == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -495,7 +532,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       Segment sg;
       while (segs.next(sg)) {
         const int tile = sg.tile;
-        const int tile_n = tile % p.num_n_tiles, tile_m = tile / p.num_n_tiles;
+        const int tile_n = tile % p.num_n_tiles, tile_m = (tile / p.num_n_tiles) * kCl + (int)cta_rank;
         const int m0 = tile_m * BM;
         const int kb0 = sg.kb0, kb1 = sg.kb1;
         int w0[kMT], h0[kMT], img0[kMT];
@@ -535,8 +572,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &p.tm_a, full, m0 + 64 * j, kb * BLOCK_K);
           }
+          // B: alone, the whole tile; in a pair, this CTA's half, multicast into both CTAs (same offsets, both full barriers)
+          constexpr int kBoxes = kBlockN / 64, kMyBoxes = kBoxes / kCl;
+          const int jb0 = (int)cta_rank * kMyBoxes;
           if (!kBMn) {
-            tma_load_2d(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN);
+            if (kCl == 1) tma_load_2d(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN);
+            else tma_load_2d_mc(sb + cta_rank * (L::B_BYTES / 2), &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN + (int)cta_rank * (kBlockN / 2), 3);
           } else if (p.b_im2col) {
             const int pix = kb * BLOCK_K;
             const int pq = p.P * p.Q;
@@ -545,14 +586,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
             const int pp = rem / p.Q, qq = rem - pp * p.Q;
             // columns are the flat (tap, cin) index; cin % 64 == 0, so every 64-wide box lies inside one tap
 #pragma unroll
-            for (int j = 0; j < kBlockN / 64; ++j) {
+            for (int jj = 0; jj < kMyBoxes; ++jj) {
+              const int j = jb0 + jj;
               const int col = tile_n * kBlockN + 64 * j;
               int tap = col / p.cin;
               int c0 = col - tap * p.cin;
               if (tap >= p.ksize * p.ksize) { tap = 0; c0 = p.cin; }     // past the last tap: channel OOB -> zero fill
               const int r = tap / p.ksize, ss = tap - r * p.ksize;
-              tma_load_im2col_4d(sb + j * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
-                                 (uint16_t)ss, (uint16_t)r);
+              if (kCl == 1)
+                tma_load_im2col_4d(sb + j * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
+                                   (uint16_t)ss, (uint16_t)r);
+              else
+                tma_load_im2col_4d_mc(sb + j * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
+                                      (uint16_t)ss, (uint16_t)r, 3);
             }
           } else {
             int row = kb * BLOCK_K, col0 = tile_n * kBlockN;
@@ -562,7 +608,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
               col0 += tap * p.b_tap_cols;
             }
 #pragma unroll
-            for (int j = 0; j < kBlockN / 64; ++j) tma_load_2d(sb + j * 8192, &p.tm_b, full, col0 + 64 * j, row);
+            for (int jj = 0; jj < kMyBoxes; ++jj) {
+              const int j = jb0 + jj;
+              if (kCl == 1) tma_load_2d(sb + j * 8192, &p.tm_b, full, col0 + 64 * j, row);
+              else tma_load_2d_mc(sb + j * 8192, &p.tm_b, full, col0 + 64 * j, row, 3);
+            }
           }
         }
       }
@@ -603,7 +653,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
               umma_bf16(tmem_acc + t * kBlockN, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(bar_empty + 8 * s);   // frees the smem slot once these MMAs have read it
+          if (kCl == 1) umma_commit(bar_empty + 8 * s);   // frees the smem slot once these MMAs have read it
+          else umma_commit_mc(bar_empty + 8 * s, 3);      // ... in both CTAs: the peer's multicast half lands in this slot too
         }
         umma_commit(bar_tfull + 8 * acc);   // accumulator complete
       }
@@ -622,18 +673,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
     Segment sg;
     for (; segs.next(sg); ++wi) {
       const int tile = sg.tile;
-      const int tile_n = tile % p.num_n_tiles, tile_m = tile / p.num_n_tiles;
+      const int tile_n = tile % p.num_n_tiles, tile_m = (tile / p.num_n_tiles) * kCl + (int)cta_rank;
       const int acc = wi % kAcc;
       const uint32_t aph = (wi / kAcc) & 1;
       const bool contributor = sg.kb0 > 0;                      // someone else owns this tile: park the partial sums
       const bool shared_owner = sg.kb0 == 0 && sg.kb1 < p.num_kb;
-      // CTAs blockIdx.x+1 .. last_contrib hold the rest of this tile (their ranges start inside it)
-      int last_contrib = blockIdx.x;
+      // scheduling units vcta+1 .. last_contrib hold the rest of this tile (their ranges start inside it); in a pair each
+      // CTA exchanges partials with the CTAs of the same rank (slot / flag index = unit * kCl + rank)
+      int last_contrib = vcta;
       if (shared_owner) {
         const long long tile_end = (long long)(tile + 1) * p.num_kb;
         while (last_contrib + 1 < p.sk_ctas && sk_begin(p.sk_units, last_contrib + 1, p.sk_ctas, p.sk_split, p.num_kb) < tile_end) ++last_contrib;
         if (warp == 2 && lane == 0)
-          for (int c = blockIdx.x + 1; c <= last_contrib; ++c) wait_flag(p.sk_flags + c);
+          for (int c = vcta + 1; c <= last_contrib; ++c) wait_flag(p.sk_flags + c * kCl + cta_rank);
         __syncwarp();
         epi_bar_sync();
       }
@@ -676,8 +728,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
                                  __uint_as_float(accv[4 * j + 3])));
             continue;
           }
-          for (int c = blockIdx.x + 1; c <= last_contrib; ++c) {       // fixed CTA order: deterministic sums
-            const float* src = p.sk_slots + (long long)c * kSlotFloats + chunk_off;
+          for (int c = vcta + 1; c <= last_contrib; ++c) {       // fixed CTA order: deterministic sums
+            const float* src = p.sk_slots + (long long)(c * kCl + cta_rank) * kSlotFloats + chunk_off;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j * (BLOCK_M * 4)));
@@ -706,12 +758,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       } else if (shared_owner) {
         epi_bar_sync();                      // every epilogue thread has read the slots: hand them back
         if (warp == 2 && lane == 0)
-          for (int c = blockIdx.x + 1; c <= last_contrib; ++c) p.sk_flags[c] = 0;
+          for (int c = vcta + 1; c <= last_contrib; ++c) p.sk_flags[c * kCl + cta_rank] = 0;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (kCl == 2) cluster_sync_all();        // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
@@ -785,20 +838,64 @@ static int make_im2col_map(CUtensorMap* tm, const PsgOperand& o, int channels_pe
   return PSG_OK;
 }
 
-template <int kBlockN, int kStages, int kMode, int kMT>
+template <int kBlockN, int kStages, int kMode, int kMT, int kCl>
 static int launch(const KernelParams& kp, dim3 grid, cudaStream_t stream) {
   using L = SmemLayout<kBlockN, kStages, kMT>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static bool configured = false;
-  auto kern = umma_gemm_kernel<kBlockN, kStages, kMode, kMT>;
+  auto kern = umma_gemm_kernel<kBlockN, kStages, kMode, kMT, kCl>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
     if (e != cudaSuccess) { psg_set_error("umma: cudaFuncSetAttribute(smem=%u): %s", L::TOTAL, cudaGetErrorString(e)); return PSG_ERR_CUDA; }
     configured = true;
   }
-  kern<<<grid, kNumThreads, L::TOTAL, stream>>>(kp);
+  if (kCl == 1) {
+    kern<<<grid, kNumThreads, L::TOTAL, stream>>>(kp);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, kp);
+    if (e != cudaSuccess) { psg_set_error("umma: cluster launch failed: %s", cudaGetErrorString(e)); return PSG_ERR_CUDA; }
+  }
   PSG_CHECK_LAUNCH("psg_umma_gemm");
   return PSG_OK;
+}
+
+// How many 2-CTA clusters of this kernel family can be resident at once (one CTA per SM; the SMs of a pair share a GPC).
+static int max_resident_pairs() {
+  static int pairs = -1;
+  if (pairs >= 0) return pairs;
+  using L = SmemLayout<256, 4, 1>;
+  auto kern = umma_gemm_kernel<256, 4, 0, 1, 2>;
+  pairs = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL) != cudaSuccess) { cudaGetLastError(); return pairs; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * 80);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return pairs; }
+  pairs = n;
+  return pairs;
 }
 
 }  // namespace umma
@@ -811,6 +908,12 @@ static constexpr int kMaxCtas = 160;
 static constexpr size_t kSlotBytes = (size_t)2 * 128 * 256 * sizeof(float);
 static void* g_sk_ws = nullptr;
 static int g_debug = 0;
+static int g_pairs_on = 1;
+
+// B-multicast CTA pairs on (1, default) / off (0): A/B switch for tools/bench_shapes.py.
+int psg_umma_pairs(int on) { g_pairs_on = on; return PSG_OK; }
+// Number of 2-CTA clusters that can be co-resident on this device (0 if cluster launch is unavailable).
+int psg_umma_max_pairs() { return umma::max_resident_pairs(); }
 
 // Profiling aid for tools/bench_shapes.py: 1 = drain TMEM but skip the epilogue body (mainloop time alone).
 int psg_umma_debug(int flags) { g_debug = flags; return PSG_OK; }
@@ -883,6 +986,13 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   kp.epi = d->epi;
   PSG_CHECK_ARG(d->split_k <= 1, "psg_umma_gemm: split-K is gone (stream-K scheduling balances the k-range itself)");
   plan_tiles(mode, d->M, d->N, d->K, &block_n, &m_tiles);
+  // B-multicast pairs: two CTAs on vertically adjacent row tiles share one B tile (each fetches half of it)
+  int cl = 1, units = psg_num_sms();
+  if (g_pairs_on && block_n % 128 == 0 && d->M > (long long)BLOCK_M * m_tiles) {
+    const int pairs = max_resident_pairs();
+    if (pairs >= 8) { cl = 2; units = pairs; }
+  }
+  if (units > kMaxCtas / cl) units = kMaxCtas / cl;
 
   long long n_tiles = (d->N + block_n - 1) / block_n;
   kp.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
@@ -908,7 +1018,7 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   }
   // ---- B operand ----
   if (mode == 0) {
-    rc = make_tiled_map(&kp.tm_b, d->b.ptr, d->N, d->K, d->b.ld, 64, block_n);
+    rc = make_tiled_map(&kp.tm_b, d->b.ptr, d->N, d->K, d->b.ld, 64, block_n / cl);
     if (rc) return rc;
   } else {
     PSG_CHECK_ARG(block_n % 64 == 0, "psg_umma_gemm: MN-major B needs block_n %% 64 == 0");
@@ -937,7 +1047,7 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
       if (rc) return rc;
     }
   }
-  const long long m_tiles_n = (d->M + BLOCK_M * m_tiles - 1) / (BLOCK_M * m_tiles);
+  const long long m_tiles_n = (d->M + BLOCK_M * m_tiles * cl - 1) / (BLOCK_M * m_tiles * cl);    // row tiles per scheduling unit
   const long long tiles = m_tiles_n * n_tiles;
   PSG_CHECK_ARG(tiles < 2147483647LL / 2, "psg_umma_gemm: too many tiles");
   kp.num_m_tiles = (int)m_tiles_n;
@@ -946,8 +1056,7 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   kp.debug = g_debug;
   // whole waves of tiles are dealt round-robin; the remainder is the stream-K region, each CTA's share of it being at
   // least max(8, num_kb / 8) k-blocks (at most ~8 CTAs per tile: the owner adds their partials serially)
-  int sms = psg_num_sms();
-  if (sms > kMaxCtas) sms = kMaxCtas;
+  const int sms = units;      // scheduling units: CTAs, or CTA pairs
   const long long sk_tiles = tiles % sms;
   long long ctas = tiles >= sms ? sms : 0, sk_ctas = 0;
   // reduction over activations (NT mode) bigger than the L2 can hold next to everything else: keep the k-ranges of all
@@ -976,12 +1085,16 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
       kp.sk_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(g_sk_ws) + 1024);
     }
   }
-  dim3 grid((unsigned)ctas);
+  dim3 grid((unsigned)(ctas * cl));
   cudaStream_t s = (cudaStream_t)stream;
 
-#define PSG_LAUNCH(BN, ST1, ST2, MODE)                              \
-  if (m_tiles == 1) return launch<BN, ST1, MODE, 1>(kp, grid, s);  \
-  else return launch<BN, ST2, MODE, 2>(kp, grid, s)
+#define PSG_LAUNCH(BN, ST1, ST2, MODE)                                                            \
+  if (BN % 128 == 0 && cl == 2) {                                                                 \
+    if (m_tiles == 1) return launch<BN, ST1, MODE, 1, (BN % 128 == 0 ? 2 : 1)>(kp, grid, s);     \
+    else return launch<BN, ST2, MODE, 2, (BN % 128 == 0 ? 2 : 1)>(kp, grid, s);                  \
+  }                                                                                               \
+  if (m_tiles == 1) return launch<BN, ST1, MODE, 1, 1>(kp, grid, s);                              \
+  else return launch<BN, ST2, MODE, 2, 1>(kp, grid, s)
   if (mode == 0) {
     switch (block_n) {
       case 64: PSG_LAUNCH(64, 6, 4, 0);

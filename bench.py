@@ -179,6 +179,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # rank 0 must print exactly one line on stdout
         dist.init_process_group("nccl", device_id=dev)
     L.check(L.load().psg_check_device(), "psg_check_device")
     W = max(args.warmup, 3)

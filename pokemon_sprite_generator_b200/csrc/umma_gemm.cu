@@ -10,11 +10,15 @@
 // kMode 2 ("TT"):  A as kMode 0, B MN-major: the weight matrix as stored ([N_w, K_w] row-major, conv weights
 //                  [Cout][tap][Cin]) read transposed -- dgrad needs no transposed weight copy.
 //
-// kCl == 2 ("B-multicast pairs"): two CTAs of a thread-block cluster take vertically adjacent 128*kMT-row tiles of the
-// same column block; each loads only HALF of the B tile and TMA-multicasts it into both CTAs' shared memory, so a CTA
-// pulls 32 KB instead of 48 KB through L2 per 128x256x64 block (the mainloop is L2->SM bound, not tensor-pipe bound) while
-// keeping its own double-buffered TMEM accumulators and its own cta_group::1 MMAs.  A stage is refilled only after BOTH
-// CTAs' MMAs have drained it (tcgen05.commit multicast onto both empty barriers).
+// kCl == 2 (CTA pairs, tcgen05 cta_group::2): two CTAs of a thread-block cluster compute ONE 256*kMT-row tile: each holds
+// its own 128*kMT rows of A and HALF of the B tile, the leader CTA (rank 0) issues tcgen05.mma.cta_group::2 (M = 256)
+// which reads both CTAs' shared memory and writes both CTAs' TMEM.  Per 128x256x64 block a CTA then moves 32+32 KB
+// through its shared memory instead of 48+48 KB: measured, the single-CTA mainloop is bound by shared-memory bandwidth
+// (TMA fill + MMA operand fetch ~190 B/clk wanted vs 128 B/clk), not by the tensor pipe and not by L2 (a B-multicast
+// variant that only cut the L2 reads gained 1%).  Protocol: each CTA's TMA producer fills its own stage, both counting their
+// bytes on the LEADER's full barrier (cp.async.bulk.tensor .cta_group::2); the leader's tcgen05.commit is multicast
+// onto both CTAs' empty / accumulator-full barriers; both CTAs' epilogue warps drain their own TMEM lanes and release
+// the accumulator on the leader's barrier.
 //
 // Scheduling is "data-parallel + stream-K": whole waves of tiles are dealt round-robin to the persistent CTAs; the
 // remainder tiles (all tiles, when there are fewer tiles than SMs) form a stream-K region whose (tile, k-block)
@@ -93,6 +97,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   atomicExch(&g_timeout_flag, 1);
 }
 
+// Polite wait for the epilogue warps: while the mainloop runs they have nothing to do, and eight warps spinning on
+// try_wait took issue slots from the single TMA and MMA threads that share their schedulers (ncu: 70% of all samples sat in
+// this loop; the per-k-block cost of the producer, not the tensor pipe, bounded the 128-row tiles).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(128);
+  }
+  atomicExch(&g_timeout_flag, 1);
+}
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -107,19 +122,32 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+// cta_group::2 forms: the data lands in THIS CTA's shared memory, the bytes are counted on `bar`, a shared::cluster address
+// that may name the barrier of the pair's leader CTA.
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_im2col_4d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h, int n,
-                                                      uint16_t off_w, uint16_t off_h, uint16_t mask) {
+__device__ __forceinline__ void tma_load_im2col_4d_2cta(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h, int n,
+                                                        uint16_t off_w, uint16_t off_h) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h), "h"(mask)
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
+}
+template <int kCl>
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  if (kCl == 1) tma_load_2d(dst, tm, bar, c0, c1);
+  else tma_load_2d_2cta(dst, tm, bar, c0, c1);
+}
+template <int kCl>
+__device__ __forceinline__ void tma_im2col(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h, int n, uint16_t off_w,
+                                           uint16_t off_h) {
+  if (kCl == 1) tma_load_im2col_4d(dst, tm, bar, c, w, h, n, off_w, off_h);
+  else tma_load_im2col_4d_2cta(dst, tm, bar, c, w, h, n, off_w, off_h);
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -136,12 +164,40 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+template <int kCl>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (kCl == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {      // one warp of EACH CTA of the pair executes this; both get the same column base
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int kCl>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if (kCl == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else          asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// the same barrier in the leader CTA (rank 0) of the pair, as a shared::cluster address
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local_bar) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_bar), "r"(0));
+  return r;
+}
+// relaxed on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR (~1 us), once per k-block that
+// serialised the whole pipeline (measured: 2x slower than one CTA).  What the arrive publishes was written by the async
+// proxy (TMA complete_tx already observed) or lives in TMEM (ordered by tcgen05.fence), not by this thread's stores.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -156,7 +212,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 // arrives on the barrier at the same shared-memory offset in every CTA of `mask` once the MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -185,10 +241,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn, int m = BLOCK_M) {
   return (1u << 4)                      // D = f32
          | (1u << 7) | (1u << 10)       // A, B = bf16
-         | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+         | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,17 +464,17 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int n) { return n <= 32 ? 3
 // kMT = number of 128-row MMA tiles stacked in one CTA tile (BLOCK_M = 128 * kMT).  The two MMAs of a k-step share
 // the B tile in shared memory, which halves the L2->SM bytes per FLOP of the weight operand; measured on B200 the
 // engine is bound by operand delivery (bytes per FLOP), not by the tensor pipe, so larger CTA tiles are what moves it.
-template <int kBlockN, int kStages, int kMT>
+template <int kBlockN, int kStages, int kMT, int kCl = 1>
 struct SmemLayout {
   static constexpr uint32_t A_TILE_BYTES = A_BYTES * kMT;
-  static constexpr uint32_t B_BYTES = kBlockN * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = kBlockN * BLOCK_K * 2 / kCl;      // a CTA of a pair holds half of the B tile
   static constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_BYTES;
   static constexpr int kAcc = (2 * kMT * kBlockN <= 512) ? 2 : 1;          // TMEM accumulator stages
   static constexpr uint32_t TMEM_COLS = tmem_cols_for(kAcc * kMT * kBlockN);
   static constexpr uint32_t EPI_OFFSET = STAGE_BYTES * kStages;         // one 2 KiB staging tile per epilogue warp
   static constexpr uint32_t EPI_BYTES = kEpiWarps * 2048;
   static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
-  static constexpr uint32_t TOTAL = BAR_OFFSET + (2 * kStages + 4) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr uint32_t TOTAL = BAR_OFFSET + (3 * kStages + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -488,21 +544,22 @@ __device__ __forceinline__ void wait_flag(const int* flag) {
 // ---------------------------------------------------------------------------------------------
 template <int kBlockN, int kStages, int kMode, int kMT, int kCl>
 __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_constant__ KernelParams p) {
-  using L = SmemLayout<kBlockN, kStages, kMT>;
+  using L = SmemLayout<kBlockN, kStages, kMT, kCl>;
   constexpr int kAcc = L::kAcc;
-  constexpr int BM = BLOCK_M * kMT;
+  constexpr int BM = BLOCK_M * kMT;          // rows of this CTA's share of the tile
   static_assert(kBlockN % 32 == 0 && kBlockN <= 256, "BLOCK_N must be a multiple of 32 (epilogue chunk) and <= 256");
   static_assert(kMode == 0 || kBlockN % 64 == 0, "MN-major B tiles are built from 64-wide TMA boxes");
   constexpr bool kAMn = (kMode == 1), kBMn = (kMode >= 1);
-  static_assert(kCl == 1 || (kCl == 2 && kBlockN % 128 == 0), "B-multicast pairs split the B tile in two halves of whole 64-wide boxes");
-  const uint32_t cta_rank = (kCl == 2) ? cluster_ctarank() : 0u;     // which half of B this CTA fetches, which row tile it owns
+  static_assert(kCl == 1 || (kCl == 2 && kBlockN % 128 == 0), "CTA pairs split the B tile in two halves of whole 64-wide boxes");
+  const uint32_t cta_rank = (kCl == 2) ? cluster_ctarank() : 0u;     // which half of B / which 128-row halves of the tile are this CTA's
   const int vcta = blockIdx.x / kCl, vctas = gridDim.x / kCl;        // scheduling unit: a CTA, or a CTA pair
   static_assert(kMT * kBlockN <= 512, "accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = smem + L::BAR_OFFSET;
   const uint32_t bar_empty = bar_full + 8 * kStages;
-  const uint32_t bar_tfull = bar_empty + 8 * kStages;     // [kAcc] accumulator ready for the epilogue
+  const uint32_t bar_pfull = bar_empty + 8 * kStages;     // [kStages] pair only, used in the leader: the peer's stage is full
+  const uint32_t bar_tfull = bar_pfull + 8 * kStages;     // [kAcc] accumulator ready for the epilogue
   const uint32_t bar_tempty = bar_tfull + 16;             // [kAcc] accumulator drained by the epilogue
   const uint32_t tmem_slot = bar_tempty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -513,14 +570,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tm_a);
     prefetch_tmap(&p.tm_b);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, kCl); }   // empty: every CTA's MMAs
-    for (int a = 0; a < kAcc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kEpiWarps); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_pfull + 8 * s, 1); }
+    for (int a = 0; a < kAcc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kCl * kEpiWarps); }   // both CTAs' epilogues
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
+  if (warp == 1) tmem_alloc<kCl>(tmem_slot, L::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if (kCl == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast at them
+  if (kCl == 2) cluster_sync_all();        // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -532,15 +589,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       Segment sg;
       while (segs.next(sg)) {
         const int tile = sg.tile;
-        const int tile_n = tile % p.num_n_tiles, tile_m = (tile / p.num_n_tiles) * kCl + (int)cta_rank;
-        const int m0 = tile_m * BM;
+        const int tile_n = tile % p.num_n_tiles, tile_m = tile / p.num_n_tiles;
+        // rows of this CTA's t-th 128-row sub-tile: m0 + t * kRowStep (alone: consecutive; in a pair the t-th MMA spans 256 rows)
+        constexpr int kRowStep = BLOCK_M * kCl;
+        const int m0 = tile_m * (BM * kCl) + (int)cta_rank * BLOCK_M;
         const int kb0 = sg.kb0, kb1 = sg.kb1;
         int w0[kMT], h0[kMT], img0[kMT];
         if (!kAMn && p.a_im2col) {
           const int pq = p.P * p.Q;
 #pragma unroll
           for (int t = 0; t < kMT; ++t) {
-            const int mm = m0 + t * BLOCK_M;
+            const int mm = m0 + t * kRowStep;
             img0[t] = mm / pq;
             const int rem = mm - img0[t] * pq;
             const int pp = rem / p.Q, qq = rem - pp * p.Q;
@@ -552,8 +611,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const uint32_t full = bar_full + 8 * s;
-          mbar_expect_tx(full, L::STAGE_BYTES);
+          // in a pair both CTAs' loads are counted on the LEADER's full barrier (the leader issues the MMAs)
+          const uint32_t full = (kCl == 2) ? leader_addr(bar_full + 8 * s) : bar_full + 8 * s;
+          if (kCl == 1 || cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, kCl * L::STAGE_BYTES);
           const uint32_t sa = smem + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_TILE_BYTES;
           if (!kAMn) {
@@ -563,21 +623,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
               if (p.flip) { r = p.ksize - 1 - r; ss = p.ksize - 1 - ss; }
 #pragma unroll
               for (int t = 0; t < kMT; ++t)
-                tma_load_im2col_4d(sa + t * A_BYTES, &p.tm_a, full, cb * BLOCK_K, w0[t], h0[t], img0[t], (uint16_t)ss, (uint16_t)r);
+                tma_im2col<kCl>(sa + t * A_BYTES, &p.tm_a, full, cb * BLOCK_K, w0[t], h0[t], img0[t], (uint16_t)ss, (uint16_t)r);
             } else {
 #pragma unroll
-              for (int t = 0; t < kMT; ++t) tma_load_2d(sa + t * A_BYTES, &p.tm_a, full, kb * BLOCK_K, m0 + t * BLOCK_M);
+              for (int t = 0; t < kMT; ++t) tma_2d<kCl>(sa + t * A_BYTES, &p.tm_a, full, kb * BLOCK_K, m0 + t * kRowStep);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &p.tm_a, full, m0 + 64 * j, kb * BLOCK_K);
+            for (int j = 0; j < BM / 64; ++j) tma_2d<kCl>(sa + j * 8192, &p.tm_a, full, m0 + (j >> 1) * kRowStep + 64 * (j & 1), kb * BLOCK_K);
           }
-          // B: alone, the whole tile; in a pair, this CTA's half, multicast into both CTAs (same offsets, both full barriers)
-          constexpr int kBoxes = kBlockN / 64, kMyBoxes = kBoxes / kCl;
+          // B: alone, the whole tile; in a pair, this CTA's half of it (the MMA reads the other half from the peer's smem)
+          constexpr int kMyBoxes = kBlockN / 64 / kCl;
           const int jb0 = (int)cta_rank * kMyBoxes;
           if (!kBMn) {
-            if (kCl == 1) tma_load_2d(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN);
-            else tma_load_2d_mc(sb + cta_rank * (L::B_BYTES / 2), &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN + (int)cta_rank * (kBlockN / 2), 3);
+            tma_2d<kCl>(sb, &p.tm_b, full, kb * BLOCK_K, tile_n * kBlockN + (int)cta_rank * (kBlockN / kCl));
           } else if (p.b_im2col) {
             const int pix = kb * BLOCK_K;
             const int pq = p.P * p.Q;
@@ -587,18 +646,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
             // columns are the flat (tap, cin) index; cin % 64 == 0, so every 64-wide box lies inside one tap
 #pragma unroll
             for (int jj = 0; jj < kMyBoxes; ++jj) {
-              const int j = jb0 + jj;
-              const int col = tile_n * kBlockN + 64 * j;
+              const int col = tile_n * kBlockN + 64 * (jb0 + jj);
               int tap = col / p.cin;
               int c0 = col - tap * p.cin;
               if (tap >= p.ksize * p.ksize) { tap = 0; c0 = p.cin; }     // past the last tap: channel OOB -> zero fill
               const int r = tap / p.ksize, ss = tap - r * p.ksize;
-              if (kCl == 1)
-                tma_load_im2col_4d(sb + j * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
-                                   (uint16_t)ss, (uint16_t)r);
-              else
-                tma_load_im2col_4d_mc(sb + j * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
-                                      (uint16_t)ss, (uint16_t)r, 3);
+              tma_im2col<kCl>(sb + jj * 8192, &p.tm_b, full, c0, qq * p.conv_stride - p.pad, pp * p.conv_stride - p.pad, img,
+                                 (uint16_t)ss, (uint16_t)r);
             }
           } else {
             int row = kb * BLOCK_K, col0 = tile_n * kBlockN;
@@ -608,11 +662,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
               col0 += tap * p.b_tap_cols;
             }
 #pragma unroll
-            for (int jj = 0; jj < kMyBoxes; ++jj) {
-              const int j = jb0 + jj;
-              if (kCl == 1) tma_load_2d(sb + j * 8192, &p.tm_b, full, col0 + 64 * j, row);
-              else tma_load_2d_mc(sb + j * 8192, &p.tm_b, full, col0 + 64 * j, row, 3);
-            }
+            for (int jj = 0; jj < kMyBoxes; ++jj) tma_2d<kCl>(sb + jj * 8192, &p.tm_b, full, col0 + 64 * (jb0 + jj), row);
           }
         }
       }
@@ -620,8 +670,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(kBlockN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+      if (kCl == 2 && cta_rank != 0) {
+        // ===== peer of a pair: nothing to issue (its TMA loads are counted on the leader's barriers) =====
+      } else {
+      // ===== MMA issuer (alone, or leader of a pair: one instruction drives both CTAs' tensor cores) =====
+      // kNSplit > 1 issues the tile as independent column halves per k-step (experiment: does a single dependent
+      // accumulator chain leave a bubble in the tensor pipe? it does not).
+      constexpr int kNSplit = 1;   // (2 was measured: 8% slower -- the smaller MMAs cost more than the dependency they remove)
+      constexpr int kMmaN = kBlockN / kNSplit;
+      constexpr uint32_t idesc = make_idesc(kMmaN, kAMn ? 1 : 0, kBMn ? 1 : 0, BLOCK_M * kCl);
       uint32_t it = 0;
       int wi = 0;   // local segment counter -> accumulator stage and phase
       PSG_SEGMENTS(p);
@@ -630,7 +687,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
         const int kb0 = sg.kb0, kb1 = sg.kb1;
         const int acc = wi % kAcc;
         const uint32_t aph = (wi / kAcc) & 1;
-        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);       // epilogue has drained this accumulator
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);       // the epilogue (of both CTAs) has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc * (kMT * kBlockN);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -642,21 +699,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
           const uint32_t sb = sa + L::A_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            uint64_t bd;
-            if (!kBMn) bd = make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            else       bd = make_desc(sb + k * (UMMA_K * 128), 8192, 1024);
 #pragma unroll
-            for (int t = 0; t < kMT; ++t) {
-              uint64_t ad;
-              if (!kAMn) ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 2), 16, 1024);
-              else       ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 128), 8192, 1024);
-              umma_bf16(tmem_acc + t * kBlockN, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int h = 0; h < kNSplit; ++h) {
+              // column half h of the B tile: rows h*kMmaN.. (K-major) / boxes h*kMmaN/64.. (MN-major) = h * B_BYTES / kNSplit bytes
+              const uint32_t sbh = sb + h * (L::B_BYTES / kNSplit);
+              uint64_t bd;
+              if (!kBMn) bd = make_desc(sbh + k * (UMMA_K * 2), 16, 1024);
+              else       bd = make_desc(sbh + k * (UMMA_K * 128), 8192, 1024);
+#pragma unroll
+              for (int t = 0; t < kMT; ++t) {
+                uint64_t ad;
+                if (!kAMn) ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 2), 16, 1024);
+                else       ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 128), 8192, 1024);
+                if (kCl == 1) umma_bf16(tmem_acc + t * kBlockN + h * kMmaN, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                else          umma_bf16_2cta(tmem_acc + t * kBlockN + h * kMmaN, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
             }
           }
           if (kCl == 1) umma_commit(bar_empty + 8 * s);   // frees the smem slot once these MMAs have read it
-          else umma_commit_mc(bar_empty + 8 * s, 3);      // ... in both CTAs: the peer's multicast half lands in this slot too
+          else umma_commit_mc(bar_empty + 8 * s, 3);      // ... in both CTAs
         }
-        umma_commit(bar_tfull + 8 * acc);   // accumulator complete
+        if (kCl == 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
+        else umma_commit_mc(bar_tfull + 8 * acc, 3);      // ... for both CTAs' epilogue warps
+      }
       }
     }
     __syncwarp();
@@ -673,7 +738,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
     Segment sg;
     for (; segs.next(sg); ++wi) {
       const int tile = sg.tile;
-      const int tile_n = tile % p.num_n_tiles, tile_m = (tile / p.num_n_tiles) * kCl + (int)cta_rank;
+      const int tile_n = tile % p.num_n_tiles, tile_m = tile / p.num_n_tiles;
+      const long long tile_row0 = (long long)tile_m * (BM * kCl) + (long long)cta_rank * BLOCK_M;   // + t * BLOCK_M * kCl per sub-tile
       const int acc = wi % kAcc;
       const uint32_t aph = (wi / kAcc) & 1;
       const bool contributor = sg.kb0 > 0;                      // someone else owns this tile: park the partial sums
@@ -695,7 +761,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
         // while the MMAs of this tile are still running: pull the epilogue's input tiles towards L2
 #pragma unroll 1
         for (int t = 0; t < kMT; ++t) {
-          const long long m = (long long)tile_m * BM + t * BLOCK_M + row;
+          const long long m = tile_row0 + (long long)t * (BLOCK_M * kCl) + row;
           if (m >= p.M) continue;
 #pragma unroll 1
           for (int ch = cslot; ch < kChunks; ch += kEpiWarps / 4) {
@@ -707,12 +773,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
           }
         }
       }
-      mbar_wait(bar_tfull + 8 * acc, aph);
+      mbar_wait_backoff(bar_tfull + 8 * acc, aph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * (kMT * kBlockN);
 #pragma unroll 1
       for (int t = 0; t < kMT; ++t) {
-        const long long m_base = (long long)tile_m * BM + t * BLOCK_M + q * 32;
+        const long long m_base = tile_row0 + (long long)t * (BLOCK_M * kCl) + q * 32;
 #pragma unroll 1
         for (int ch = cslot; ch < kChunks; ch += kEpiWarps / 4) {
           uint32_t accv[32];
@@ -747,7 +813,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if (kCl == 2 && cta_rank != 0) mbar_arrive_remote(leader_addr(bar_tempty + 8 * acc));   // the leader issues the MMAs
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       if (contributor) {
         __threadfence();                     // partial sums visible device-wide before the flag
         epi_bar_sync();
@@ -765,7 +834,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   if (kCl == 2) cluster_sync_all();        // the peer may still multicast into this CTA's smem / arrive on its barriers
-  if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
+  if (warp == 1) tmem_dealloc<kCl>(tmem_base, L::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -840,7 +909,7 @@ static int make_im2col_map(CUtensorMap* tm, const PsgOperand& o, int channels_pe
 
 template <int kBlockN, int kStages, int kMode, int kMT, int kCl>
 static int launch(const KernelParams& kp, dim3 grid, cudaStream_t stream) {
-  using L = SmemLayout<kBlockN, kStages, kMT>;
+  using L = SmemLayout<kBlockN, kStages, kMT, kCl>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   auto kern = umma_gemm_kernel<kBlockN, kStages, kMode, kMT, kCl>;
@@ -872,12 +941,24 @@ static int launch(const KernelParams& kp, dim3 grid, cudaStream_t stream) {
   return PSG_OK;
 }
 
+// CTA-pair launch: a pair CTA's stage holds only half of B (BN 128: 24 / 40 KB, BN 256: 32 / 48 KB), so it gets more stages.
+template <int kBlockN, int kMode>
+static int launch_pair(const KernelParams& kp, dim3 grid, cudaStream_t stream, int m_tiles) {
+  if constexpr (kBlockN % 128 == 0) {
+    if (m_tiles == 1) return launch<kBlockN, (kBlockN == 128 ? 8 : 6), kMode, 1, 2>(kp, grid, stream);
+    return launch<kBlockN, (kBlockN == 128 ? 5 : 4), kMode, 2, 2>(kp, grid, stream);
+  } else {
+    psg_set_error("psg_umma_gemm: CTA pairs need block_n %% 128 == 0");
+    return PSG_ERR_UNSUPPORTED;
+  }
+}
+
 // How many 2-CTA clusters of this kernel family can be resident at once (one CTA per SM; the SMs of a pair share a GPC).
 static int max_resident_pairs() {
   static int pairs = -1;
   if (pairs >= 0) return pairs;
-  using L = SmemLayout<256, 4, 1>;
-  auto kern = umma_gemm_kernel<256, 4, 0, 1, 2>;
+  using L = SmemLayout<256, 6, 1, 2>;
+  auto kern = umma_gemm_kernel<256, 6, 0, 1, 2>;
   pairs = 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL) != cudaSuccess) { cudaGetLastError(); return pairs; }
   cudaLaunchConfig_t cfg;
@@ -910,7 +991,7 @@ static void* g_sk_ws = nullptr;
 static int g_debug = 0;
 static int g_pairs_on = 1;
 
-// B-multicast CTA pairs on (1, default) / off (0): A/B switch for tools/bench_shapes.py.
+// CTA pairs (cta_group::2): 0 = never, 1 = where they were measured to pay (default), 2 = wherever the shape allows.
 int psg_umma_pairs(int on) { g_pairs_on = on; return PSG_OK; }
 // Number of 2-CTA clusters that can be co-resident on this device (0 if cluster launch is unavailable).
 int psg_umma_max_pairs() { return umma::max_resident_pairs(); }
@@ -929,7 +1010,7 @@ int psg_umma_set_workspace(void* ws, size_t bytes) {
 }
 
 // Tile-shape heuristic shared by the auto path and psg_umma_plan.
-static void plan_tiles(int mode, long long M, long long N, long long K, int* block_n, int* m_tiles) {
+static void plan_tiles(int mode, int b_im2col, long long M, long long N, long long K, int* block_n, int* m_tiles) {
   int bn = *block_n;
   if (bn == 0) {
     if (mode == 0) {
@@ -946,8 +1027,11 @@ static void plan_tiles(int mode, long long M, long long N, long long K, int* blo
     mt = 1;
     // 256-row CTA tiles (two MMAs share the B tile) pay off for long reductions with no extra row padding; short-K
     // GEMMs prefer 128-row tiles with double-buffered TMEM (epilogue overlap).  Stream-K balances any tile count.
-    // The NT (wgrad) mode runs ~1.6x faster per MMA row with 256-row tiles, so it takes them even with padded rows.
-    if (M > 128 && ((mode == 1 && pad2 * 2 <= pad1 * 3) || (pad2 == pad1 && K >= 2048))) mt = 2;
+    // The conv wgrad (NT over im2col pixels) runs ~1.6x faster per MMA row with 256-row tiles, so it takes them even with
+    // padded rows; the plain NT products (Linear wgrad) were measured faster with 128-row tiles unless 256 divides M.
+    if (M > 128 && ((mode == 1 && b_im2col && pad2 * 2 <= pad1 * 3) || (mode == 1 && !b_im2col && pad2 == pad1 && N >= 1024) ||
+                    (mode != 1 && pad2 == pad1 && K >= 2048)))
+      mt = 2;
   }
   *block_n = bn;
   *m_tiles = mt;
@@ -957,7 +1041,7 @@ static void plan_tiles(int mode, long long M, long long N, long long K, int* blo
 int psg_umma_plan(const PsgGemmDesc* d, int* block_n, int* m_tiles) {
   PSG_CHECK_ARG(d && block_n && m_tiles, "psg_umma_plan: null pointer");
   const int mode = (d->a.mode == PSG_OP_MNMAJOR) ? 1 : ((d->b.mode == PSG_OP_MNMAJOR || d->b.mode == PSG_OP_CONVW_T) ? 2 : 0);
-  plan_tiles(mode, d->M, d->N, d->K, block_n, m_tiles);
+  plan_tiles(mode, d->b.mode == PSG_OP_IM2COL_T, d->M, d->N, d->K, block_n, m_tiles);
   return PSG_OK;
 }
 
@@ -985,11 +1069,17 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   kp.N = (int)d->N;
   kp.epi = d->epi;
   PSG_CHECK_ARG(d->split_k <= 1, "psg_umma_gemm: split-K is gone (stream-K scheduling balances the k-range itself)");
-  plan_tiles(mode, d->M, d->N, d->K, &block_n, &m_tiles);
+  plan_tiles(mode, bm == PSG_OP_IM2COL_T, d->M, d->N, d->K, &block_n, &m_tiles);
   // B-multicast pairs: two CTAs on vertically adjacent row tiles share one B tile (each fetches half of it)
+  // CTA pairs (cta_group::2).  Measured on this model's shapes (profiles/r01_bench_gemm_modes.txt): a gain of 10-25% for
+  // the NT (wgrad) reductions when the 2x taller pair tile does not add much row padding, nothing for TN / TT (equal to a
+  // single CTA within noise, slightly worse at short K) -- so only the former use them unless forced (psg_umma_pairs(2)).
   int cl = 1, units = psg_num_sms();
   if (g_pairs_on && block_n % 128 == 0 && d->M > (long long)BLOCK_M * m_tiles) {
-    const int pairs = max_resident_pairs();
+    const long long rows1 = (d->M + BLOCK_M * m_tiles - 1) / (BLOCK_M * m_tiles) * (BLOCK_M * m_tiles);
+    const long long rows2 = (d->M + 2 * BLOCK_M * m_tiles - 1) / (2 * BLOCK_M * m_tiles) * (2 * BLOCK_M * m_tiles);
+    const bool worth = g_pairs_on == 2 || (mode == 1 && rows2 * 4 <= rows1 * 5);
+    const int pairs = worth ? max_resident_pairs() : 0;
     if (pairs >= 8) { cl = 2; units = pairs; }
   }
   if (units > kMaxCtas / cl) units = kMaxCtas / cl;
@@ -1089,10 +1179,7 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   cudaStream_t s = (cudaStream_t)stream;
 
 #define PSG_LAUNCH(BN, ST1, ST2, MODE)                                                            \
-  if (BN % 128 == 0 && cl == 2) {                                                                 \
-    if (m_tiles == 1) return launch<BN, ST1, MODE, 1, (BN % 128 == 0 ? 2 : 1)>(kp, grid, s);     \
-    else return launch<BN, ST2, MODE, 2, (BN % 128 == 0 ? 2 : 1)>(kp, grid, s);                  \
-  }                                                                                               \
+  if (cl == 2) return launch_pair<BN, MODE>(kp, grid, s, m_tiles);                                \
   if (m_tiles == 1) return launch<BN, ST1, MODE, 1, 1>(kp, grid, s);                              \
   else return launch<BN, ST2, MODE, 2, 1>(kp, grid, s)
   if (mode == 0) {

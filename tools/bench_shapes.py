@@ -75,6 +75,10 @@ def epi_sweep(M=50176, N=1280, K=640):
         timeit(lambda: G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out, **kw), engine="umma"), 2.0 * M * N * K, f"EPI {M}x{N}x{K} {name}")
 
 
+import os
+if os.environ.get("PSG_PAIRS") is not None:
+    from pokemon_sprite_generator_b200 import _lib as _L
+    _L.load().psg_umma_pairs(int(os.environ["PSG_PAIRS"]))
 B = 256
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "wgrad"):

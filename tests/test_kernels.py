@@ -203,6 +203,20 @@ def test_layout_and_reductions(cuda_device, dtype):
     ref = 0.5 * a.float().view(groups, -1, C_).sum(1)
     assert torch.allclose(og, ref, rtol=1e-4, atol=1e-3)
     assert torch.allclose(ot, 1.0 + ref.sum(0), rtol=1e-4, atol=1e-3)
+    # ungrouped total only (bias gradient): single-launch kernel, alternating with the grouped path on the same workspace,
+    # bit-reproducible, wide matrices in column chunks
+    for rows2, c2 in ((50176, 640), (777, 320), (256, 15360)):
+        b2 = torch.randn(rows2, c2, device="cuda").to(dtype)
+        t1, t2 = torch.empty(c2, device="cuda"), torch.full((c2,), 2.0, device="cuda")
+        K.colsum(b2, 1, None, t1)
+        K.colsum(a, groups, og, None)
+        K.colsum(b2, 1, None, t2, acc_total=True, scale=-1.0)
+        ref2 = b2.float().sum(0)
+        assert torch.allclose(t1, ref2, rtol=1e-4, atol=2e-2 * rows2 ** 0.5), (rows2, c2)
+        assert torch.allclose(t2, 2.0 - ref2, rtol=1e-4, atol=2e-2 * rows2 ** 0.5)
+        t3 = torch.empty(c2, device="cuda")
+        K.colsum(b2, 1, None, t3)
+        assert torch.equal(t1, t3)
     # zero insertion
     dy = torch.randn(2 * 14 * 14, 64, device="cuda").to(dtype)
     dil = torch.empty(2 * 27 * 27, 64, device="cuda", dtype=dtype)

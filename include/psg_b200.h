@@ -176,6 +176,9 @@ int psg_timestep_embedding(const long long* t, const float* coeff, float* out, i
 int psg_mean_pool(const float* x, float* out, int B, int L, int D, void* stream);
 int psg_pack_conv_weight(const float* w_oihw, void* wp, void* wd, int Cout, int Cin, int kk, int Cin_p, int Cout_p, int dtype,
                          void* stream);
+/* every tap-major bf16 conv weight [Cout][kk][Cin] -> dgrad layout [Cin][kk][Cout] in one launch; jobs = n x {src offset, dst offset,
+ * Cout, Cin, kk} (elements), host array */
+int psg_conv_weights_transpose(const void* src_base, void* dst_base, const long long* jobs, int n, void* stream);
 int psg_pack_linear_weight(const float* w, void* wk, void* wt, int N, int K, int dtype, void* stream);
 int psg_wgrad_finalize(const float* partial, int splits, long long split_stride, float* grad_oihw, int Cout, int Cin, int kk,
                        int Cin_p, int accumulate, void* stream);

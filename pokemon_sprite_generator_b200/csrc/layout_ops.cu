@@ -150,6 +150,45 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
   }
 }
 
+// ---- conv weights, tap-major bf16 [Cout][kk][Cin] -> dgrad layout [Cin][kk][Cout], every conv of the model in ONE launch ----
+// (dgrad then reads a K-major B operand like fprop does: the transposed-in-place MN-major read cost 10-20% per GEMM)
+struct TransposeJobs {
+  static constexpr int kMax = 64;
+  int n;
+  int tile_begin[kMax + 1];          // prefix sums of 64x64 tiles over (cin block, cout block, tap)
+  long long src[kMax], dst[kMax];    // element offsets into the two bf16 buffers
+  int cout[kMax], cin[kMax], kk[kMax];
+};
+
+__global__ void __launch_bounds__(256) conv_weight_transpose_kernel(const __nv_bfloat16* __restrict__ src_base,
+                                                                     __nv_bfloat16* __restrict__ dst_base, const TransposeJobs jobs) {
+  __shared__ __nv_bfloat16 tile[64][72];
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.tile_begin[j + 1]) ++j;
+  const int t = blockIdx.x - jobs.tile_begin[j];
+  const int Cout = jobs.cout[j], Cin = jobs.cin[j], kk = jobs.kk[j];
+  const int cib = Cin / 64, cob = Cout / 64;
+  const int tap = t / (cib * cob), r = t - tap * (cib * cob);
+  const int co0 = (r / cib) * 64, ci0 = (r % cib) * 64;
+  const __nv_bfloat16* src = src_base + jobs.src[j];
+  __nv_bfloat16* dst = dst_base + jobs.dst[j];
+  // 64 rows (co) x 8 vectors of 8 ci
+  for (int idx = threadIdx.x; idx < 512; idx += 256) {
+    const int row = idx >> 3, v = idx & 7;
+    const uint4 val = *reinterpret_cast<const uint4*>(src + ((long long)(co0 + row) * kk + tap) * Cin + ci0 + v * 8);
+    *reinterpret_cast<uint4*>(&tile[row][v * 8]) = val;
+  }
+  __syncthreads();
+  // 64 rows (ci) x 8 vectors of 8 co
+  for (int idx = threadIdx.x; idx < 512; idx += 256) {
+    const int row = idx >> 3, v = idx & 7;
+    __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = tile[v * 8 + e][row];
+    *reinterpret_cast<uint4*>(dst + ((long long)(ci0 + row) * kk + tap) * Cout + co0 + v * 8) = *reinterpret_cast<const uint4*>(out);
+  }
+}
+
 // ---- bilinear resize (align_corners=False), token-major ----------------------------------------------------
 __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
   float s = scale * ((float)dst + 0.5f) - 0.5f;
@@ -538,6 +577,26 @@ int psg_pack_conv_weight(const float* w, void* wp, void* wd, int Cout, int Cin, 
   const size_t smem = (size_t)32 * (32 * kk + 1) * sizeof(float);
   DISPATCH_T(dtype, (pack_conv_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (T*)wp, (T*)wd, Cout, Cin, kk, Cin_p, Cout_p)));
   PSG_CHECK_LAUNCH("psg_pack_conv_weight");
+  return PSG_OK;
+}
+
+// jobs: n x {src element offset, dst element offset, Cout, Cin, kk} (host array of long long[5]); channels % 64 == 0.
+int psg_conv_weights_transpose(const void* src_base, void* dst_base, const long long* jobs, int n, void* stream) {
+  PSG_CHECK_ARG(src_base && dst_base && jobs && n > 0 && n <= TransposeJobs::kMax, "psg_conv_weights_transpose: bad args (n=%d)", n);
+  TransposeJobs tj;
+  tj.n = n;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const long long* j = jobs + 5 * i;
+    PSG_CHECK_ARG(j[2] % 64 == 0 && j[3] % 64 == 0 && j[4] > 0 && j[0] % 8 == 0 && j[1] % 8 == 0,
+                  "psg_conv_weights_transpose: job %d: channels must be multiples of 64 and offsets of 8", i);
+    tj.tile_begin[i] = tiles;
+    tj.src[i] = j[0]; tj.dst[i] = j[1]; tj.cout[i] = (int)j[2]; tj.cin[i] = (int)j[3]; tj.kk[i] = (int)j[4];
+    tiles += (int)(j[2] / 64 * (j[3] / 64) * j[4]);
+  }
+  tj.tile_begin[n] = tiles;
+  conv_weight_transpose_kernel<<<tiles, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_base, (__nv_bfloat16*)dst_base, tj);
+  PSG_CHECK_LAUNCH("psg_conv_weights_transpose");
   return PSG_OK;
 }
 

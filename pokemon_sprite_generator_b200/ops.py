@@ -104,6 +104,13 @@ def pack_conv_weight(w: torch.Tensor, wp: torch.Tensor | None, wd: torch.Tensor 
            C.c_int(cin_p or cin), C.c_int(cout_p or cout), C.c_int(L.dt(ref)), L.stream_ptr())
 
 
+def conv_weights_transpose(src_base: torch.Tensor, dst_base: torch.Tensor, jobs) -> None:
+    """jobs: list of (src element offset, dst element offset, Cout, Cin, kk); one launch for all of them."""
+    assert src_base.dtype == torch.bfloat16 and dst_base.dtype == torch.bfloat16
+    arr = (C.c_longlong * (5 * len(jobs)))(*[int(v) for j in jobs for v in j])
+    L.call("psg_conv_weights_transpose", L.ptr(src_base), L.ptr(dst_base), arr, C.c_int(len(jobs)), L.stream_ptr())
+
+
 def pack_linear_weight(w: torch.Tensor, wk: torch.Tensor | None, wt: torch.Tensor | None) -> None:
     n, k = w.shape
     ref = wk if wk is not None else wt

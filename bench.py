@@ -127,6 +127,15 @@ def cpu_reference_steps(steps: int, warmup: int, batch: int = 2):
     return {"samples_per_s": batch / sec, "ms_per_step": sec * 1e3, "cores": torch.get_num_threads(), "batch": batch, "steps": steps}
 
 
+def workload_config(B: int, Lt: int, heads: int, dropout: bool, world: int) -> dict:
+    """`config` of both arms (the reference arm times a bounded sample of this workload on the host cores)."""
+    return {"workload": f"U-Net diffusion train step (config 2), 27x27x8 latents, batch {B}/GPU, bf16 compute + fp32 master, "
+                        f"1000-step cosine schedule, {Lt}x256 text emb, AdamW + clip 0.7 + OneCycleLR, dropout "
+                        f"{'on' if dropout else 'off'}, heads {heads}",
+            "global_batch": world * B, "parallelism": f"dp{world}",
+            "l2": "per-step working set (>10 GB activations + 1.3 GB bf16 weights) far exceeds the 126 MB L2"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,8 +144,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "U-Net diffusion train step, 27x27x8 latents, 1000-step cosine schedule, 32x256 text emb",
-                       "sample": f"batch {r['batch']} per step on the host CPU"},
+            "config": dict(workload_config(args.batch, args.text_len, args.heads, not args.no_dropout, max(1, args.gpus)),
+                           sample=f"the reference algorithm's fp32 step at batch {r['batch']} per step on the host CPU (same graph, "
+                                  f"same optimiser; samples/s does not depend on the batch split)"),
             "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                              "sample": f"{args.steps} steps of batch {r['batch']} (oracle port of the reference step, fp32)"},
             "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -310,11 +320,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": Ksteps, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": f"U-Net diffusion train step (config 2), 27x27x8 latents, batch {B}/GPU, bf16 compute + fp32 master, "
-                                       f"1000-step cosine schedule, {Lt}x256 text emb, AdamW + clip 0.7 + OneCycleLR, dropout "
-                                       f"{'off' if args.no_dropout else 'on'}, heads {args.heads}",
-                           "global_batch": world * B, "parallelism": f"dp{world}",
-                           "l2": "per-step working set (>10 GB activations + 2.6 GB weights) far exceeds the 126 MB L2"},
+                "config": workload_config(B, Lt, args.heads, not args.no_dropout, world),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "denoise": denoise, "loss": final_loss}
         print(json.dumps(line), flush=True)

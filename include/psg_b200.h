@@ -128,6 +128,13 @@ int psg_groupnorm_bwd(const void* dy, long long ld_dy, const void* x, long long 
  * gradients of the conv bias and of the broadcast time/text conditioning that produced x (unet.py:116-124).           */
 int psg_groupnorm_fused_ok(int B, int HW, int C, int G, int dtype);
 int psg_groupnorm_fused_plan(int B, int HW, int C, int G, int* out8);
+/* The fused entry points run the cluster-split kernels (norm_cluster.cu: pixels of a (sample, 160-channel) unit split over
+ * the CTAs of a thread-block cluster, partial sums exchanged through distributed shared memory) where their plan applies
+ * and the slab kernels otherwise.  psg_groupnorm_fused_mode(1) forces the slab kernels (A/B measurements); returns the
+ * previous mode.  psg_groupnorm_cluster_plan: out8 = {CC, cluster size, rows per CTA, R, TU, U, iters, smem bytes}.     */
+int psg_groupnorm_fused_mode(int mode);
+int psg_groupnorm_cluster_plan(int B, int HW, int C, int G, int bwd, int* out8);
+int psg_groupnorm_cluster_tune(int which, int value); /* measurement hook: 0 fwd threads, 1 bwd threads, 2 fwd slab bytes per CTA, 3 max cluster, 4 vectors per unit row, 5 bwd slab bytes */
 int psg_groupnorm_fused_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
                             float* stats, int B, int HW, int C, int G, float eps, int act, void* stream);
 int psg_groupnorm_fused_bwd(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,

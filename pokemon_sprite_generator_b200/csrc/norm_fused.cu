@@ -17,7 +17,10 @@
 // The backward also emits, for free, the per-(sample, channel) sum over pixels of dx (analytically, from the same
 // reductions): that is the gradient of the conv bias / broadcast conditioning that produced x (unet.py:116-124), which
 // saves a separate column-sum pass over dx.
+#include "norm_cluster.h"
 #include "psg_common.cuh"
+
+static int g_gn_mode = 0;   // 0: cluster-split kernels where their plan applies, else the slab kernels; 1: slab kernels only
 
 namespace gnf {
 
@@ -406,8 +409,25 @@ constexpr size_t kSmemLimit = 220 * 1024;
 extern "C" {
 
 // 1 if the single-pass kernels handle this problem (bf16, slab fits in shared memory); else the two-pass kernels run.
+int psg_groupnorm_fused_mode(int mode) {
+  const int prev = g_gn_mode;
+  if (mode == 0 || mode == 1) g_gn_mode = mode;
+  return prev;
+}
+
+// tunables of the cluster-split kernels (measurement hook): which = 0 fwd threads, 1 bwd threads, 2 bytes of one tensor per
+// CTA, 3 largest cluster size; value <= 0 only reads.  Returns the previous value.
+int psg_groupnorm_cluster_tune(int which, int value) { return gnc_tune(which, value); }
+
+// out8 = {CC, cluster size, rows per CTA, R, TU, U, iters, smem bytes} of the cluster-split kernels (norm_cluster.cu)
+int psg_groupnorm_cluster_plan(int B, int HW, int C, int G, int bwd, int* out) {
+  PSG_CHECK_ARG(out && gnc_plan(B, HW, C, G, bwd, out) == 0, "psg_groupnorm_cluster_plan: unsupported shape B=%d HW=%d C=%d G=%d", B, HW, C, G);
+  return PSG_OK;
+}
+
 int psg_groupnorm_fused_ok(int B, int HW, int C, int G, int dtype) {
   if (dtype != PSG_DTYPE_BF16) return 0;
+  if (g_gn_mode == 0 && gnc_supported(B, HW, C, G, 0) && gnc_supported(B, HW, C, G, 1)) return 1;
   gnf::FShape s;
   if (gnf::plan(s, B, HW, C, G) != 0) return 0;
   return gnf::bwd_smem(s) <= gnf::kSmemLimit ? 1 : 0;
@@ -426,12 +446,16 @@ int psg_groupnorm_fused_fwd(const void* x, long long ld_x, void* y, long long ld
                             float* stats, int B, int HW, int C, int G, float eps, int act, void* stream) {
   using namespace gnf;
   PSG_CHECK_ARG(x && y && gamma && beta && stats, "psg_groupnorm_fused_fwd: null pointer");
-  FShape s;
-  PSG_CHECK_ARG(plan(s, B, HW, C, G) == 0 && fwd_smem(s) <= kSmemLimit,
-                "psg_groupnorm_fused_fwd: unsupported shape B=%d HW=%d C=%d G=%d", B, HW, C, G);
   PSG_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
                     ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0),
                 "psg_groupnorm_fused_fwd: pitches/pointers must be 16B aligned");
+  if (g_gn_mode == 0) {
+    const int rc = gnc_fwd(x, ld_x, y, ld_y, gamma, beta, stats, B, HW, C, G, eps, act, (cudaStream_t)stream);
+    if (rc != PSG_ERR_UNSUPPORTED) return rc;
+  }
+  FShape s;
+  PSG_CHECK_ARG(plan(s, B, HW, C, G) == 0 && fwd_smem(s) <= kSmemLimit,
+                "psg_groupnorm_fused_fwd: unsupported shape B=%d HW=%d C=%d G=%d", B, HW, C, G);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gn_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
@@ -455,12 +479,22 @@ int psg_groupnorm_fused_bwd(const void* dy, long long ld_dy, const void* x, long
   using namespace gnf;
   PSG_CHECK_ARG(dy && x && dx && gamma && beta && stats && dgamma && dbeta && workspace, "psg_groupnorm_fused_bwd: null pointer");
   PSG_CHECK_ARG(!(accumulate_dx && (dx_colsum || bias_total)), "psg_groupnorm_fused_bwd: column sums of dx need accumulate_dx == 0");
-  FShape s;
-  PSG_CHECK_ARG(plan(s, B, HW, C, G) == 0 && bwd_smem(s) <= kSmemLimit,
-                "psg_groupnorm_fused_bwd: unsupported shape B=%d HW=%d C=%d G=%d", B, HW, C, G);
   PSG_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) &&
                     ((uintptr_t)dx % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0),
                 "psg_groupnorm_fused_bwd: pitches/pointers must be 16B aligned");
+  if (g_gn_mode == 0) {
+    const int rc = gnc_bwd(dy, ld_dy, x, ld_x, dx, ld_dx, gamma, beta, stats, workspace, dx_colsum, ld_colsum, B, HW, C, G, act,
+                           accumulate_dx, (cudaStream_t)stream);
+    if (rc == PSG_OK) {
+      gn_fused_param_grad_kernel<<<(C + 31) / 32, 512, 0, (cudaStream_t)stream>>>(workspace, B, C, dgamma, dbeta, bias_total, accumulate_params);
+      PSG_CHECK_LAUNCH("psg_groupnorm_fused_bwd");
+      return PSG_OK;
+    }
+    if (rc != PSG_ERR_UNSUPPORTED) return rc;
+  }
+  FShape s;
+  PSG_CHECK_ARG(plan(s, B, HW, C, G) == 0 && bwd_smem(s) <= kSmemLimit,
+                "psg_groupnorm_fused_bwd: unsupported shape B=%d HW=%d C=%d G=%d", B, HW, C, G);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gn_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);

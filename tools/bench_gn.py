@@ -1,4 +1,4 @@
-"""GroupNorm(+SiLU) kernel micro-benchmark: achieved GB/s per U-Net shape, single-pass vs two-pass kernels."""
+"""GroupNorm(+SiLU) kernel micro-benchmark: achieved GB/s per U-Net shape, cluster-split vs slab single-pass kernels (algorithmic bytes: fwd 2N, bwd 3N)."""
 import sys
 from pathlib import Path
 
@@ -27,6 +27,8 @@ def timeit(fn, n=5):
     return sorted(ts)[len(ts) // 2]
 
 
+lib = K.L.load()
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ""          # "cluster": time only the cluster-split kernels (for ncu)
 for hw, c in SHAPES:
     x = torch.randn(B * hw, c, device=dev).bfloat16()
     dy = torch.randn(B * hw, c, device=dev).bfloat16()
@@ -35,10 +37,15 @@ for hw, c in SHAPES:
     stats = torch.empty(B, 32, 2, device=dev)
     dg, db = torch.empty(c, device=dev), torch.empty(c, device=dev)
     nbytes = x.numel() * 2
-    t_f = timeit(lambda: K.groupnorm_fused_fwd(x, y, gamma, beta, stats, B, 32, 1e-5, True))
-    t_b = timeit(lambda: K.groupnorm_fused_bwd(dy, x, dx, gamma, beta, stats, dg, db, B, 32, True, False))
-    t_f2 = timeit(lambda: K.groupnorm_fwd(x, y, gamma, beta, stats, B, 32, 1e-5, True))
-    t_b2 = timeit(lambda: K.groupnorm_bwd(dy, x, dx, gamma, beta, stats, dg, db, B, 32, True, False))
-    print(f"HW={hw:4d} C={c:5d} {nbytes / 1e6:7.1f} MB | fused fwd {t_f * 1e3:7.1f} us {2 * nbytes / t_f / 1e6:7.0f} GB/s | "
-          f"fused bwd {t_b * 1e3:7.1f} us {3 * nbytes / t_b / 1e6:7.0f} GB/s | 2-pass fwd {t_f2 * 1e3:7.1f} us {2 * nbytes / t_f2 / 1e6:7.0f} GB/s | "
-          f"2-pass bwd {t_b2 * 1e3:7.1f} us {3 * nbytes / t_b2 / 1e6:7.0f} GB/s")
+    res = {}
+    for mode, name in ((0, "cluster"), (1, "slab")):
+        if ONLY and name != ONLY:
+            continue
+        lib.psg_groupnorm_fused_mode(mode)
+        t_f = timeit(lambda: K.groupnorm_fused_fwd(x, y, gamma, beta, stats, B, 32, 1e-5, True))
+        t_b = timeit(lambda: K.groupnorm_fused_bwd(dy, x, dx, gamma, beta, stats, dg, db, B, 32, True, False))
+        res[name] = (t_f, t_b)
+    lib.psg_groupnorm_fused_mode(0)
+    print(f"HW={hw:4d} C={c:5d} {nbytes / 1e6:7.1f} MB | " + " | ".join(
+        f"{name} fwd {t_f * 1e3:7.1f} us {2 * nbytes / t_f / 1e6:6.0f} GB/s bwd {t_b * 1e3:7.1f} us {3 * nbytes / t_b / 1e6:6.0f} GB/s"
+        for name, (t_f, t_b) in res.items()), flush=True)

@@ -191,6 +191,9 @@ def main():
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
             os.environ["NCCL_DEBUG"] = "WARN"       # rank 0 must print exactly one line on stdout
+        # the gradient all-reduce runs inside backward (parallel.GradSync): keep its CTA count small and known, so the
+        # persistent GEMM grids can leave exactly that many SMs free while buckets are in flight
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("PSG_COMM_SMS", "8"))
         dist.init_process_group("nccl", device_id=dev)
     L.check(L.load().psg_check_device(), "psg_check_device")
     W = max(args.warmup, 3)
@@ -284,6 +287,15 @@ def main():
     e2e = {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": host_lat[0].numel() * 4 + host_txt[0].numel() * 4,
            "d2h_bytes_per_step": 4, "wall_s": time.perf_counter() - t0}
 
+    comm = None
+    if getattr(step_fn, "grad_sync", None) is not None:
+        gs = step_fn.grad_sync
+        comm = {"overlap": "backward", "buckets": len(gs.bounds), "head_bucket_mb": round((gs.bounds[0][1] - gs.bounds[0][0]) * 4 / 2**20, 1),
+                "bucket_mb": round(gs.bucket_elems * 4 / 2**20), "reserve_sms": gs.reserve_sms, "window_entries": gs.window_entries,
+                "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), **gs.stats}
+    elif world > 1:
+        comm = {"overlap": "none", "buckets": step_fn.buckets, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
+
     # ---- DDPM denoise steps/s per GPU (second half of the BASELINE metric), eval mode, prompt-sharded ----
     denoise = None
     try:
@@ -322,7 +334,7 @@ def main():
                 "data": "synthetic",
                 "config": workload_config(B, Lt, args.heads, not args.no_dropout, world),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "denoise": denoise, "loss": final_loss}
+                "denoise": denoise, "loss": final_loss, "comm": comm}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -87,6 +87,7 @@ size_t psg_umma_workspace_bytes(void);
 int psg_umma_set_workspace(void* workspace, size_t bytes);
 int psg_umma_pairs(int on);                    /* cta_group::2 CTA pairs: 0 never, 1 where measured to pay (default), 2 always */
 int psg_umma_max_pairs(void);                  /* co-resident 2-CTA clusters on this device */
+int psg_umma_reserve_sms(int n);               /* SMs the persistent GEMM grids leave to a concurrent collective (n < 0: read); returns the previous value */
 int psg_umma_debug(int flags);                 /* profiling aid: 1 = skip the epilogue body (mainloop time alone); 0 = normal */
 /* CUDA-core fp32-accumulate engine (fp32 parity mode, edge shapes, general-stride dgrad gather). */
 int psg_simt_gemm(const PsgGemmDesc* desc, void* stream);

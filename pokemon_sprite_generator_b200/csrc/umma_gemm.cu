@@ -998,6 +998,14 @@ int psg_umma_max_pairs() { return umma::max_resident_pairs(); }
 
 // Profiling aid for tools/bench_shapes.py: 1 = drain TMEM but skip the epilogue body (mainloop time alone).
 int psg_umma_debug(int flags) { g_debug = flags; return PSG_OK; }
+// SMs the persistent grids leave free (for a concurrently running collective's CTAs: parallel.GradSync).  Returns the
+// previous value.
+static int g_reserve_sms = 0;
+int psg_umma_reserve_sms(int n) {
+  const int prev = g_reserve_sms;
+  if (n >= 0) g_reserve_sms = n;
+  return prev;
+}
 
 size_t psg_umma_workspace_bytes() { return 1024 + (size_t)kMaxCtas * kSlotBytes; }
 
@@ -1074,13 +1082,14 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   // CTA pairs (cta_group::2).  Measured on this model's shapes (profiles/r01_bench_gemm_modes.txt): a gain of 10-25% for
   // the NT (wgrad) reductions when the 2x taller pair tile does not add much row padding, nothing for TN / TT (equal to a
   // single CTA within noise, slightly worse at short K) -- so only the former use them unless forced (psg_umma_pairs(2)).
-  int cl = 1, units = psg_num_sms();
+  const int free_sms = psg_num_sms() - g_reserve_sms > 8 ? psg_num_sms() - g_reserve_sms : 8;
+  int cl = 1, units = free_sms;
   if (g_pairs_on && block_n % 128 == 0 && d->M > (long long)BLOCK_M * m_tiles) {
     const long long rows1 = (d->M + BLOCK_M * m_tiles - 1) / (BLOCK_M * m_tiles) * (BLOCK_M * m_tiles);
     const long long rows2 = (d->M + 2 * BLOCK_M * m_tiles - 1) / (2 * BLOCK_M * m_tiles) * (2 * BLOCK_M * m_tiles);
     const bool worth = g_pairs_on == 2 || (mode == 1 && rows2 * 4 <= rows1 * 5);
     const int pairs = worth ? max_resident_pairs() : 0;
-    if (pairs >= 8) { cl = 2; units = pairs; }
+    if (pairs >= 8) { cl = 2; units = pairs < free_sms / 2 ? pairs : free_sms / 2; }
   }
   if (units > kMaxCtas / cl) units = kMaxCtas / cl;
 

@@ -115,6 +115,8 @@ class FlatLinW(LinW):
     def views(self, store: "ParamStore"):
         ow, ob = store.offset_of(self.weight), store.offset_of(self.bias)
         n, k = self.n, self.k
+        store.touch(ow, n * k)
+        store.touch(ob, n)
         return (store.flat[ow:ow + n * k].view(n, k), store.flat[ob:ob + n], store.grads[ow:ow + n * k].view(n, k),
                 store.grads[ob:ob + n])
 
@@ -156,6 +158,7 @@ class ParamStore:
         self.grads: Optional[torch.Tensor] = None
         self._by_id = {}
         self.generation = 0
+        self.touch_log: Optional[list] = None
 
     def ensure_flat(self, device) -> bool:
         """(Re)builds the flat buffer if any parameter was moved/replaced.  Returns True when rebuilt."""
@@ -206,7 +209,15 @@ class ParamStore:
         self._index_grads()
 
     def grad_of(self, p: nn.Parameter) -> torch.Tensor:
+        if self.touch_log is not None:
+            self.touch_log.append((self.offsets[self._name_of[id(p)]], p.numel()))
         return self._by_id[id(p)]
+
+    def touch(self, offset: int, numel: int) -> None:
+        """Records that the gradient range [offset, offset + numel) is about to be written (backward only: the bucketed
+        all-reduce in parallel.GradSync learns from this log when each bucket of the flat buffer is final)."""
+        if self.touch_log is not None:
+            self.touch_log.append((offset, numel))
 
     def offset_of(self, p: nn.Parameter) -> int:
         return self.offsets[self._name_of[id(p)]]
@@ -749,15 +760,28 @@ class UNetEngine:
         self.taping = False
         return out, (tape, y)
 
-    def backward(self, ctx, dout: torch.Tensor) -> None:
-        """Runs the tape; parameter gradients are written (not accumulated) into self.store.grads."""
+    def backward(self, ctx, dout: torch.Tensor, grad_sync=None) -> None:
+        """Runs the tape; parameter gradients are written (not accumulated) into self.store.grads.
+        `grad_sync` (parallel.GradSync): data-parallel gradient all-reduce, bucket by bucket as the tape finalises the
+        flat gradient buffer (tail first), overlapped with the rest of the backward pass."""
         tape, y = ctx
         self.taping = False
         lat_c = dout.shape[1]
         y.grad = (torch.zeros if y.C != lat_c else torch.empty)(y.M, y.C, dtype=y.t.dtype, device=y.t.device)
         K.nchw_to_tokens(dout.detach().contiguous().float(), y.grad[:, :lat_c])
-        while tape:
-            tape.pop()()
+        if grad_sync is None:
+            while tape:
+                tape.pop()()
+            return
+        grad_sync.begin(self.store, len(tape))
+        try:
+            done = 0
+            while tape:
+                tape.pop()()
+                done += 1
+                grad_sync.after_entry(done)
+        finally:
+            grad_sync.finish()
 
     # ------------------------------------------------------------------------------------------------------------
     # autograd glue

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 from pathlib import Path
 from typing import Any, Callable, Dict, Optional
 
@@ -27,7 +28,7 @@ import torch.distributed as dist
 from . import _lib as L
 from . import ops as K
 from .losses import SmoothL1Loss, smooth_l1_fwd_bwd
-from .parallel import allreduce_mean_
+from .parallel import GradSync, allreduce_mean_
 from .scheduler import NoiseScheduler
 from .unet import UNet
 
@@ -117,6 +118,15 @@ class TrainStep:
         self.pg = process_group
         self.buckets = 8
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        # overlap="backward": bucketed all-reduce issued from inside backward (parallel.GradSync); "none": after backward
+        self.overlap = os.environ.get("PSG_GRAD_OVERLAP", "backward")
+        self.grad_sync = None
+        if self.world > 1 and self.overlap == "backward":
+            reserve = int(os.environ.get("PSG_COMM_SMS", os.environ.get("NCCL_MAX_CTAS", "8")))
+            lib = L.load()
+            self.grad_sync = GradSync(process_group, bucket_bytes=int(os.environ.get("PSG_BUCKET_MB", "128")) << 20,
+                                      reserve_sms=reserve, reserve_hook=lambda n: lib.psg_umma_reserve_sms(int(n)), prescaled=True,
+                                      window_entries=int(os.environ.get("PSG_COMM_WINDOW", "6")))
 
     def __call__(self, latent: torch.Tensor, text_emb: torch.Tensor, timesteps: Optional[torch.Tensor] = None,
                  noise: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -131,9 +141,12 @@ class TrainStep:
         noisy = self.ns.add_noise(latent, noise, timesteps, clamp=self.clamp)          # clamp(+-3) fused (:363)
         pred, ctx = eng.forward(noisy, timesteps, text_emb, need_grad=True)
         loss, dpred = smooth_l1_fwd_bwd(pred, noise, beta=self.beta, grad_scale=1.0 / self.world)
-        eng.backward(ctx, dpred)
-        if self.world > 1:
-            allreduce_mean_(eng.store.grads, group=self.pg, prescaled=True, buckets=self.buckets)
+        if self.grad_sync is not None:
+            eng.backward(ctx, dpred, grad_sync=self.grad_sync)      # gradient buckets reduced while backward still runs
+        else:
+            eng.backward(ctx, dpred)
+            if self.world > 1:
+                allreduce_mean_(eng.store.grads, group=self.pg, prescaled=True, buckets=self.buckets)
         self.opt.step()
         if self.lr_sched is not None:
             self.lr_sched.step()

@@ -55,3 +55,84 @@ def test_two_rank_gloo_allreduce_and_sharding():
         assert p.exitcode == 0
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(all(r[1:]) for r in results), results
+
+
+class _FakeStore:
+    """The part of engine.ParamStore that GradSync uses: a flat gradient buffer, a touch log, a generation counter."""
+
+    def __init__(self, sizes):
+        self.sizes, self.offsets, off = sizes, [], 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += (n + 63) // 64 * 64
+        self.total = off
+        self.grads = torch.zeros(off)
+        self.touch_log = None
+        self.generation = 1
+
+    def write(self, i, value):
+        if self.touch_log is not None:
+            self.touch_log.append((self.offsets[i], self.sizes[i]))
+        self.grads[self.offsets[i]:self.offsets[i] + self.sizes[i]] = value
+
+
+def _run_backward(sync, store, order, values):
+    """`order`: one list of parameter indices per tape entry (the engine's backward protocol, engine.UNetEngine.backward)."""
+    store.grads.zero_()
+    sync.begin(store, len(order))
+    try:
+        for done, params in enumerate(order, 1):
+            for i in params:
+                store.write(i, values[i])
+            sync.after_entry(done)
+    finally:
+        sync.finish()
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pokemon_sprite_generator_b200.parallel import GradSync
+    sizes = [300, 70, 1000, 64, 513, 2000, 5, 900]
+    store = _FakeStore(sizes)
+    # backward finalises the tail first; parameter 1 is written twice (entries 2 and 6); parameter 0 last
+    order = [[7], [6, 1], [5], [4, 3], [], [2, 1], [0]]
+    reserved = []
+    sync = GradSync(None, bucket_bytes=4 * 1024, reserve_sms=8, reserve_hook=reserved.append, prescaled=False)
+    results = []
+    for step in range(3):
+        values = [float((rank + 1) * (i + 1) + step) for i in range(len(sizes))]
+        _run_backward(sync, store, order, values)
+        expect = torch.zeros(store.total)
+        for i, n in enumerate(sizes):
+            expect[store.offsets[i]:store.offsets[i] + n] = sum((r + 1) * (i + 1) + step for r in range(world)) / world
+        results.append(torch.allclose(store.grads, expect, atol=1e-6))
+    st = dict(sync.stats)
+    ok_plan = st["calibrations"] == 1 and st["overlapped_buckets"] > 0 and store.touch_log is None
+    # steps 2 and 3 issue most buckets from inside backward; the SM reservation is raised then and always released
+    ok_hook = reserved.count(8) >= 2 and reserved[-1] == 0
+    # a tape that writes a bucket after it was reduced must be caught, not silently mis-reduced
+    caught = False
+    try:
+        _run_backward(sync, store, [[7], [6, 1], [5], [4, 3], [], [2], [0, 7]], [1.0] * len(sizes))
+    except RuntimeError:
+        caught = True
+    # a different tape length recalibrates instead of reusing the schedule
+    _run_backward(sync, store, order[:-1] + [[], [0]], [2.0] * len(sizes))
+    ok_recal = sync.stats["calibrations"] == 2 and bool(torch.all(store.grads[:300] == 2.0))
+    q.put((rank, all(results), ok_plan, ok_hook, caught, ok_recal))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradsync_overlapped_buckets():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(all(r[1:]) for r in results), results

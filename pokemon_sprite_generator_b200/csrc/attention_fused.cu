@@ -35,6 +35,7 @@ struct Params {
   unsigned long long seed;
   unsigned int thr;
   float ks;                           // 1 / (1 - p)
+  int bar_off;                        // byte offset of the two mbarriers in dynamic shared memory (end of the kernel's layout)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -49,23 +50,54 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
-// rows [r0, r0 + rows_padded) of a token-major [*, hd] matrix -> smem tile [rows_padded][hp]; rows >= rmax are zero-filled.
-// One warp per row, lanes over the row's 16-byte pieces: no integer division in the copy loop.
+// ---- mbarrier + bulk-copy helpers: one cp.async.bulk per row (the rows of a head are hd*2 contiguous bytes in global
+// memory and land at the padded pitch hp in shared memory).  The per-16-byte cp.async loops this replaces were 27-37 % of
+// all executed instructions of these kernels (profiles/r01_ncu_attention_v2.md).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU; on timeout fall through (the parity tests then fail loudly).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 24); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+// bytes the live rows of a tile will deliver
+__device__ __forceinline__ uint32_t tile_bytes(int r0, int rmax, int rows_padded, int hd) {
+  const int live = max(0, min(rows_padded, rmax - r0));
+  return (uint32_t)live * (uint32_t)hd * 2u;
+}
+// rows [r0, r0 + rows_padded) of a token-major [*, hd] matrix -> smem tile [rows_padded][hp]: one bulk copy per live row
+// (completing on `bar`, whose expect_tx the caller posts with tile_bytes), plain zero stores for rows >= rmax.
 __device__ __forceinline__ void load_rows(__nv_bfloat16* dst, int hp, const __nv_bfloat16* src, long long ld, int r0, int rmax,
-                                          int rows_padded, int hd) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int vpr = hd >> 3;
-  for (int r = warp; r < rows_padded; r += nwarps) {
-    const bool ok = r0 + r < rmax;
-    const __nv_bfloat16* srow = ok ? src + (long long)(r0 + r) * ld : src;
+                                          int rows_padded, int hd, uint32_t bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy accesses of the tile vs the async writes
+  for (int r = threadIdx.x; r < rows_padded; r += blockDim.x) {
     __nv_bfloat16* drow = dst + r * hp;
-    for (int v = lane; v < vpr; v += 32) cp_async16(drow + v * 8, ok ? srow + v * 8 : src, ok ? 16 : 0);
+    if (r0 + r < rmax) {
+      bulk_g2s(smem_u32(drow), src + (long long)(r0 + r) * ld, (uint32_t)hd * 2u, bar);
+    } else {
+      for (int v = 0; v < hd; v += 8) *reinterpret_cast<uint4*>(drow + v) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 }
 
@@ -122,7 +154,18 @@ __device__ __forceinline__ void keep_pair(const Params& p, uint64_t row_base, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// forward: grid (ceil(Lq / 64), B * H)
+// All three kernels: grid (nsplit, B * H); a CTA keeps the head's resident tiles (K, V or Q, dO) in shared memory and walks
+// the 64-row blocks blockIdx.x, blockIdx.x + nsplit, ... of that head, so the resident tiles are fetched once per head
+// (nsplit == 1 whenever B * H alone fills the GPU) and the next block's tiles are fetched while the current block's last
+// phase still runs.  bars[0]: resident tiles, bars[1]: per-block tiles (parity flips once per block).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_item(int item, int mtl, int& nc, int& mt) {     // item = nc * mtl + mt, mtl in 1..4
+  nc = mtl == 4 ? item >> 2 : mtl == 1 ? item : mtl == 2 ? item >> 1 : item / 3;
+  mt = item - nc * mtl;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// forward
 //   smem: K [Lk16][hp] | V [Lk16][hp] | Q [64][hp] | S fp32 [64][sp]   (the bf16 Pd rows overwrite their own S rows)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kQB = 64;
@@ -130,108 +173,134 @@ constexpr int kQB = 64;
 __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
-  const int q0 = blockIdx.x * kQB;
   const int hp = p.hp, sp = p.Lk16 + 4;
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* Vs = Ks + (size_t)p.Lk16 * hp;
   __nv_bfloat16* Qs = Vs + (size_t)p.Lk16 * hp;
   float* Sf = reinterpret_cast<float*>(Qs + (size_t)kQB * hp);
+  const uint32_t bar0 = smem_u32(smem + p.bar_off), bar1 = bar0 + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kWarps = blockDim.x >> 5;
-  const int mtl = min(kQB / 16, (p.Lq - q0 + 15) >> 4);      // live 16-row tiles of this block
+  const int nqb = (p.Lq + kQB - 1) / kQB;
+  const __nv_bfloat16* qsrc = p.q + (long long)b * p.Lq * p.ldq + h * p.hd;
 
-  load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, 0, p.Lk, p.Lk16, p.hd);
-  load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, 0, p.Lk, p.Lk16, p.hd);
-  load_rows(Qs, hp, p.q + (long long)b * p.Lq * p.ldq + h * p.hd, p.ldq, q0, p.Lq, kQB, p.hd);
-  cp_async_wait_all();
-  __syncthreads();
-
-  // S = scale * Q K^T
-  const int nchunks = (p.Lk16 + 31) / 32;
-  for (int item = warp; item < mtl * nchunks; item += kWarps) {
-    const int nc = item / mtl, mt = item - nc * mtl;
-    float acc[4][4];
-    // the last chunk may run 16 columns past Lk16: those B rows belong to the V tile (finite data), results are dropped
-    warp_mma_16x32<false>(acc, Qs, hp, mt * 16, Ks, hp, nc * 32, p.hd, lane);
-#pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = mt * 16 + (lane >> 2) + 8 * (e >> 1), n = nc * 32 + jn * 8 + (lane & 3) * 2 + (e & 1);
-        if (n < p.Lk16) Sf[m * sp + n] = acc[jn][e] * p.scale;
-      }
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar0, 2u * tile_bytes(0, p.Lk, p.Lk16, p.hd));
+    mbar_expect_tx(bar1, tile_bytes(blockIdx.x * kQB, p.Lq, kQB, p.hd));
   }
-  __syncthreads();
+  __syncthreads();           // barriers initialised and their byte counts posted before any copy is issued
+  load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, 0, p.Lk, p.Lk16, p.hd, bar0);
+  load_rows(Qs, hp, qsrc, p.ldq, blockIdx.x * kQB, p.Lq, kQB, p.hd, bar1);
+  load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, 0, p.Lk, p.Lk16, p.hd, bar0);
+  mbar_wait(bar0, 0);
 
-  // row softmax (one warp per row; lane l owns the column pairs 2l + 64 i), LSE out, dropout (one hash per pair), bf16 Pd
-  // written over the row's own fp32 storage
-  for (int r = warp; r < mtl * 16; r += kWarps) {
-    float2 v[kMaxLk / 64];
-    float mx = -INFINITY;
-    float* srow = Sf + r * sp;
+  uint32_t phase = 0;
+  for (int qb = blockIdx.x; qb < nqb; qb += gridDim.x) {
+    const int q0 = qb * kQB;
+    const int mtl = min(kQB / 16, (p.Lq - q0 + 15) >> 4);      // live 16-row tiles of this block
+    mbar_wait(bar1, phase);
+    phase ^= 1;
+    // the next block's byte count is posted a barrier ahead of its copies (issued after the S phase)
+    if (threadIdx.x == 0 && qb + (int)gridDim.x < nqb) mbar_expect_tx(bar1, tile_bytes((qb + gridDim.x) * kQB, p.Lq, kQB, p.hd));
+    __syncthreads();           // zero-filled rows are visible; the previous block's Pd reads are over
+
+    // S = scale * Q K^T
+    const int nchunks = (p.Lk16 + 31) / 32;
+    for (int item = warp; item < mtl * nchunks; item += kWarps) {
+      int nc, mt;
+      split_item(item, mtl, nc, mt);
+      float acc[4][4];
+      // the last chunk may run 16 columns past Lk16: those B rows belong to the V tile (finite data), results are dropped
+      warp_mma_16x32<false>(acc, Qs, hp, mt * 16, Ks, hp, nc * 32, p.hd, lane);
 #pragma unroll
-    for (int i = 0; i < kMaxLk / 64; ++i) {
-      const int jx = 2 * lane + 64 * i;
-      v[i] = (jx < p.Lk16) ? *reinterpret_cast<const float2*>(srow + jx) : make_float2(-INFINITY, -INFINITY);
-      if (jx >= p.Lk) v[i].x = -INFINITY;
-      if (jx + 1 >= p.Lk) v[i].y = -INFINITY;
-      mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
-    }
+      for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxLk / 64; ++i) {
-      v[i].x = __expf(v[i].x - mx);       // exp(-inf) = 0 on the padding
-      v[i].y = __expf(v[i].y - mx);
-      sum += v[i].x + v[i].y;
-    }
-    sum = psg_warp_sum(sum);
-    const float inv = 1.f / sum;
-    const bool valid = q0 + r < p.Lq;
-    const long long row_global = ((long long)bh) * p.Lq + q0 + r;
-    if (valid && lane == 0 && p.lse) p.lse[row_global] = mx + __logf(sum);
-    __syncwarp();
-    __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(srow);
-    const uint64_t row_base = (uint64_t)row_global * (uint64_t)p.Lk;
-    const float live = valid ? inv : 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxLk / 64; ++i) {
-      const int jx = 2 * lane + 64 * i;
-      if (jx < p.Lk16) {
-        float p0 = v[i].x * live, p1 = v[i].y * live;
-        if (p.thr) {
-          bool k0, k1;
-          keep_pair(p, row_base, jx, k0, k1);
-          p0 = k0 ? p0 * p.ks : 0.f;
-          p1 = k1 ? p1 * p.ks : 0.f;
+        for (int half = 0; half < 2; ++half) {
+          const int m = mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
+          if (n < p.Lk16) *reinterpret_cast<float2*>(Sf + m * sp + n) = make_float2(acc[jn][2 * half] * p.scale, acc[jn][2 * half + 1] * p.scale);
         }
-        *reinterpret_cast<__nv_bfloat162*>(prow + jx) = __floats2bfloat162_rn(p0, p1);
+    }
+    __syncthreads();
+    if (qb + (int)gridDim.x < nqb) {      // the Q tile is free: fetch the next block's while this one finishes
+      const int qn = (qb + gridDim.x) * kQB;
+      load_rows(Qs, hp, qsrc, p.ldq, qn, p.Lq, kQB, p.hd, bar1);
+    }
+
+    // row softmax (one warp per row; lane l owns the column pairs 2l + 64 i), LSE out, dropout (one hash per pair), bf16 Pd
+    // written over the row's own fp32 storage
+    for (int r = warp; r < mtl * 16; r += kWarps) {
+      float2 v[kMaxLk / 64];
+      float mx = -INFINITY;
+      float* srow = Sf + r * sp;
+#pragma unroll
+      for (int i = 0; i < kMaxLk / 64; ++i) {
+        const int jx = 2 * lane + 64 * i;
+        v[i] = (jx < p.Lk16) ? *reinterpret_cast<const float2*>(srow + jx) : make_float2(-INFINITY, -INFINITY);
+        if (jx >= p.Lk) v[i].x = -INFINITY;
+        if (jx + 1 >= p.Lk) v[i].y = -INFINITY;
+        mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+      const float mxl = mx * 1.4426950408889634f;
+#pragma unroll
+      for (int i = 0; i < kMaxLk / 64; ++i) {
+        v[i].x = psg_ex2_approx(fmaf(v[i].x, 1.4426950408889634f, -mxl));       // exp(-inf) = 0 on the padding
+        v[i].y = psg_ex2_approx(fmaf(v[i].y, 1.4426950408889634f, -mxl));
+        sum += v[i].x + v[i].y;
+      }
+      sum = psg_warp_sum(sum);
+      const float inv = 1.f / sum;
+      const bool valid = q0 + r < p.Lq;
+      const long long row_global = ((long long)bh) * p.Lq + q0 + r;
+      if (valid && lane == 0 && p.lse) p.lse[row_global] = mx + __logf(sum);
+      __syncwarp();
+      __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(srow);
+      const uint64_t row_base = (uint64_t)row_global * (uint64_t)p.Lk;
+      const float live = valid ? inv : 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxLk / 64; ++i) {
+        const int jx = 2 * lane + 64 * i;
+        if (jx < p.Lk16) {
+          float p0 = v[i].x * live, p1 = v[i].y * live;
+          if (p.thr) {
+            bool k0, k1;
+            keep_pair(p, row_base, jx, k0, k1);
+            p0 = k0 ? p0 * p.ks : 0.f;
+            p1 = k1 ? p1 * p.ks : 0.f;
+          }
+          *reinterpret_cast<__nv_bfloat162*>(prow + jx) = __floats2bfloat162_rn(p0, p1);
+        }
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // O = Pd V
-  const __nv_bfloat16* Pd = reinterpret_cast<const __nv_bfloat16*>(Sf);
-  const int ldp = 2 * sp;
-  __nv_bfloat16* obase = p.out + (long long)b * p.Lq * p.ldo + h * p.hd;
-  const int ochunks = (p.hd + 31) / 32;      // head_dim % 32 == 16: the last chunk's upper half is dropped
-  for (int item = warp; item < mtl * ochunks; item += kWarps) {
-    const int nc = item / mtl, mt = item - nc * mtl;
-    float acc[4][4];
-    warp_mma_16x32<true>(acc, Pd, ldp, mt * 16, Vs, hp, nc * 32, p.Lk16, lane);
+    // O = Pd V
+    const __nv_bfloat16* Pd = reinterpret_cast<const __nv_bfloat16*>(Sf);
+    const int ldp = 2 * sp;
+    __nv_bfloat16* obase = p.out + (long long)b * p.Lq * p.ldo + h * p.hd;
+    const int ochunks = (p.hd + 31) / 32;      // head_dim % 32 == 16: the last chunk's upper half is dropped
+    for (int item = warp; item < mtl * ochunks; item += kWarps) {
+      int nc, mt;
+      split_item(item, mtl, nc, mt);
+      float acc[4][4];
+      warp_mma_16x32<true>(acc, Pd, ldp, mt * 16, Vs, hp, nc * 32, p.Lk16, lane);
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
+      for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int m = q0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
-        if (m < p.Lq && n < p.hd) *reinterpret_cast<__nv_bfloat162*>(obase + (long long)m * p.ldo + n) = __floats2bfloat162_rn(acc[jn][2 * half], acc[jn][2 * half + 1]);
-      }
+        for (int half = 0; half < 2; ++half) {
+          const int m = q0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
+          if (m < p.Lq && n < p.hd) *reinterpret_cast<__nv_bfloat162*>(obase + (long long)m * p.ldo + n) = __floats2bfloat162_rn(acc[jn][2 * half], acc[jn][2 * half + 1]);
+        }
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward, dQ: grid (ceil(Lq / 64), B * H)
+// backward, dQ
 //   smem: K [Lk16][hp] | V [Lk16][hp] | Q [64][hp] | dO [64][hp] | dS bf16 [64][dp] | lse[64] | delta[64]
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kBB = 64;
@@ -239,7 +308,6 @@ constexpr int kBB = 64;
 __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
-  const int q0 = blockIdx.x * kBB;
   const int hp = p.hp, dp = p.Lk16 + 8;
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* Vs = Ks + (size_t)p.Lk16 * hp;
@@ -248,96 +316,124 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Params p) {
   __nv_bfloat16* dSs = dOs + (size_t)kBB * hp;
   float* lse_s = reinterpret_cast<float*>(dSs + (size_t)kBB * dp);
   float* del_s = lse_s + kBB;
+  const uint32_t bar0 = smem_u32(smem + p.bar_off), bar1 = bar0 + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kWarps = blockDim.x >> 5;
-  const int mtl = min(kBB / 16, (p.Lq - q0 + 15) >> 4);      // live 16-row tiles of this block
+  const int nqb = (p.Lq + kBB - 1) / kBB;
+  const __nv_bfloat16* qsrc = p.q + (long long)b * p.Lq * p.ldq + h * p.hd;
+  const __nv_bfloat16* dosrc = p.dout + (long long)b * p.Lq * p.lddo + h * p.hd;
+  const float scale_l2 = p.scale * 1.4426950408889634f;
 
-  load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, 0, p.Lk, p.Lk16, p.hd);
-  load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, 0, p.Lk, p.Lk16, p.hd);
-  load_rows(Qs, hp, p.q + (long long)b * p.Lq * p.ldq + h * p.hd, p.ldq, q0, p.Lq, kBB, p.hd);
-  load_rows(dOs, hp, p.dout + (long long)b * p.Lq * p.lddo + h * p.hd, p.lddo, q0, p.Lq, kBB, p.hd);
-  // delta[i] = dO_i . O_i (O straight from global), one warp per row; also stage lse
-  for (int r = warp; r < kBB; r += kWarps) {
-    const int qi = q0 + r;
-    float s = 0.f;
-    if (qi < p.Lq) {
-      const __nv_bfloat16* orow = p.o + ((long long)b * p.Lq + qi) * p.ldo + h * p.hd;
-      const __nv_bfloat16* drow = p.dout + ((long long)b * p.Lq + qi) * p.lddo + h * p.hd;
-      for (int c = lane * 8; c < p.hd; c += 256) {
-        Vec8<__nv_bfloat16> a, d;
-        a.load(orow + c);
-        d.load(drow + c);
-#pragma unroll
-        for (int x = 0; x < 8; ++x) s = fmaf(a.v[x], d.v[x], s);
-      }
-    }
-    s = psg_warp_sum(s);
-    if (lane == 0) {
-      const long long rg = (long long)bh * p.Lq + qi;
-      del_s[r] = s;
-      lse_s[r] = (qi < p.Lq) ? p.lse[rg] : 0.f;
-      if (qi < p.Lq) p.delta[rg] = s;
-    }
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar0, 2u * tile_bytes(0, p.Lk, p.Lk16, p.hd));
+    mbar_expect_tx(bar1, 2u * tile_bytes(blockIdx.x * kBB, p.Lq, kBB, p.hd));
   }
-  cp_async_wait_all();
-  __syncthreads();
+  __syncthreads();           // barriers initialised and their byte counts posted before any copy is issued
+  load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, 0, p.Lk, p.Lk16, p.hd, bar0);
+  load_rows(Qs, hp, qsrc, p.ldq, blockIdx.x * kBB, p.Lq, kBB, p.hd, bar1);
+  load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, 0, p.Lk, p.Lk16, p.hd, bar0);
+  load_rows(dOs, hp, dosrc, p.lddo, blockIdx.x * kBB, p.Lq, kBB, p.hd, bar1);
 
-  // per 16 x 32 tile: S = Q K^T and dPd = dO V^T in registers -> dS = P o (drop(dPd) - delta) -> shared memory
-  const int nchunks = (p.Lk16 + 31) / 32;
-  for (int item = warp; item < mtl * nchunks; item += kWarps) {
-    const int nc = item / mtl, mt = item - nc * mtl;
-    float sa[4][4], da[4][4];
-    warp_mma_16x32<false>(sa, Qs, hp, mt * 16, Ks, hp, nc * 32, p.hd, lane);
-    warp_mma_16x32<false>(da, dOs, hp, mt * 16, Vs, hp, nc * 32, p.hd, lane);
+  uint32_t phase = 0;
+  for (int qb = blockIdx.x; qb < nqb; qb += gridDim.x) {
+    const int q0 = qb * kBB;
+    const int mtl = min(kBB / 16, (p.Lq - q0 + 15) >> 4);      // live 16-row tiles of this block
+    // delta[i] = dO_i . O_i (both straight from global, while the tiles are in flight), one warp per row; also stage lse
+    for (int r = warp; r < kBB; r += kWarps) {
+      const int qi = q0 + r;
+      float s = 0.f;
+      if (qi < p.Lq) {
+        const __nv_bfloat16* orow = p.o + ((long long)b * p.Lq + qi) * p.ldo + h * p.hd;
+        const __nv_bfloat16* drow = dosrc + (long long)qi * p.lddo;
+        for (int c = lane * 8; c < p.hd; c += 256) {
+          Vec8<__nv_bfloat16> a, d;
+          a.load(orow + c);
+          d.load(drow + c);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int m = mt * 16 + (lane >> 2) + 8 * half;
-      const bool row_ok = q0 + m < p.Lq;
-      const float lse_m = lse_s[m], del_m = del_s[m];
-      const uint64_t row_base = (uint64_t)((long long)bh * p.Lq + q0 + m) * (uint64_t)p.Lk;
-      __nv_bfloat16* drow = dSs + m * dp;
-#pragma unroll
-      for (int jn = 0; jn < 4; ++jn) {
-        const int n = nc * 32 + jn * 8 + (lane & 3) * 2;          // columns n, n + 1
-        if (n >= p.Lk16) continue;
-        float d0 = 0.f, d1 = 0.f;
-        if (row_ok) {
-          bool k0 = true, k1 = true;
-          if (p.thr) keep_pair(p, row_base, n, k0, k1);
-          if (n < p.Lk) d0 = __expf(sa[jn][2 * half] * p.scale - lse_m) * ((k0 ? da[jn][2 * half] * p.ks : 0.f) - del_m);
-          if (n + 1 < p.Lk) d1 = __expf(sa[jn][2 * half + 1] * p.scale - lse_m) * ((k1 ? da[jn][2 * half + 1] * p.ks : 0.f) - del_m);
+          for (int x = 0; x < 8; ++x) s = fmaf(a.v[x], d.v[x], s);
         }
-        *reinterpret_cast<__nv_bfloat162*>(drow + n) = __floats2bfloat162_rn(d0, d1);
+      }
+      s = psg_warp_sum(s);
+      if (lane == 0) {
+        const long long rg = (long long)bh * p.Lq + qi;
+        del_s[r] = s;
+        lse_s[r] = (qi < p.Lq) ? p.lse[rg] * 1.4426950408889634f : 0.f;
+        if (qi < p.Lq) p.delta[rg] = s;
       }
     }
-  }
-  __syncthreads();
-  // dQ = scale * dS K
-  __nv_bfloat16* qbase = p.dq + (long long)b * p.Lq * p.lddq + h * p.hd;
-  const int ochunks = (p.hd + 31) / 32;      // head_dim % 32 == 16: the last chunk's upper half is dropped
-  for (int item = warp; item < mtl * ochunks; item += kWarps) {
-    const int nc = item / mtl, mt = item - nc * mtl;
-    float acc[4][4];
-    warp_mma_16x32<true>(acc, dSs, dp, mt * 16, Ks, hp, nc * 32, p.Lk16, lane);
-#pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
+    if (qb == (int)blockIdx.x) mbar_wait(bar0, 0);
+    mbar_wait(bar1, phase);
+    phase ^= 1;
+    if (threadIdx.x == 0 && qb + (int)gridDim.x < nqb) mbar_expect_tx(bar1, 2u * tile_bytes((qb + gridDim.x) * kBB, p.Lq, kBB, p.hd));
+    __syncthreads();
+
+    // per 16 x 32 tile: S = Q K^T and dPd = dO V^T in registers -> dS = P o (drop(dPd) - delta) -> shared memory
+    const int nchunks = (p.Lk16 + 31) / 32;
+    for (int item = warp; item < mtl * nchunks; item += kWarps) {
+      int nc, mt;
+      split_item(item, mtl, nc, mt);
+      float sa[4][4], da[4][4];
+      warp_mma_16x32<false>(sa, Qs, hp, mt * 16, Ks, hp, nc * 32, p.hd, lane);
+      warp_mma_16x32<false>(da, dOs, hp, mt * 16, Vs, hp, nc * 32, p.hd, lane);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int m = q0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
-        if (m < p.Lq && n < p.hd)
-          *reinterpret_cast<__nv_bfloat162*>(qbase + (long long)m * p.lddq + n) =
-              __floats2bfloat162_rn(acc[jn][2 * half] * p.scale, acc[jn][2 * half + 1] * p.scale);
+        const int m = mt * 16 + (lane >> 2) + 8 * half;
+        const bool row_ok = q0 + m < p.Lq;
+        const float lse_m = lse_s[m], del_m = del_s[m];
+        const uint64_t row_base = (uint64_t)((long long)bh * p.Lq + q0 + m) * (uint64_t)p.Lk;
+        __nv_bfloat16* drow = dSs + m * dp;
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+          const int n = nc * 32 + jn * 8 + (lane & 3) * 2;          // columns n, n + 1
+          if (n >= p.Lk16) continue;
+          float d0 = 0.f, d1 = 0.f;
+          if (row_ok) {
+            bool k0 = true, k1 = true;
+            if (p.thr) keep_pair(p, row_base, n, k0, k1);
+            if (n < p.Lk) d0 = psg_ex2_approx(fmaf(sa[jn][2 * half], scale_l2, -lse_m)) * ((k0 ? da[jn][2 * half] * p.ks : 0.f) - del_m);
+            if (n + 1 < p.Lk) d1 = psg_ex2_approx(fmaf(sa[jn][2 * half + 1], scale_l2, -lse_m)) * ((k1 ? da[jn][2 * half + 1] * p.ks : 0.f) - del_m);
+          }
+          *reinterpret_cast<__nv_bfloat162*>(drow + n) = __floats2bfloat162_rn(d0, d1);
+        }
       }
+    }
+    __syncthreads();
+    if (qb + (int)gridDim.x < nqb) {      // Q / dO tiles are free: fetch the next block's under the dQ product
+      const int qn = (qb + gridDim.x) * kBB;
+      load_rows(Qs, hp, qsrc, p.ldq, qn, p.Lq, kBB, p.hd, bar1);
+      load_rows(dOs, hp, dosrc, p.lddo, qn, p.Lq, kBB, p.hd, bar1);
+    }
+    // dQ = scale * dS K
+    __nv_bfloat16* qbase = p.dq + (long long)b * p.Lq * p.lddq + h * p.hd;
+    const int ochunks = (p.hd + 31) / 32;      // head_dim % 32 == 16: the last chunk's upper half is dropped
+    for (int item = warp; item < mtl * ochunks; item += kWarps) {
+      int nc, mt;
+      split_item(item, mtl, nc, mt);
+      float acc[4][4];
+      warp_mma_16x32<true>(acc, dSs, dp, mt * 16, Ks, hp, nc * 32, p.Lk16, lane);
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int m = q0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
+          if (m < p.Lq && n < p.hd)
+            *reinterpret_cast<__nv_bfloat162*>(qbase + (long long)m * p.lddq + n) =
+                __floats2bfloat162_rn(acc[jn][2 * half] * p.scale, acc[jn][2 * half + 1] * p.scale);
+        }
+    }
+    __syncthreads();           // lse_s / del_s / dSs are rewritten by the next block
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward, dK / dV: grid (ceil(Lk / 64), B * H)
+// backward, dK / dV
 //   smem: Q [Lq16][hp] | dO [Lq16][hp] | K [64][hp] | V [64][hp] | T bf16 [64][dp] (Pd^T, then dS^T) | lse[Lq16] | delta[Lq16]
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
-  const int k0 = blockIdx.x * kBB;
   const int hp = p.hp, dp = p.Lq16 + 8;
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* dOs = Qs + (size_t)p.Lq16 * hp;
@@ -346,97 +442,141 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Params p) 
   __nv_bfloat16* Ts = Vs + (size_t)kBB * hp;
   float* lse_s = reinterpret_cast<float*>(Ts + (size_t)kBB * dp);
   float* del_s = lse_s + p.Lq16;
+  const uint32_t bar0 = smem_u32(smem + p.bar_off), bar1 = bar0 + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kWarps = blockDim.x >> 5;
-  const int mtl = min(kBB / 16, (p.Lk - k0 + 15) >> 4);      // live 16-key tiles of this block
+  const int nkb = (p.Lk + kBB - 1) / kBB;
+  const __nv_bfloat16* ksrc = p.k + (long long)b * p.Lk * p.ldk + h * p.hd;
+  const __nv_bfloat16* vsrc = p.v + (long long)b * p.Lk * p.ldv + h * p.hd;
+  const float scale_l2 = p.scale * 1.4426950408889634f;
 
-  load_rows(Qs, hp, p.q + (long long)b * p.Lq * p.ldq + h * p.hd, p.ldq, 0, p.Lq, p.Lq16, p.hd);
-  load_rows(dOs, hp, p.dout + (long long)b * p.Lq * p.lddo + h * p.hd, p.lddo, 0, p.Lq, p.Lq16, p.hd);
-  load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, k0, p.Lk, kBB, p.hd);
-  load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, k0, p.Lk, kBB, p.hd);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar0, 2u * tile_bytes(0, p.Lq, p.Lq16, p.hd));
+    mbar_expect_tx(bar1, 2u * tile_bytes(blockIdx.x * kBB, p.Lk, kBB, p.hd));
+  }
+  __syncthreads();           // barriers initialised and their byte counts posted before any copy is issued
+  load_rows(Ks, hp, ksrc, p.ldk, blockIdx.x * kBB, p.Lk, kBB, p.hd, bar1);
+  load_rows(Qs, hp, p.q + (long long)b * p.Lq * p.ldq + h * p.hd, p.ldq, 0, p.Lq, p.Lq16, p.hd, bar0);
+  load_rows(Vs, hp, vsrc, p.ldv, blockIdx.x * kBB, p.Lk, kBB, p.hd, bar1);
+  load_rows(dOs, hp, p.dout + (long long)b * p.Lq * p.lddo + h * p.hd, p.lddo, 0, p.Lq, p.Lq16, p.hd, bar0);
   for (int i = threadIdx.x; i < p.Lq16; i += blockDim.x) {
     const bool ok = i < p.Lq;
-    lse_s[i] = ok ? p.lse[(long long)bh * p.Lq + i] : 0.f;
+    lse_s[i] = ok ? p.lse[(long long)bh * p.Lq + i] * 1.4426950408889634f : 0.f;
     del_s[i] = ok ? p.delta[(long long)bh * p.Lq + i] : 0.f;
   }
-  cp_async_wait_all();
-  __syncthreads();
+  mbar_wait(bar0, 0);
 
   const int nchunks = (p.Lq16 + 31) / 32;
   const int ochunks = (p.hd + 31) / 32;
-  // pass A: Pd^T = drop(exp(scale K Q^T - lse)) -> T (rows = keys of this block, columns = queries)
-  for (int item = warp; item < mtl * nchunks; item += kWarps) {
-    const int nc = item / mtl, mt = item - nc * mtl;
-    float sa[4][4];
-    warp_mma_16x32<false>(sa, Ks, hp, mt * 16, Qs, hp, nc * 32, p.hd, lane);
+  uint32_t phase = 0;
+  for (int kb = blockIdx.x; kb < nkb; kb += gridDim.x) {
+    const int k0 = kb * kBB;
+    const int mtl = min(kBB / 16, (p.Lk - k0 + 15) >> 4);      // live 16-key tiles of this block
+    mbar_wait(bar1, phase);
+    phase ^= 1;
+    if (threadIdx.x == 0 && kb + (int)gridDim.x < nkb) mbar_expect_tx(bar1, 2u * tile_bytes((kb + gridDim.x) * kBB, p.Lk, kBB, p.hd));
+    __syncthreads();
+    // pass A: Pd^T = drop(exp(scale K Q^T - lse)) -> T (rows = keys of this block, columns = queries)
+    for (int item = warp; item < mtl * nchunks; item += kWarps) {
+      int nc, mt;
+      split_item(item, mtl, nc, mt);
+      float sa[4][4];
+      warp_mma_16x32<false>(sa, Ks, hp, mt * 16, Qs, hp, nc * 32, p.hd, lane);
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
+      for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = mt * 16 + (lane >> 2) + 8 * (e >> 1), n = nc * 32 + jn * 8 + (lane & 3) * 2 + (e & 1);
-        if (n >= p.Lq16) continue;
-        float pd = 0.f;
-        if (n < p.Lq && k0 + m < p.Lk) {
-          pd = __expf(sa[jn][e] * p.scale - lse_s[n]);
-          if (p.thr) pd = keep_ij(p, (long long)bh * p.Lq + n, k0 + m) ? pd * p.ks : 0.f;
+        for (int half = 0; half < 2; ++half) {
+          const int m = mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;    // queries n, n + 1
+          if (n >= p.Lq16) continue;
+          float pd0 = 0.f, pd1 = 0.f;
+          if (k0 + m < p.Lk) {
+            if (n < p.Lq) {
+              pd0 = psg_ex2_approx(fmaf(sa[jn][2 * half], scale_l2, -lse_s[n]));
+              if (p.thr) pd0 = keep_ij(p, (long long)bh * p.Lq + n, k0 + m) ? pd0 * p.ks : 0.f;
+            }
+            if (n + 1 < p.Lq) {
+              pd1 = psg_ex2_approx(fmaf(sa[jn][2 * half + 1], scale_l2, -lse_s[n + 1]));
+              if (p.thr) pd1 = keep_ij(p, (long long)bh * p.Lq + n + 1, k0 + m) ? pd1 * p.ks : 0.f;
+            }
+          }
+          *reinterpret_cast<__nv_bfloat162*>(Ts + m * dp + n) = __floats2bfloat162_rn(pd0, pd1);
         }
-        Ts[m * dp + n] = __float2bfloat16_rn(pd);
-      }
-  }
-  __syncthreads();
-  // dV = Pd^T dO
-  __nv_bfloat16* vbase = p.dv + (long long)b * p.Lk * p.lddv + h * p.hd;
-  for (int item = warp; item < mtl * ochunks; item += kWarps) {
-    const int nc = item / mtl, mt = item - nc * mtl;
-    float acc[4][4];
-    warp_mma_16x32<true>(acc, Ts, dp, mt * 16, dOs, hp, nc * 32, p.Lq16, lane);
+    }
+    __syncthreads();
+    // dV = Pd^T dO
+    __nv_bfloat16* vbase = p.dv + (long long)b * p.Lk * p.lddv + h * p.hd;
+    for (int item = warp; item < mtl * ochunks; item += kWarps) {
+      int nc, mt;
+      split_item(item, mtl, nc, mt);
+      float acc[4][4];
+      warp_mma_16x32<true>(acc, Ts, dp, mt * 16, dOs, hp, nc * 32, p.Lq16, lane);
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
+      for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int m = k0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
-        if (m < p.Lk && n < p.hd)
-          *reinterpret_cast<__nv_bfloat162*>(vbase + (long long)m * p.lddv + n) = __floats2bfloat162_rn(acc[jn][2 * half], acc[jn][2 * half + 1]);
-      }
-  }
-  __syncthreads();
-  // pass B: dS^T = P^T o (drop(V dO^T) - delta) -> T
-  for (int item = warp; item < mtl * nchunks; item += kWarps) {
-    const int nc = item / mtl, mt = item - nc * mtl;
-    float sa[4][4], da[4][4];
-    warp_mma_16x32<false>(sa, Ks, hp, mt * 16, Qs, hp, nc * 32, p.hd, lane);
-    warp_mma_16x32<false>(da, Vs, hp, mt * 16, dOs, hp, nc * 32, p.hd, lane);
-#pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = mt * 16 + (lane >> 2) + 8 * (e >> 1), n = nc * 32 + jn * 8 + (lane & 3) * 2 + (e & 1);
-        if (n >= p.Lq16) continue;
-        float ds = 0.f;
-        if (n < p.Lq && k0 + m < p.Lk) {
-          const float pr = __expf(sa[jn][e] * p.scale - lse_s[n]);
-          float dpv = da[jn][e];
-          if (p.thr) dpv = keep_ij(p, (long long)bh * p.Lq + n, k0 + m) ? dpv * p.ks : 0.f;
-          ds = pr * (dpv - del_s[n]);
+        for (int half = 0; half < 2; ++half) {
+          const int m = k0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
+          if (m < p.Lk && n < p.hd)
+            *reinterpret_cast<__nv_bfloat162*>(vbase + (long long)m * p.lddv + n) = __floats2bfloat162_rn(acc[jn][2 * half], acc[jn][2 * half + 1]);
         }
-        Ts[m * dp + n] = __float2bfloat16_rn(ds);
-      }
-  }
-  __syncthreads();
-  // dK = scale * dS^T Q
-  __nv_bfloat16* kbase = p.dk + (long long)b * p.Lk * p.lddk + h * p.hd;
-  for (int item = warp; item < mtl * ochunks; item += kWarps) {
-    const int nc = item / mtl, mt = item - nc * mtl;
-    float acc[4][4];
-    warp_mma_16x32<true>(acc, Ts, dp, mt * 16, Qs, hp, nc * 32, p.Lq16, lane);
+    }
+    __syncthreads();
+    // pass B: dS^T = P^T o (drop(V dO^T) - delta) -> T
+    for (int item = warp; item < mtl * nchunks; item += kWarps) {
+      int nc, mt;
+      split_item(item, mtl, nc, mt);
+      float sa[4][4], da[4][4];
+      warp_mma_16x32<false>(sa, Ks, hp, mt * 16, Qs, hp, nc * 32, p.hd, lane);
+      warp_mma_16x32<false>(da, Vs, hp, mt * 16, dOs, hp, nc * 32, p.hd, lane);
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
+      for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int m = k0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
-        if (m < p.Lk && n < p.hd)
-          *reinterpret_cast<__nv_bfloat162*>(kbase + (long long)m * p.lddk + n) =
-              __floats2bfloat162_rn(acc[jn][2 * half] * p.scale, acc[jn][2 * half + 1] * p.scale);
-      }
+        for (int half = 0; half < 2; ++half) {
+          const int m = mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;    // queries n, n + 1
+          if (n >= p.Lq16) continue;
+          float ds0 = 0.f, ds1 = 0.f;
+          if (k0 + m < p.Lk) {
+            if (n < p.Lq) {
+              const float pr = psg_ex2_approx(fmaf(sa[jn][2 * half], scale_l2, -lse_s[n]));
+              float dpv = da[jn][2 * half];
+              if (p.thr) dpv = keep_ij(p, (long long)bh * p.Lq + n, k0 + m) ? dpv * p.ks : 0.f;
+              ds0 = pr * (dpv - del_s[n]);
+            }
+            if (n + 1 < p.Lq) {
+              const float pr = psg_ex2_approx(fmaf(sa[jn][2 * half + 1], scale_l2, -lse_s[n + 1]));
+              float dpv = da[jn][2 * half + 1];
+              if (p.thr) dpv = keep_ij(p, (long long)bh * p.Lq + n + 1, k0 + m) ? dpv * p.ks : 0.f;
+              ds1 = pr * (dpv - del_s[n + 1]);
+            }
+          }
+          *reinterpret_cast<__nv_bfloat162*>(Ts + m * dp + n) = __floats2bfloat162_rn(ds0, ds1);
+        }
+    }
+    __syncthreads();
+    if (kb + (int)gridDim.x < nkb) {      // K / V tiles are free: fetch the next block's under the dK product
+      const int kn = (kb + gridDim.x) * kBB;
+      load_rows(Ks, hp, ksrc, p.ldk, kn, p.Lk, kBB, p.hd, bar1);
+      load_rows(Vs, hp, vsrc, p.ldv, kn, p.Lk, kBB, p.hd, bar1);
+    }
+    // dK = scale * dS^T Q
+    __nv_bfloat16* kbase = p.dk + (long long)b * p.Lk * p.lddk + h * p.hd;
+    for (int item = warp; item < mtl * ochunks; item += kWarps) {
+      int nc, mt;
+      split_item(item, mtl, nc, mt);
+      float acc[4][4];
+      warp_mma_16x32<true>(acc, Ts, dp, mt * 16, Qs, hp, nc * 32, p.Lq16, lane);
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int m = k0 + mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
+          if (m < p.Lk && n < p.hd)
+            *reinterpret_cast<__nv_bfloat162*>(kbase + (long long)m * p.lddk + n) =
+                __floats2bfloat162_rn(acc[jn][2 * half] * p.scale, acc[jn][2 * half + 1] * p.scale);
+        }
+    }
+    // (the next block's first __syncthreads orders these reads of T before its pass A writes)
   }
 }
 
@@ -452,6 +592,14 @@ static size_t dkv_smem(const Params& p) {
 
 // one CTA per SM anyway (shared memory): 16 warps; otherwise 8 warps so that two or three CTAs share an SM
 static int threads_for(size_t smem) { return smem > 110 * 1024 ? kThreads : 256; }
+
+// CTAs per (batch, head): 1 when the heads alone fill the GPU (resident tiles fetched once per head), else as many as
+// keep every SM busy.  g_split > 0 forces a value (psg_attn_fused_split: tests drive the block loop at small batch).
+static int g_split = 0;
+static int split_for(int nblocks, int heads_total) {
+  int s = g_split > 0 ? g_split : (psg_num_sms() + heads_total - 1) / heads_total;
+  return s < 1 ? 1 : (s > nblocks ? nblocks : s);
+}
 
 static int fill(Params& p, int B, int H, int Lq, int Lk, int hd, float scale, unsigned long long seed, float drop_p) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || hd <= 0 || hd % 16 != 0 || Lk > kMaxLk || Lq > 1024) return -1;
@@ -480,6 +628,13 @@ static int configure(Kern kern, bool& done, const char* name) {
 
 extern "C" {
 
+// Test / measurement hook: CTAs per (batch, head) of the fused attention kernels (0 = by problem size).  Returns the previous value.
+int psg_attn_fused_split(int n) {
+  const int prev = fattn::g_split;
+  if (n >= 0) fattn::g_split = n;
+  return prev;
+}
+
 // 1 if the fused kernels take this problem (bf16; head_dim % 16 == 0; Lk <= 256; everything fits in shared memory).
 int psg_attn_fused_ok(int B, int H, int Lq, int Lk, int hd) {
   fattn::Params p;
@@ -506,7 +661,8 @@ int psg_attn_fused_fwd(const void* q, long long ldq, const void* k, long long ld
   static bool done = false;
   int rc = configure(attn_fwd_kernel, done, "psg_attn_fused_fwd");
   if (rc) return rc;
-  dim3 grid((Lq + kQB - 1) / kQB, B * H);
+  dim3 grid(split_for((Lq + kQB - 1) / kQB, B * H), B * H);
+  p.bar_off = (int)fwd_smem(p) - 32;
   attn_fwd_kernel<<<grid, threads_for(fwd_smem(p)), fwd_smem(p), (cudaStream_t)stream>>>(p);
   PSG_CHECK_LAUNCH("psg_attn_fused_fwd");
   return PSG_OK;
@@ -537,8 +693,10 @@ int psg_attn_fused_bwd(const void* q, long long ldq, const void* k, long long ld
   rc = configure(attn_bwd_dkv_kernel, done2, "psg_attn_fused_bwd");
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  attn_bwd_dq_kernel<<<dim3((Lq + kBB - 1) / kBB, B * H), threads_for(dq_smem(p)), dq_smem(p), st>>>(p);
-  attn_bwd_dkv_kernel<<<dim3((Lk + kBB - 1) / kBB, B * H), threads_for(dkv_smem(p)), dkv_smem(p), st>>>(p);
+  p.bar_off = (int)dq_smem(p) - 32;
+  attn_bwd_dq_kernel<<<dim3(split_for((Lq + kBB - 1) / kBB, B * H), B * H), threads_for(dq_smem(p)), dq_smem(p), st>>>(p);
+  p.bar_off = (int)dkv_smem(p) - 32;
+  attn_bwd_dkv_kernel<<<dim3(split_for((Lk + kBB - 1) / kBB, B * H), B * H), threads_for(dkv_smem(p)), dkv_smem(p), st>>>(p);
   PSG_CHECK_LAUNCH("psg_attn_fused_bwd");
   g_psg_launch_count += 1;  // two kernels
   return PSG_OK;

@@ -341,10 +341,20 @@ def test_attention_tensor_core(cuda_device, B, H, Lq, Lk, hd, p):
 @pytest.mark.parametrize("B,H,Lq,Lk,hd,p", [(2, 4, 196, 196, 160, 0.0), (2, 8, 196, 196, 80, 0.0), (3, 4, 196, 32, 160, 0.0), (3, 4, 49, 49, 320, 0.0),
                                             (2, 8, 49, 77, 160, 0.0), (2, 4, 16, 16, 320, 0.0), (2, 4, 16, 7, 320, 0.0), (5, 8, 100, 70, 48, 0.0),
                                             (2, 4, 49, 32, 320, 0.25), (2, 8, 196, 64, 80, 0.25)])
-def test_attention_fused(cuda_device, B, H, Lq, Lk, hd, p):
-    """Fused bf16 attention (scores on chip, LSE saved, probabilities recomputed in backward) vs an fp32 PyTorch reference."""
+@pytest.mark.parametrize("split", [0, 1, 2])
+def test_attention_fused(cuda_device, B, H, Lq, Lk, hd, p, split):
+    """Fused bf16 attention (scores on chip, LSE saved, probabilities recomputed in backward) vs an fp32 PyTorch reference.
+    split: CTAs per (batch, head); 1 and 2 make one CTA walk several 64-row blocks (the large-batch configuration)."""
     K = _ops()
     dtype = torch.bfloat16
+    prev = K.L.load().psg_attn_fused_split(split)
+    try:
+        _attention_fused_case(K, dtype, B, H, Lq, Lk, hd, p)
+    finally:
+        K.L.load().psg_attn_fused_split(prev)
+
+
+def _attention_fused_case(K, dtype, B, H, Lq, Lk, hd, p):
     assert K.attn_fused_ok(B, H, Lq, Lk, hd)
     C_ = H * hd
     g = torch.Generator(device="cuda").manual_seed(Lq * Lk + hd + 2)

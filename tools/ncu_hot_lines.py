@@ -1,0 +1,65 @@
+"""Executed warp-instructions per CUDA source line of one kernel: joins the SASS page of an .ncu-rep (per-instruction
+counts) with nvdisasm's line table of the object the kernel was built from (same instruction order).
+python tools/ncu_hot_lines.py rep kernel_regex object.o [top_n]"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+import tempfile
+
+rep, kern, obj = sys.argv[1], sys.argv[2], sys.argv[3]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+hdr = rows[hi]
+kname = rows[hi - 1][1] if hi > 0 else kern
+sass = [r for r in rows[hi + 1:] if len(r) > 6 and r[0].startswith("0x")]
+if len([i for i, r in enumerate(rows) if r and r[0] == "Address"]) > 1:      # first kernel only
+    nxt = [i for i, r in enumerate(rows) if r and r[0] == "Address"][1]
+    sass = [r for r in rows[hi + 1:nxt] if len(r) > 6 and r[0].startswith("0x")]
+ie, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
+tmp = tempfile.mkdtemp()
+import os
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
+import glob
+cubin = glob.glob(tmp + "/*.cubin")[0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+# find the function whose mangled name matches
+fn_short = re.sub(r"\(.*", "", kname).split("::")[-1]
+lines_of = []
+cur_line, in_fn = None, False
+for ln in dis:
+    m = re.match(r"\s*\.text\.(\S+):", ln)
+    if m:
+        in_fn = fn_short in m.group(1)
+        continue
+    if ln.startswith("\t.section") or ln.startswith(".section"):
+        in_fn = False
+    if not in_fn:
+        continue
+    m = re.search(r'//## File ".*?", line (\d+)', ln)
+    if m:
+        cur_line = int(m.group(1))
+        continue
+    if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+        lines_of.append(cur_line)
+print(f"kernel {kname[:80]}: {len(sass)} SASS rows in the report, {len(lines_of)} instructions in the object")
+per, smp = collections.Counter(), collections.Counter()
+total = 0
+for i, r in enumerate(sass):
+    n = int(r[ie])
+    line = lines_of[i] if i < len(lines_of) else -1
+    per[line] += n
+    smp[line] += int(r[isamp] or 0)
+    total += n
+src = {}
+try:
+    m = re.search(r'//## File "(.*?)"', "\n".join(dis))
+    src = dict(enumerate(open(m.group(1)).read().splitlines(), 1))
+except Exception:  # noqa: BLE001
+    pass
+print(f"total warp-instructions {total}")
+for line, n in per.most_common(top):
+    print(f"{n / total * 100:5.1f}%  samples {smp[line]:6d}  line {line}: {src.get(line, '').strip()[:110]}")

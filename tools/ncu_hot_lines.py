@@ -9,7 +9,7 @@ import sys
 import tempfile
 
 rep, kern, obj = sys.argv[1], sys.argv[2], sys.argv[3]
-top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+top = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
@@ -27,13 +27,20 @@ import glob
 cubin = glob.glob(tmp + "/*.cubin")[0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 # find the function whose mangled name matches
-fn_short = re.sub(r"\(.*", "", kname).split("::")[-1]
+fn_short = re.sub(r"\(.*", "", kname.replace("(int)", "").replace("(bool)", "")).split("::")[-1]
+targs = ""
+m = re.match(r"(\w+)<(.*)>", fn_short)
+if m:      # template instance: match the Itanium-mangled argument list (ints LiNE, bools LbNE)
+    fn_short = m.group(1)
+    targs = "I" + "".join(("Lb%sE" % a.strip()) if a.strip() in ("0", "1") and kind == "b" else ("Li%sE" % a.strip())
+                          for a, kind in zip(m.group(2).split(","), re.findall(r"\((int|bool)\)", kname.split("(const")[0]) and
+                                             ["b" if k == "bool" else "i" for k in re.findall(r"\((int|bool)\)", kname.split("(const")[0])])) + "E"
 lines_of = []
 cur_line, in_fn = None, False
 for ln in dis:
     m = re.match(r"\s*\.text\.(\S+):", ln)
     if m:
-        in_fn = fn_short in m.group(1)
+        in_fn = fn_short in m.group(1) and targs in m.group(1)
         continue
     if ln.startswith("\t.section") or ln.startswith(".section"):
         in_fn = False
@@ -61,5 +68,7 @@ try:
 except Exception:  # noqa: BLE001
     pass
 print(f"total warp-instructions {total}")
-for line, n in per.most_common(top):
+order = sorted(per, key=lambda l: -smp[l]) if "--by-samples" in sys.argv else [l for l, _ in per.most_common()]
+for line in order[:top]:
+    n = per[line]
     print(f"{n / total * 100:5.1f}%  samples {smp[line]:6d}  line {line}: {src.get(line, '').strip()[:110]}")

@@ -241,6 +241,7 @@ class UNetEngine:
         self._packed_generation = None
         self._edges_dirty = False
         self._wd_all = None
+        self._wt_all = None
         self._build_descriptors()
         self.step_counter = 0
         self.dropout_enabled = True      # honoured only in train() mode
@@ -349,7 +350,7 @@ class UNetEngine:
                 if l.rows is not None:
                     a, e = l.rows
                     wk = wk[a:e]
-                l.wk, l.wt = wk, None
+                l.wk = wk
         self._edges_dirty = False
         self._packed_version = store.version()
         self._packed_generation = store.generation
@@ -373,6 +374,33 @@ class UNetEngine:
                 c.wd = self._wd_all[off:off + n].view(c.cin, c.k * c.k * c.cout)
             off += n
         K.conv_weights_transpose(self.store.shadow, self._wd_all, jobs)
+        # Linear weights [N, K] likewise: dgrad (dX = dY W) reads a K-major [K, N] copy instead of the MN-major in-place
+        # operand (a Linear is a 1-tap conv for the transpose kernel; row slices of a packed in_proj are column slices here)
+        weights = {}
+        for l in self.lins:
+            if isinstance(l, FlatLinW):
+                continue
+            n, k = l.weight.shape[0], l.weight.numel() // l.weight.shape[0]
+            if n % 64 == 0 and k % 64 == 0:
+                weights.setdefault(id(l.weight), l.weight)
+        total = sum(w.numel() for w in weights.values())
+        if total == 0:
+            return
+        if self._wt_all is None or self._wt_all.device != device or self._wt_all.numel() != total:
+            self._wt_all = torch.empty(total, dtype=torch.bfloat16, device=device)
+            rebuild_views = True
+        jobs, off, views = [], 0, {}
+        for wid, w in weights.items():
+            n, k = w.shape[0], w.numel() // w.shape[0]
+            jobs.append((self.store.offset_of(w), off, n, k, 1))
+            views[wid] = self._wt_all[off:off + n * k].view(k, n)
+            off += n * k
+        if rebuild_views:
+            for l in self.lins:
+                full = views.get(id(l.weight)) if not isinstance(l, FlatLinW) else None
+                l.wt = None if full is None else (full if l.rows is None else full[:, l.rows[0]:l.rows[1]])
+        for i in range(0, len(jobs), 64):
+            K.conv_weights_transpose(self.store.shadow, self._wt_all, jobs[i:i + 64])
 
     def mark_params_dirty(self) -> None:
         """Call after updating the flat parameter buffer outside of torch: forces a full refresh of the kernel-side copies."""
@@ -534,7 +562,10 @@ class UNetEngine:
         if not x_needs_grad:
             return
         tgt, acc = self._grad_target(x) if x.parent is None else (x.g(), False)
-        bop = G.mnmajor(w2) if fp32 else G.mnmajor(lw.wk)      # the [N, K] weight read transposed in place
+        if not fp32 and eng == "umma" and lw.wt is not None:
+            bop = G.kmajor(lw.wt)                              # K-major [K, N] copy (see _refresh_dgrad_weights)
+        else:
+            bop = G.mnmajor(w2) if fp32 else G.mnmajor(lw.wk)      # the [N, K] weight read transposed in place
         if eng == "simt" and x.pre is None and scale == 1.0 and tgt.dtype == torch.float32 and tgt.is_contiguous() \
                 and N >= 2048 and x.M * Kd <= 256 * 512:
             # skinny dgrad with a long reduction (the all-blocks conditioning projection): split-K over the CUDA-core engine

@@ -50,7 +50,7 @@ for ln in dis:
     if m:
         cur_line = int(m.group(1))
         continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines_of.append(cur_line)
 print(f"kernel {kname[:80]}: {len(sass)} SASS rows in the report, {len(lines_of)} instructions in the object")
 per, smp = collections.Counter(), collections.Counter()

@@ -63,9 +63,19 @@ def test_groupnorm_fwd_bwd(cuda_device, dtype, B, HW, C, G, silu, eps):
                                                (2, 196, 1280, 32, True, 1e-5), (2, 49, 2560, 32, True, 1e-5), (5, 49, 1280, 32, False, 1e-6),
                                                (5, 16, 1280, 32, False, 1e-6), (7, 16, 2560, 32, True, 1e-5), (1, 729, 64, 32, True, 1e-5),
                                                (300, 16, 640, 32, True, 1e-5), (2, 100, 96, 8, True, 1e-5)])
-def test_groupnorm_fused_fwd_bwd(cuda_device, B, HW, C, G, silu, eps):
-    """Single-pass bf16 GroupNorm(+SiLU) forward/backward, including the free column sums of dx, vs torch fp32."""
+@pytest.mark.parametrize("mode", [0, 1])
+def test_groupnorm_fused_fwd_bwd(cuda_device, B, HW, C, G, silu, eps, mode):
+    """Single-pass bf16 GroupNorm(+SiLU) forward/backward, including the free column sums of dx, vs torch fp32.
+    mode 0: cluster-split kernels where their plan applies (the U-Net shapes), slab kernels otherwise; mode 1: slab only."""
     K = _ops()
+    prev = K.L.load().psg_groupnorm_fused_mode(mode)
+    try:
+        _groupnorm_fused_case(K, B, HW, C, G, silu, eps)
+    finally:
+        K.L.load().psg_groupnorm_fused_mode(prev)
+
+
+def _groupnorm_fused_case(K, B, HW, C, G, silu, eps):
     dtype = torch.bfloat16
     assert K.groupnorm_fused_ok(B, HW, C, G, dtype)
     g = torch.Generator(device="cuda").manual_seed(B * HW + C + 1)

@@ -52,7 +52,13 @@ class FusedAdamW(torch.optim.Optimizer):
         self.step_count = 0
 
     def _ensure_state(self):
-        store = self.unet.engine().store
+        eng = self.unet.engine()
+        store = eng.store
+        if store.flat is None:      # no forward yet (e.g. load_state_dict on a fresh trainer): build the flat buffers now
+            dev = next(self.unet.parameters()).device
+            if dev.type != "cuda":
+                raise L.PsgError("FusedAdamW needs the U-Net on a CUDA device (there is no CPU path)")
+            eng.prepare(dev)
         if self._m is None or self._m.device != store.flat.device or self._m.numel() != store.total:
             dev = store.flat.device
             self._m = torch.zeros(store.total, dtype=torch.float32, device=dev)

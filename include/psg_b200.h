@@ -108,6 +108,7 @@ int psg_ddpm_step(const float* x, const float* eps, const float* z, float* out, 
 /* ---- fused tensor-core attention (bf16): scores stay on chip, forward saves only the row log-sum-exp ------------------
  * replaces the nn.MultiheadAttention core, src/models/unet.py:160-173,217,235 (softmax over keys, dropout on probabilities) */
 int psg_attn_fused_ok(int B, int H, int Lq, int Lk, int hd);
+int psg_attn_fused_small_bwd(int on); /* test / measurement hook: single-kernel backward for Lq, Lk <= 64 (default 1); returns the previous value */
 int psg_attn_fused_split(int n);   /* test / measurement hook: CTAs per (batch, head), 0 = by problem size; returns the previous value */
 int psg_attn_fused_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                        float* lse, int B, int H, int Lq, int Lk, int hd, float scale, unsigned long long drop_seed, float drop_p,

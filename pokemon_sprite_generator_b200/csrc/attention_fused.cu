@@ -141,6 +141,35 @@ __device__ __forceinline__ void warp_mma_16x32(float (&acc)[4][4], const __nv_bf
 }
 // element (e) of acc[jn] sits at row m0 + (lane >> 2) + 8 * (e >> 1), column n0 + jn * 8 + (lane & 3) * 2 + (e & 1)
 
+// Same product with BOTH operands stored reduction-major: A stored [k][m] (pitch lda: the m16k16 fragment comes out of
+// ldmatrix.trans), B stored [k][n] (pitch ldb).  acc = A^T-stored[m0.., :] * B[:, n0..] over k in [0, K), K % 16 == 0.
+__device__ __forceinline__ void warp_mma_16x32_at(float (&acc)[4][4], const __nv_bfloat16* At, int lda, int m0, const __nv_bfloat16* Bm,
+                                                  int ldb, int n0, int K, int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const int j = lane >> 3, r = lane & 7;
+  uint32_t a_addr = smem_u32(At + (r + 8 * (j >> 1)) * lda + m0 + 8 * (j & 1));
+  uint32_t b_addr0 = smem_u32(Bm + (r + 8 * (j & 1)) * ldb + n0 + 8 * (j >> 1));
+  uint32_t b_addr1 = b_addr0 + 32;
+  const uint32_t a_step = (uint32_t)lda * 32u, b_step = (uint32_t)ldb * 32u;
+#pragma unroll 2
+  for (int kk = 0; kk < K; kk += 16) {
+    uint32_t af[4], b0[4], b1[4];
+    ldsm_x4_t(af, a_addr);
+    ldsm_x4_t(b0, b_addr0);
+    ldsm_x4_t(b1, b_addr1);
+    a_addr += a_step;
+    b_addr0 += b_step;
+    b_addr1 += b_step;
+    mma16816(acc[0], af, b0[0], b0[1]);
+    mma16816(acc[1], af, b0[2], b0[3]);
+    mma16816(acc[2], af, b1[0], b1[1]);
+    mma16816(acc[3], af, b1[2], b1[3]);
+  }
+}
+
 __device__ __forceinline__ bool keep_ij(const Params& p, long long row_global, int j) {
   return p.thr == 0 || psg_drop_keep(p.seed, (uint64_t)(row_global * p.Lk + j), p.thr);
 }
@@ -580,6 +609,142 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Params p) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// backward for small problems (Lq <= 64 and Lk <= 64: the 7x7 and 4x4 levels and their cross-attention): ONE CTA per
+// (batch, head) holds Q, K, V, dO, computes S / dPd once and produces dQ, dK and dV (the two-kernel path loads the same four
+// tiles twice, recomputes S three times and spends most of its time in launch and phase latency at these sizes).
+//   smem: K [Lk16][hp] | V [Lk16][hp] | Q [Lq16][hp] | dO [Lq16][hp] | Pd bf16 [Lq16][dp] | dS bf16 [Lq16][dp] | lse | delta
+//   dQ = scale dS K;  dV = Pd^T dO;  dK = scale dS^T Q   (the transposed products read Pd / dS through ldmatrix.trans)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) attn_bwd_small_kernel(const Params p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int bh = blockIdx.x, b = bh / p.H, h = bh - b * p.H;
+  const int hp = p.hp, dp = p.Lk16 + 8;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* Vs = Ks + (size_t)p.Lk16 * hp;
+  __nv_bfloat16* Qs = Vs + (size_t)p.Lk16 * hp;
+  __nv_bfloat16* dOs = Qs + (size_t)p.Lq16 * hp;
+  __nv_bfloat16* Pds = dOs + (size_t)p.Lq16 * hp;
+  __nv_bfloat16* dSs = Pds + (size_t)p.Lq16 * dp;
+  float* lse_s = reinterpret_cast<float*>(dSs + (size_t)p.Lq16 * dp);
+  float* del_s = lse_s + p.Lq16;
+  const uint32_t bar0 = smem_u32(smem + p.bar_off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kWarps = blockDim.x >> 5;
+  const __nv_bfloat16* dosrc = p.dout + (long long)b * p.Lq * p.lddo + h * p.hd;
+  const float scale_l2 = p.scale * 1.4426950408889634f;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar0, 2u * tile_bytes(0, p.Lk, p.Lk16, p.hd) + 2u * tile_bytes(0, p.Lq, p.Lq16, p.hd));
+  }
+  __syncthreads();
+  load_rows(Ks, hp, p.k + (long long)b * p.Lk * p.ldk + h * p.hd, p.ldk, 0, p.Lk, p.Lk16, p.hd, bar0);
+  load_rows(Qs, hp, p.q + (long long)b * p.Lq * p.ldq + h * p.hd, p.ldq, 0, p.Lq, p.Lq16, p.hd, bar0);
+  load_rows(Vs, hp, p.v + (long long)b * p.Lk * p.ldv + h * p.hd, p.ldv, 0, p.Lk, p.Lk16, p.hd, bar0);
+  load_rows(dOs, hp, dosrc, p.lddo, 0, p.Lq, p.Lq16, p.hd, bar0);
+  // delta[i] = dO_i . O_i straight from global while the tiles are in flight, one warp per row; also stage lse (log2 units)
+  for (int r = warp; r < p.Lq16; r += kWarps) {
+    float s = 0.f;
+    if (r < p.Lq) {
+      const __nv_bfloat16* orow = p.o + ((long long)b * p.Lq + r) * p.ldo + h * p.hd;
+      const __nv_bfloat16* drow = dosrc + (long long)r * p.lddo;
+      for (int c = lane * 8; c < p.hd; c += 256) {
+        Vec8<__nv_bfloat16> a, d;
+        a.load(orow + c);
+        d.load(drow + c);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) s = fmaf(a.v[x], d.v[x], s);
+      }
+    }
+    s = psg_warp_sum(s);
+    if (lane == 0) {
+      del_s[r] = s;
+      lse_s[r] = (r < p.Lq) ? p.lse[(long long)bh * p.Lq + r] * 1.4426950408889634f : 0.f;
+    }
+  }
+  mbar_wait(bar0, 0);
+  __syncthreads();
+
+  // S = Q K^T and dPd = dO V^T per 16 x 32 tile in registers -> Pd = drop(P), dS = P o (drop(dPd) - delta) -> shared memory
+  const int mq = p.Lq16 >> 4, mk = p.Lk16 >> 4;
+  const int nchunks = (p.Lk16 + 31) / 32;
+  for (int item = warp; item < mq * nchunks; item += kWarps) {
+    const int nc = item / mq, mt = item - nc * mq;
+    float sa[4][4], da[4][4];
+    // (a chunk may run 16 columns past Lk16: those B rows belong to the next tile in shared memory, results are dropped)
+    warp_mma_16x32<false>(sa, Qs, hp, mt * 16, Ks, hp, nc * 32, p.hd, lane);
+    warp_mma_16x32<false>(da, dOs, hp, mt * 16, Vs, hp, nc * 32, p.hd, lane);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m = mt * 16 + (lane >> 2) + 8 * half;
+      const bool row_ok = m < p.Lq;
+      const float lse_m = lse_s[m], del_m = del_s[m];
+      const uint64_t row_base = (uint64_t)((long long)bh * p.Lq + m) * (uint64_t)p.Lk;
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        const int n = nc * 32 + jn * 8 + (lane & 3) * 2;          // columns n, n + 1
+        if (n >= p.Lk16) continue;
+        float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+        if (row_ok) {
+          bool k0 = true, k1 = true;
+          if (p.thr) keep_pair(p, row_base, n, k0, k1);
+          if (n < p.Lk) {
+            const float pr = psg_ex2_approx(fmaf(sa[jn][2 * half], scale_l2, -lse_m));
+            p0 = k0 ? pr * p.ks : 0.f;
+            d0 = pr * ((k0 ? da[jn][2 * half] * p.ks : 0.f) - del_m);
+          }
+          if (n + 1 < p.Lk) {
+            const float pr = psg_ex2_approx(fmaf(sa[jn][2 * half + 1], scale_l2, -lse_m));
+            p1 = k1 ? pr * p.ks : 0.f;
+            d1 = pr * ((k1 ? da[jn][2 * half + 1] * p.ks : 0.f) - del_m);
+          }
+        }
+        *reinterpret_cast<__nv_bfloat162*>(Pds + m * dp + n) = __floats2bfloat162_rn(p0, p1);
+        *reinterpret_cast<__nv_bfloat162*>(dSs + m * dp + n) = __floats2bfloat162_rn(d0, d1);
+      }
+    }
+  }
+  __syncthreads();
+  // the three output products, one item list: [dQ tiles | dV tiles | dK tiles] x head_dim chunks of 32
+  const int ochunks = (p.hd + 31) / 32;      // head_dim % 32 == 16: the last chunk's upper half is dropped
+  const int nq = mq * ochunks, nk = mk * ochunks;
+  for (int item = warp; item < nq + 2 * nk; item += kWarps) {
+    float acc[4][4];
+    __nv_bfloat16* obase;
+    long long ldo_;
+    int mt, nc, rows;
+    float osc;
+    if (item < nq) {                     // dQ = scale dS K
+      nc = item / mq; mt = item - nc * mq;
+      warp_mma_16x32<true>(acc, dSs, dp, mt * 16, Ks, hp, nc * 32, p.Lk16, lane);
+      obase = p.dq + (long long)b * p.Lq * p.lddq + h * p.hd; ldo_ = p.lddq; rows = p.Lq; osc = p.scale;
+    } else if (item < nq + nk) {         // dV = Pd^T dO
+      const int it = item - nq;
+      nc = it / mk; mt = it - nc * mk;
+      warp_mma_16x32_at(acc, Pds, dp, mt * 16, dOs, hp, nc * 32, p.Lq16, lane);
+      obase = p.dv + (long long)b * p.Lk * p.lddv + h * p.hd; ldo_ = p.lddv; rows = p.Lk; osc = 1.f;
+    } else {                             // dK = scale dS^T Q
+      const int it = item - nq - nk;
+      nc = it / mk; mt = it - nc * mk;
+      warp_mma_16x32_at(acc, dSs, dp, mt * 16, Qs, hp, nc * 32, p.Lq16, lane);
+      obase = p.dk + (long long)b * p.Lk * p.lddk + h * p.hd; ldo_ = p.lddk; rows = p.Lk; osc = p.scale;
+    }
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int m = mt * 16 + (lane >> 2) + 8 * half, n = nc * 32 + jn * 8 + (lane & 3) * 2;
+        if (m < rows && n < p.hd)
+          *reinterpret_cast<__nv_bfloat162*>(obase + (long long)m * ldo_ + n) = __floats2bfloat162_rn(acc[jn][2 * half] * osc, acc[jn][2 * half + 1] * osc);
+      }
+  }
+}
+
+static size_t small_smem(const Params& p) {
+  return ((size_t)2 * p.Lk16 * p.hp + (size_t)2 * p.Lq16 * p.hp) * 2 + (size_t)2 * p.Lq16 * (p.Lk16 + 8) * 2 + (size_t)2 * p.Lq16 * 4 + 64;
+}
+
 static size_t fwd_smem(const Params& p) {
   return ((size_t)2 * p.Lk16 * p.hp + (size_t)kQB * p.hp) * 2 + (size_t)kQB * (p.Lk16 + 4) * 4 + 64;
 }
@@ -596,6 +761,7 @@ static int threads_for(size_t smem) { return smem > 110 * 1024 ? kThreads : 256;
 // CTAs per (batch, head): 1 when the heads alone fill the GPU (resident tiles fetched once per head), else as many as
 // keep every SM busy.  g_split > 0 forces a value (psg_attn_fused_split: tests drive the block loop at small batch).
 static int g_split = 0;
+static int g_small_bwd = 1;      // psg_attn_fused_small_bwd: single-kernel backward for Lq, Lk <= 64
 static int split_for(int nblocks, int heads_total) {
   int s = g_split > 0 ? g_split : (psg_num_sms() + heads_total - 1) / heads_total;
   return s < 1 ? 1 : (s > nblocks ? nblocks : s);
@@ -632,6 +798,14 @@ extern "C" {
 int psg_attn_fused_split(int n) {
   const int prev = fattn::g_split;
   if (n >= 0) fattn::g_split = n;
+  return prev;
+}
+
+// Test / measurement hook: 1 (default) = problems with Lq, Lk <= 64 use the single-kernel backward; 0 = always the dQ + dK/dV
+// pair.  Returns the previous value.
+int psg_attn_fused_small_bwd(int on) {
+  const int prev = fattn::g_small_bwd;
+  if (on == 0 || on == 1) fattn::g_small_bwd = on;
   return prev;
 }
 
@@ -687,6 +861,16 @@ int psg_attn_fused_bwd(const void* q, long long ldq, const void* k, long long ld
   p.dout = (const __nv_bfloat16*)dout; p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.lddo = lddo; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.lse = const_cast<float*>(lse); p.delta = delta;
+  cudaStream_t st0 = (cudaStream_t)stream;
+  if (g_small_bwd && Lq <= 64 && Lk <= 64 && small_smem(p) <= kSmemLimit) {
+    static bool done0 = false;
+    int rc0 = configure(attn_bwd_small_kernel, done0, "psg_attn_fused_bwd");
+    if (rc0) return rc0;
+    p.bar_off = (int)small_smem(p) - 32;
+    attn_bwd_small_kernel<<<B * H, threads_for(small_smem(p)), small_smem(p), st0>>>(p);
+    PSG_CHECK_LAUNCH("psg_attn_fused_bwd");
+    return PSG_OK;
+  }
   static bool done1 = false, done2 = false;
   int rc = configure(attn_bwd_dq_kernel, done1, "psg_attn_fused_bwd");
   if (rc) return rc;

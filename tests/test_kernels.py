@@ -358,10 +358,12 @@ def test_attention_fused(cuda_device, B, H, Lq, Lk, hd, p, split):
     K = _ops()
     dtype = torch.bfloat16
     prev = K.L.load().psg_attn_fused_split(split)
+    prev_small = K.L.load().psg_attn_fused_small_bwd(0 if split == 2 else 1)   # split 2 also keeps the dQ + dK/dV pair covered at Lq, Lk <= 64
     try:
         _attention_fused_case(K, dtype, B, H, Lq, Lk, hd, p)
     finally:
         K.L.load().psg_attn_fused_split(prev)
+        K.L.load().psg_attn_fused_small_bwd(prev_small)
 
 
 def _attention_fused_case(K, dtype, B, H, Lq, Lk, hd, p):

@@ -424,6 +424,16 @@ class UNetEngine:
             return a.grad, False
         return a.grad, True
 
+    def _pass_grad(self, dy: torch.Tensor, a: Act) -> None:
+        """grad(a) += dy for a residual connection (out = f(..) + a).  The first contribution to a stand-alone activation
+        takes dy's buffer itself instead of a copy: dy is dead once its producer's backward entry has been enqueued, and
+        later contributions accumulate into it in place, in stream order."""
+        if a.parent is None and a.grad is None and dy.is_contiguous() and dy.shape == a.t.shape and dy.dtype == a.t.dtype:
+            a.grad = dy
+            return
+        tgt, acc = self._grad_target(a)
+        K.copy_strided(dy, tgt, accumulate=acc)
+
     def _engine_for(self, t: torch.Tensor, edge: bool = False) -> str:
         return "umma" if (t.dtype == torch.bfloat16 and not edge) else "simt"
 
@@ -469,8 +479,7 @@ class UNetEngine:
         else:
             K.colsum(dy_real, 1, None, gb)
         if residual is not None:
-            tgt, acc = self._grad_target(residual)
-            K.copy_strided(dy, tgt, accumulate=acc)
+            self._pass_grad(dy, residual)
         # wgrad: dW[co][tap][ci] = sum_pix dY[pix, co] * im2col(X)[pix, (tap, ci)]
         gw = self.store.grad_of(cw.mod.weight)
         kk = cw.k * cw.k
@@ -548,8 +557,7 @@ class UNetEngine:
         fp32 = x.t.dtype == torch.float32
         dy = out.g()            # for act != NONE this already is the gradient w.r.t. the pre-activation
         if residual is not None:
-            tgt, acc = self._grad_target(residual)
-            K.copy_strided(dy, tgt, accumulate=acc)
+            self._pass_grad(dy, residual)
         scale = alpha
         if act == L.ACT_NONE and drop is not None:
             dpre = torch.empty(dy.shape, dtype=dy.dtype, device=dy.device)

@@ -245,6 +245,7 @@ class UNetEngine:
         self._build_descriptors()
         self.step_counter = 0
         self.dropout_enabled = True      # honoured only in train() mode
+        self.cond_on_tensor_cores = True  # bf16 mode: all-blocks conditioning GEMMs on the tcgen05 engine (see _cond_all)
         self.seed = 0x5EED
         self.launches = 0
 
@@ -351,6 +352,9 @@ class UNetEngine:
                     a, e = l.rows
                     wk = wk[a:e]
                 l.wk = wk
+            for fl in (self.d_cond_time, self.d_cond_text):
+                ow = store.offset_of(fl.weight)
+                fl.wk = store.shadow[ow:ow + fl.n * fl.k].view(fl.n, fl.k)
         self._edges_dirty = False
         self._packed_version = store.version()
         self._packed_generation = store.generation
@@ -681,8 +685,38 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------------------------
     def _cond_all(self, temb: Act, pooled: Act) -> Act:
         """time_proj(time_emb) + text_proj(text_pooled) of every ResBlock at once: [B, sum Cout] (unet.py:119-124)."""
-        cond = self.linear(temb, self.d_cond_time)
-        self.linear(pooled, self.d_cond_text, into=cond, x_needs_grad=False)
+        if not (self.bf16 and self.cond_on_tensor_cores):
+            cond = self.linear(temb, self.d_cond_time)
+            self.linear(pooled, self.d_cond_text, into=cond, x_needs_grad=False)
+            return cond
+        # bf16 mode: the two [B, K] x [sum Cout, K]^T products (and their three backward GEMMs) run on the tcgen05 engine over
+        # bf16 copies of the [B, K] inputs and the bf16 weight shadow, fp32 accumulation and fp32 output (the result is the
+        # conv epilogues' broadcast row bias); on the CUDA-core engine they were 1.2 ms of the step at 5 TFLOP/s
+        store, B, N = self.store, temb.M, self.cond_width
+        lt, lx = self.d_cond_time, self.d_cond_text
+        _, b_t, gw_t, gb_t = lt.views(store)
+        _, b_x, gw_x, gb_x = lx.views(store)
+        t16 = torch.empty(B, lt.k, dtype=torch.bfloat16, device=self.device)
+        p16 = torch.empty(B, lx.k, dtype=torch.bfloat16, device=self.device)
+        K.cast_bf16(temb.t, t16)
+        K.cast_bf16(pooled.t, p16)
+        cond = Act(torch.empty(B, N, dtype=torch.float32, device=self.device), B, 1, 1)
+        G.run_gemm(G.kmajor(t16), G.kmajor(lt.wk), G.Epilogue(out=cond.t, bias=b_t), engine="umma")
+        G.run_gemm(G.kmajor(p16), G.kmajor(lx.wk), G.Epilogue(out=cond.t, bias=b_x, accumulate=True), engine="umma")
+        if self.taping:
+            def bwd():
+                _, _, gw_t, gb_t = lt.views(store)          # (also logs the gradient ranges for parallel.GradSync)
+                _, _, gw_x, gb_x = lx.views(store)
+                dy = cond.g()
+                dy16 = torch.empty(B, N, dtype=torch.bfloat16, device=self.device)
+                K.cast_bf16(dy, dy16)
+                K.colsum(dy, 1, None, gb_t)
+                K.copy_strided(gb_t.view(1, N), gb_x.view(1, N))      # both biases are added to the same sum: same gradient
+                G.run_gemm(G.mnmajor(dy16), G.mnmajor(t16), G.Epilogue(out=gw_t), engine="umma")
+                G.run_gemm(G.mnmajor(dy16), G.mnmajor(p16), G.Epilogue(out=gw_x), engine="umma")
+                tgt, acc = self._grad_target(temb)
+                G.run_gemm(G.kmajor(dy16), G.mnmajor(lt.wk), G.Epilogue(out=tgt, accumulate=acc), engine="umma")
+            self.tape.append(bwd)
         return cond
 
     def _res_block(self, d, x: Act, cond_all: Act, out: Act = None) -> Act:

@@ -696,9 +696,12 @@ class UNetEngine:
         lt, lx = self.d_cond_time, self.d_cond_text
         _, b_t, gw_t, gb_t = lt.views(store)
         _, b_x, gw_x, gb_x = lx.views(store)
-        t16 = torch.empty(B, lt.k, dtype=torch.bfloat16, device=self.device)
+        if temb.t.dtype == torch.bfloat16:
+            t16 = temb.t
+        else:
+            t16 = torch.empty(B, lt.k, dtype=torch.bfloat16, device=self.device)
+            K.cast_bf16(temb.t, t16)
         p16 = torch.empty(B, lx.k, dtype=torch.bfloat16, device=self.device)
-        K.cast_bf16(temb.t, t16)
         K.cast_bf16(pooled.t, p16)
         cond = Act(torch.empty(B, N, dtype=torch.float32, device=self.device), B, 1, 1)
         G.run_gemm(G.kmajor(t16), G.kmajor(lt.wk), G.Epilogue(out=cond.t, bias=b_t), engine="umma")
@@ -715,7 +718,8 @@ class UNetEngine:
                 G.run_gemm(G.mnmajor(dy16), G.mnmajor(t16), G.Epilogue(out=gw_t), engine="umma")
                 G.run_gemm(G.mnmajor(dy16), G.mnmajor(p16), G.Epilogue(out=gw_x), engine="umma")
                 tgt, acc = self._grad_target(temb)
-                G.run_gemm(G.kmajor(dy16), G.mnmajor(lt.wk), G.Epilogue(out=tgt, accumulate=acc), engine="umma")
+                epi = G.Epilogue(out=tgt, accumulate=acc) if tgt.dtype == torch.float32 else G.Epilogue(out=tgt, residual=tgt if acc else None)
+                G.run_gemm(G.kmajor(dy16), G.mnmajor(lt.wk), epi, engine="umma")
             self.tape.append(bwd)
         return cond
 
@@ -785,6 +789,12 @@ class UNetEngine:
             coeff = coeff.to(dev)
         sin = Act(torch.empty(B, 2 * coeff.shape[0], dtype=torch.float32, device=dev), B, 1, 1)
         K.timestep_embedding(t, coeff.float().contiguous(), sin.t)
+        if self.bf16 and self.cond_on_tensor_cores:
+            # the time MLP ([B, 128] -> 512 -> 512 -> 128) also runs on the tcgen05 engine over a bf16 copy of the sinusoidal
+            # embedding (three ~100 us latency-bound CUDA-core launches each way otherwise)
+            sin16 = Act(torch.empty(B, sin.C, dtype=torch.bfloat16, device=dev), B, 1, 1)
+            K.cast_bf16(sin.t, sin16.t)
+            sin = sin16
         h = self.linear(sin, self.d_time[0], act=L.ACT_SILU, x_needs_grad=False)
         h = self.linear(h, self.d_time[1], act=L.ACT_SILU)
         temb = self.linear(h, self.d_time[2])

@@ -189,8 +189,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # rank 0 must print exactly one line on stdout
+        # rank 0 must print exactly ONE line on stdout: NCCL writes its debug output (the "NCCL version ..." banner at
+        # VERSION / WARN / INFO level) to stdout unless told otherwise
+        # (and NCCL honours NCCL_DEBUG_FILE only above VERSION level, so VERSION is raised to WARN)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # the gradient all-reduce runs inside backward (parallel.GradSync): keep its CTA count small and known, so the
         # persistent GEMM grids can leave exactly that many SMs free while buckets are in flight
         os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("PSG_COMM_SMS", "8"))

@@ -197,7 +197,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # the gradient all-reduce runs inside backward (parallel.GradSync): keep its CTA count small and known, so the
         # persistent GEMM grids can leave exactly that many SMs free while buckets are in flight
-        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("PSG_COMM_SMS", "8"))
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("PSG_COMM_SMS", "16"))
         dist.init_process_group("nccl", device_id=dev)
     L.check(L.load().psg_check_device(), "psg_check_device")
     W = max(args.warmup, 3)

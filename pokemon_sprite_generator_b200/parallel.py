@@ -78,7 +78,7 @@ class GradSync:
     run next to the collective on the device, however far the host runs ahead."""
 
     def __init__(self, group=None, bucket_bytes: int = 128 << 20, reserve_sms: int = 0,
-                 reserve_hook: Optional[Callable[[int], None]] = None, prescaled: bool = True, window_entries: int = 6):
+                 reserve_hook: Optional[Callable[[int], None]] = None, prescaled: bool = True, window_entries: int = 4):
         self.group = group
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.reserve_sms, self.reserve_hook = reserve_sms, reserve_hook

@@ -128,11 +128,11 @@ class TrainStep:
         self.overlap = os.environ.get("PSG_GRAD_OVERLAP", "backward")
         self.grad_sync = None
         if self.world > 1 and self.overlap == "backward":
-            reserve = int(os.environ.get("PSG_COMM_SMS", os.environ.get("NCCL_MAX_CTAS", "8")))
+            reserve = int(os.environ.get("PSG_COMM_SMS", os.environ.get("NCCL_MAX_CTAS", "16")))
             lib = L.load()
             self.grad_sync = GradSync(process_group, bucket_bytes=int(os.environ.get("PSG_BUCKET_MB", "128")) << 20,
                                       reserve_sms=reserve, reserve_hook=lambda n: lib.psg_umma_reserve_sms(int(n)), prescaled=True,
-                                      window_entries=int(os.environ.get("PSG_COMM_WINDOW", "6")))
+                                      window_entries=int(os.environ.get("PSG_COMM_WINDOW", "4")))
 
     def __call__(self, latent: torch.Tensor, text_emb: torch.Tensor, timesteps: Optional[torch.Tensor] = None,
                  noise: Optional[torch.Tensor] = None) -> torch.Tensor:

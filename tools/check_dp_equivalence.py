@@ -17,7 +17,7 @@ from pokemon_sprite_generator_b200.unet import UNet
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-os.environ.setdefault("NCCL_MAX_CTAS", "8")
+os.environ.setdefault("NCCL_MAX_CTAS", "16")
 dist.init_process_group("nccl", device_id=dev)
 per, steps = 2, 4
 dtype = torch.float32 if (len(sys.argv) < 2 or sys.argv[1] == "fp32") else torch.bfloat16

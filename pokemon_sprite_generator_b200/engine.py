@@ -782,7 +782,7 @@ class UNetEngine:
         text = text_emb.detach().contiguous().float()
         t = timesteps.detach().to(device=dev, dtype=torch.int64).contiguous()
 
-        # ---- conditioning path (fp32, M = B rows) ----
+        # ---- conditioning path (M = B rows; fp32 on the CUDA-core engine in parity mode, bf16 tensor-core GEMMs otherwise) ----
         u = self.unet
         coeff = u.time_embed.emb_coeff
         if coeff.device != dev:

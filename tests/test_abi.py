@@ -50,3 +50,21 @@ def test_compute_paths_fail_loudly_without_cuda():
     # product code must not import the oracle
     for f in (ROOT / "pokemon_sprite_generator_b200").glob("*.py"):
         assert "oracle" not in f.read_text().replace("the oracle", ""), f
+
+
+def test_groupnorm_cluster_plan_covers_the_unet_shapes(lib):
+    """Host-side planner of the cluster-split GroupNorm kernels (norm_cluster.cu): every GroupNorm shape of the U-Net gets a
+    plan whose CTAs tile the unit's pixels exactly, fit in shared memory and use a legal cluster size."""
+    out = (C.c_int * 8)()
+    for hw, c in [(729, 320), (729, 640), (196, 640), (196, 1280), (49, 1280), (49, 2560), (16, 1280), (16, 2560)]:
+        for bwd in (0, 1):
+            assert lib.psg_groupnorm_cluster_plan(256, hw, c, 32, bwd, out) == 0, (hw, c, bwd)
+            cc, s, rp, r, tu, u, iters, smem = list(out)
+            assert cc in (80, 160) and c % cc == 0 and cc % (c // 32) == 0          # whole groups, whole 32 B sectors
+            assert s in (1, 2, 4, 8) and (s - 1) * rp < hw <= s * rp                  # every rank owns rows, all rows owned
+            assert tu == (cc // 8) * r and tu % 32 == 0 and iters * r >= rp and iters <= 16
+            assert (u == 1 or s == 1) and tu * u <= 512 and smem <= 200 * 1024
+        assert lib.psg_groupnorm_fused_ok(256, hw, c, 32, 1) == 1
+    # shapes outside the family are refused by the cluster planner and served by the slab kernels
+    assert lib.psg_groupnorm_cluster_plan(2, 100, 96, 8, 0, out) != 0
+    assert lib.psg_groupnorm_fused_ok(2, 100, 96, 8, 1) == 1

@@ -136,3 +136,23 @@ def test_two_rank_gloo_gradsync_overlapped_buckets():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(all(r[1:]) for r in results), results
+
+
+def test_gradsync_plan_head_bucket_and_bounds():
+    """GradSync._plan (no process group needed): the leading ranges finalised in the last tape entries form the head bucket,
+    the rest is cut into ~bucket_bytes slices that tile the buffer exactly, and each bucket is issued after its last writer."""
+    from pokemon_sprite_generator_b200.parallel import GradSync
+    sync = GradSync(None, bucket_bytes=4 * 1000)
+    sync.flat = torch.zeros(10_000)
+    sync.n_entries = 100
+    # offset -> (numel, last entry): [0, 1500) written at the very end (conditioning / time MLP), the tail first
+    sync.range_last = {0: (1000, 100), 1000: (500, 99), 1500: (2500, 60), 4000: (3000, 40), 7000: (2990, 10)}
+    sync._plan()
+    assert sync.bounds[0] == (0, 1500)
+    assert sync.bounds[-1][1] == 10_000 and all(a[1] == b[0] for a, b in zip(sync.bounds, sync.bounds[1:]))
+    assert all(e - s <= 1000 + 1 for s, e in sync.bounds[1:])
+    issued_at = {b: at for at, bs in sync.ready_at.items() for b in bs}
+    assert 0 not in issued_at                                   # the head bucket goes out after the last entry (finish())
+    for b, (s, e) in enumerate(sync.bounds[1:], 1):
+        writers = [at for off, (n, at) in sync.range_last.items() if off < e and off + n > s]
+        assert issued_at[b] == max(writers)

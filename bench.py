@@ -272,6 +272,28 @@ def main():
                 "algorithmic_tflop_per_step": um_flops / Ksteps / 1e12,
                 "step_model_tflops": B * TRAIN_GFLOP_PER_SAMPLE / 1e3 / (ms_per_step / 1e3)}
 
+    # ---- HBM-bound kernel families: one extra (untimed) step with CUDA events around every C-ABI call ----
+    # algorithmic bytes: GroupNorm fwd 2 N s, bwd 3 N s with N = 6,403,520 activations/sample, s = 2 B (bf16);
+    # AdamW (7*4 + 2) B per parameter (fp32 p, g, m, v read, p, m, v written, bf16 shadow written); grad-norm 4 B per parameter
+    hbm_kernels = None
+    if rank == 0 and world == 1:
+        L.CALL_PROFILE = []
+        step_fn(dev_lat[0], dev_txt[0])
+        torch.cuda.synchronize()
+        calls, L.CALL_PROFILE = L.CALL_PROFILE, None
+        tot = {}
+        for name, s0, s1 in calls:
+            tot[name] = tot.get(name, 0.0) + s0.elapsed_time(s1)
+        n_act, n_par = 6403520 * B, sum(p.numel() for p in unet.parameters())
+        fams = {"groupnorm_fwd": ("psg_groupnorm_fused_fwd", 2 * n_act * 2), "groupnorm_bwd": ("psg_groupnorm_fused_bwd", 3 * n_act * 2),
+                "adamw": ("psg_adamw_step", 30 * n_par), "grad_sumsq": ("psg_sumsq", 4 * n_par)}
+        hbm_kernels = {"peak_gbs": peaks["hbm_gbs"], "peak_source": f"{peaks['src']} copy bandwidth"}
+        for fam, (cname, nbytes) in fams.items():
+            if tot.get(cname):
+                gbs = nbytes / (tot[cname] / 1e3) / 1e9
+                hbm_kernels[fam] = {"ms_per_step": round(tot[cname], 3), "algorithmic_gb": round(nbytes / 1e9, 3), "achieved_gbs": round(gbs, 1),
+                                    "frac": round(gbs / peaks["hbm_gbs"], 3) if peaks["hbm_gbs"] else None}
+
     # ---- end-to-end through the public trainer API: pinned host inputs in, loss out, every step ----
     trainer = DiffusionTrainer.__new__(DiffusionTrainer)       # public step API without the dataset / VAE set-up
     trainer.unet, trainer.device, trainer._step = unet, dev, step_fn
@@ -338,7 +360,7 @@ def main():
                 "data": "synthetic",
                 "config": workload_config(B, Lt, args.heads, not args.no_dropout, world),
                 "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "denoise": denoise, "loss": final_loss, "comm": comm}
+                "denoise": denoise, "loss": final_loss, "comm": comm, "hbm_kernels": hbm_kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

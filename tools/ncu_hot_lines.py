@@ -27,14 +27,14 @@ import glob
 cubin = glob.glob(tmp + "/*.cubin")[0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 # find the function whose mangled name matches
-fn_short = re.sub(r"\(.*", "", kname.replace("(int)", "").replace("(bool)", "")).split("::")[-1]
+# mangled-name fragments of the kernel: base name, and for a template instance its Itanium argument list (LiNE / LbNE)
+plain = kname.split("(const")[0] if "<" in kname else re.sub(r"\(.*", "", kname)
+fn_short = re.sub(r"<.*", "", re.sub(r"^void ", "", plain)).split("::")[-1]
 targs = ""
-m = re.match(r"(\w+)<(.*)>", fn_short)
-if m:      # template instance: match the Itanium-mangled argument list (ints LiNE, bools LbNE)
-    fn_short = m.group(1)
-    targs = "I" + "".join(("Lb%sE" % a.strip()) if a.strip() in ("0", "1") and kind == "b" else ("Li%sE" % a.strip())
-                          for a, kind in zip(m.group(2).split(","), re.findall(r"\((int|bool)\)", kname.split("(const")[0]) and
-                                             ["b" if k == "bool" else "i" for k in re.findall(r"\((int|bool)\)", kname.split("(const")[0])])) + "E"
+m = re.search(r"<(.*)>", plain)
+if m:
+    parts = re.findall(r"\((int|bool)\)\s*(-?\d+)", m.group(1))
+    targs = "I" + "".join(("Lb%sE" if kind == "bool" else "Li%sE") % val for kind, val in parts) + "E"
 lines_of = []
 cur_line, in_fn = None, False
 for ln in dis:
@@ -46,9 +46,9 @@ for ln in dis:
         in_fn = False
     if not in_fn:
         continue
-    m = re.search(r'//## File ".*?", line (\d+)', ln)
+    m = re.search(r'//## File "(.*?)", line (\d+)', ln)
     if m:
-        cur_line = int(m.group(1))
+        cur_line = (m.group(1), int(m.group(2)))      # inlined helpers live in other files (psg_common.cuh ...): keep the file
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines_of.append(cur_line)
@@ -57,18 +57,28 @@ per, smp = collections.Counter(), collections.Counter()
 total = 0
 for i, r in enumerate(sass):
     n = int(r[ie])
-    line = lines_of[i] if i < len(lines_of) else -1
+    line = lines_of[i] if i < len(lines_of) and lines_of[i] is not None else -1
     per[line] += n
     smp[line] += int(r[isamp] or 0)
     total += n
-src = {}
-try:
-    m = re.search(r'//## File "(.*?)"', "\n".join(dis))
-    src = dict(enumerate(open(m.group(1)).read().splitlines(), 1))
-except Exception:  # noqa: BLE001
-    pass
+sources = {}
+
+
+def text_of(key):
+    if not isinstance(key, tuple):
+        return ""
+    path, line = key
+    if path not in sources:
+        try:
+            sources[path] = open(path).read().splitlines()
+        except OSError:
+            sources[path] = []
+    lines = sources[path]
+    return lines[line - 1].strip() if 0 < line <= len(lines) else ""
+
+
 print(f"total warp-instructions {total}")
 order = sorted(per, key=lambda l: -smp[l]) if "--by-samples" in sys.argv else [l for l, _ in per.most_common()]
-for line in order[:top]:
-    n = per[line]
-    print(f"{n / total * 100:5.1f}%  samples {smp[line]:6d}  line {line}: {src.get(line, '').strip()[:110]}")
+for key in order[:top]:
+    where = f"{key[0].split('/')[-1]}:{key[1]}" if isinstance(key, tuple) else "?"
+    print(f"{per[key] / total * 100:5.1f}%  samples {smp[key]:6d}  {where}: {text_of(key)[:110]}")

@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps 3 --warmup 1        # CPU arm (oracle port of the reference path)
+    python bench.py --impl reference --steps 3 --warmup 1        # CPU arm (the unmodified reference from oracle/_ref)
 
 A "step" is one optimisation step of the stage-2 trainer on synthetic inputs of the reference's shapes
 (SURVEY.md 8d): q_sample -> U-Net forward -> SmoothL1 -> backward -> [NCCL all-reduce] -> global-norm clip -> AdamW ->
@@ -84,15 +84,73 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference step (the reference itself cannot travel to the GPU box)
+# CPU arm: the UNMODIFIED reference (oracle/_ref, shipped by oracle/build_ref.py) -- its own train_epoch, U-Net, scheduler
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps: int, warmup: int, batch: int = 2):
-    """Times the reference algorithm's train step (improved_diffusion_trainer.py:363-413) on the host cores: oracle U-Net
-    forward + autograd backward + the 478-`.item()` norm loop + clip_grad_norm_(0.7) + AdamW(eps=1e-6), fp32, batch 2."""
+CPU_BATCH = 8       # samples per CPU step: a bounded sample of the batch-256 workload (same graph, same optimiser)
+
+
+class _NullWriter:
+    def add_scalar(self, *a, **k):
+        pass
+
+
+def _reference_trainer_namespace(ref, batch: int, n_batches: int, total_steps: int):
+    """`self` for ImprovedDiffusionTrainer.train_epoch driven unbound (the full ctor needs a VAE checkpoint, BERT weights
+    and the dataset, none of which exist offline -- SURVEY 8c).  The frozen encoders, which are NOT on the path, are
+    identity stubs over pre-made synthetic latents / text embeddings; everything on the path is the reference's own:
+    UNet(num_heads=4), NoiseScheduler, SmoothL1Loss(beta=0.1), AdamW(eps=1e-6), OneCycleLR, the 478-.item() norm loop,
+    clip_grad_norm_(0.7) -- i.e. improved_diffusion_trainer.py:211-216,277-283,300,313-320,335-445 executed as written."""
+    import logging
+    import types
     import torch
-    from oracle import inputs, unet_oracle
-    from pokemon_sprite_generator_b200.unet import UNet
+    torch.manual_seed(0)
+    unet = ref.UNet(latent_dim=8, text_dim=256, time_emb_dim=128, num_heads=4)
+    opt = torch.optim.AdamW(unet.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-4, eps=1e-6)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-4, total_steps=total_steps, pct_start=0.1, anneal_strategy="cos")
+    g = torch.Generator().manual_seed(1234)
+    loader = [{"image": torch.randn(batch, 8, 27, 27, generator=g), "full_description": torch.randn(batch, 32, 256, generator=g)}
+              for _ in range(n_batches)]
+    logger = logging.getLogger("psg_b200.bench.reference")
+    logger.setLevel(logging.ERROR)
+    fake = types.SimpleNamespace(unet=unet, data_loaders={"train": loader}, device=torch.device("cpu"),
+                                 text_encoder=lambda d: d, vae_encoder=lambda im: (im, None, None),
+                                 noise_scheduler=ref.NoiseScheduler(), optimizer=opt, scheduler=sched,
+                                 criterion=torch.nn.SmoothL1Loss(beta=0.1), max_grad_norm=0.7, global_step=0,
+                                 config={"training": {"log_every": 50}}, writer=_NullWriter(), logger=logger)
+    fake.check_for_nans = types.MethodType(ref.ImprovedDiffusionTrainer.check_for_nans, fake)
+    return fake
+
+
+def cpu_reference_steps(steps: int, warmup: int, batch: int = CPU_BATCH):
+    """Times the reference's train step on the host cores, fp32, `batch` samples per step, all host threads.
+    kind "reference": ImprovedDiffusionTrainer.train_epoch itself over `steps` batches (after `warmup` batches);
+    kind "port" (only when neither /root/reference nor oracle/_ref exists): the oracle restatement of the same step."""
+    import torch
+    from oracle import ref_loader
     torch.set_num_threads(os.cpu_count() or 1)
+    if ref_loader.available():
+        from oracle import build_ref
+        if ref_loader.REFERENCE_ROOT == build_ref.DST and not build_ref.verify():
+            raise SystemExit("oracle/_ref does not match its manifest")
+        os.environ.setdefault("TQDM_DISABLE", "1")      # (read when tqdm is first imported, i.e. by the reference module)
+        ref = ref_loader.load()
+        fake = _reference_trainer_namespace(ref, batch, warmup + steps, warmup + steps + 8)
+        loader = fake.data_loaders["train"]
+        if warmup:
+            fake.data_loaders = {"train": loader[:warmup]}
+            ref.ImprovedDiffusionTrainer.train_epoch(fake, 0)
+        fake.data_loaders = {"train": loader[warmup:]}
+        t0 = time.perf_counter()
+        out = ref.ImprovedDiffusionTrainer.train_epoch(fake, 1)
+        sec = (time.perf_counter() - t0) / steps
+        assert fake.global_step == warmup + steps, f"reference train_epoch skipped batches ({fake.global_step} of {warmup + steps})"
+        return {"samples_per_s": batch / sec, "ms_per_step": sec * 1e3, "cores": torch.get_num_threads(), "batch": batch, "steps": steps,
+                "kind": "reference", "loss": out["train_loss"],
+                "what": "unmodified reference: ImprovedDiffusionTrainer.train_epoch + UNet(num_heads=4) + NoiseScheduler + "
+                        "AdamW/OneCycleLR from oracle/_ref (byte-identical copy of /root/reference/src), fp32"}
+    from oracle import inputs, unet_oracle
+    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
+    from pokemon_sprite_generator_b200.unet import UNet
     torch.manual_seed(0)
     model = UNet()
     params = {k: v.detach().clone().requires_grad_(True) for k, v in model.named_parameters()}
@@ -100,8 +158,8 @@ def cpu_reference_steps(steps: int, warmup: int, batch: int = 2):
     sd["time_embed.emb_coeff"] = model.time_embed.emb_coeff
     del model
     opt = torch.optim.AdamW(list(params.values()), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-4, eps=1e-6)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-4, total_steps=warmup + steps + 8, pct_start=0.1, anneal_strategy="cos")
     crit = torch.nn.SmoothL1Loss(beta=0.1)
-    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
     ns = NoiseScheduler()
     latent, text, _, _ = inputs.make_inputs(batch, 32, 1234)
     times = []
@@ -120,11 +178,13 @@ def cpu_reference_steps(steps: int, warmup: int, batch: int = 2):
             total += p.grad.norm(2).item() ** 2
         torch.nn.utils.clip_grad_norm_(list(params.values()), max_norm=0.7)
         opt.step()
+        sched.step()
         loss.item()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return {"samples_per_s": batch / sec, "ms_per_step": sec * 1e3, "cores": torch.get_num_threads(), "batch": batch, "steps": steps}
+    return {"samples_per_s": batch / sec, "ms_per_step": sec * 1e3, "cores": torch.get_num_threads(), "batch": batch, "steps": steps,
+            "kind": "port", "what": "oracle port of the reference train step (oracle/_ref absent), fp32"}
 
 
 def workload_config(B: int, Lt: int, heads: int, dropout: bool, world: int) -> dict:
@@ -141,16 +201,88 @@ def run_reference_arm(args):
     if rank != 0:
         return
     r = cpu_reference_steps(max(1, args.steps), max(0, args.warmup))
+    sample = f"{r['steps']} steps of {r['batch']} samples after {max(0, args.warmup)} warm-up ({r['what']})"
     line = {"impl": "reference", "metric": METRIC, "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args.batch, args.text_len, args.heads, not args.no_dropout, max(1, args.gpus)),
-                           sample=f"the reference algorithm's fp32 step at batch {r['batch']} per step on the host CPU (same graph, "
-                                  f"same optimiser; samples/s does not depend on the batch split)"),
-            "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                             "sample": f"{args.steps} steps of batch {r['batch']} (oracle port of the reference step, fp32)"},
-            "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": workload_config(args.batch, args.text_len, args.heads, not args.no_dropout, max(1, args.gpus)),
+            "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+            "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "loss": r.get("loss")}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm, config 4: DDPM sampling (improved_diffusion_trainer.py:508-569), prompt-sharded, no communication
+# ----------------------------------------------------------------------------------------------------------------------
+def run_sample_mode(args):
+    """Every rank runs sampler.ddpm_sample(use_cuda_graph=True) over ITS 128 prompts (1024 / 8; weak scaling in the GPU count)
+    for `--sample-steps` reverse steps (1000: fast_sampling=False; anything else: the 20-step fast schedule).  The timed
+    region is the whole public call (x_T draw, graph capture excluded by one untimed 20-step call, 1000 x [graph replay +
+    noise draw + reverse-step kernel]); rank 0 prints one JSON line with denoise steps/s per GPU and whole-job prompts/s."""
+    import torch
+    import torch.distributed as dist
+    from pokemon_sprite_generator_b200 import _lib as L
+    from pokemon_sprite_generator_b200 import parallel, sampler
+    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
+    from pokemon_sprite_generator_b200.unet import UNet
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    L.check(L.load().psg_check_device(), "psg_check_device")
+    per_gpu = args.prompts // 8
+    torch.manual_seed(0)
+    unet = UNet(num_heads=args.heads, compute_dtype=torch.bfloat16).to(dev).eval()
+    ns = NoiseScheduler().to(dev)
+    g = torch.Generator(device="cpu").manual_seed(4321)
+    all_text = torch.randn(world * per_gpu, args.text_len, 256, generator=g)
+    text = parallel.shard_prompts(all_text).to(dev)          # this rank's slice; nothing is exchanged afterwards
+    assert text.shape[0] == per_gpu
+    full = args.sample_steps >= 1000
+    torch.manual_seed(1000 + rank)
+    sampler.ddpm_sample(unet, ns, text, per_gpu, fast_sampling=True, use_cuda_graph=True)      # warm-up (20 steps)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib = L.load()
+    lib.psg_launch_count.restype = __import__("ctypes").c_longlong
+    lib.psg_launch_count(1)
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    x = sampler.ddpm_sample(unet, ns, text, per_gpu, fast_sampling=not full, use_cuda_graph=True)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    n_steps = 1000 if full else 20
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    finite = bool(torch.isfinite(x).all())
+    if rank == 0:
+        steps_per_s = n_steps / (ms / 1e3)
+        line = {"metric": "ddpm_denoise_steps_per_s_per_gpu", "value": steps_per_s, "unit": "steps/s/GPU", "n_gpus": world,
+                "steps": n_steps, "warmup": 20, "ms_per_step": ms / n_steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"DDPM sampling (config 4), {n_steps} reverse steps, {per_gpu} prompts/GPU ({world * per_gpu} total), "
+                                       f"27x27x8 latents, {args.text_len}x256 text emb, heads {args.heads}, no CFG, CUDA-graph U-Net forward",
+                           "parallelism": f"prompt-sharded x{world}, no communication"},
+                "prompts_per_s": world * per_gpu / (ms / 1e3), "total_s": ms / 1e3, "finite": finite,
+                "tflops_per_gpu": per_gpu * FWD_GFLOP_PER_SAMPLE / 1e3 / (ms / n_steps / 1e3),
+                "gpu_launches": int(lib.psg_launch_count(0)), "clocks": clk,
+                "note": "launch count: kernels inside graph replays are counted once at capture, not per replay"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -169,9 +301,15 @@ def main():
     ap.add_argument("--denoise-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "sample"],
+                    help="sample: BASELINE config 4 -- full DDPM sampling, prompts sharded over the GPUs with no communication")
+    ap.add_argument("--prompts", type=int, default=1024, help="--mode sample: global prompt batch at 8 GPUs (128 per GPU, weak scaling)")
+    ap.add_argument("--sample-steps", type=int, default=1000, help="--mode sample: reverse steps (1000 = fast_sampling=False)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.mode == "sample":
+        return run_sample_mode(args)
 
     import torch
     import torch.distributed as dist
@@ -286,7 +424,7 @@ def main():
             tot[name] = tot.get(name, 0.0) + s0.elapsed_time(s1)
         n_act, n_par = 6403520 * B, sum(p.numel() for p in unet.parameters())
         fams = {"groupnorm_fwd": ("psg_groupnorm_fused_fwd", 2 * n_act * 2), "groupnorm_bwd": ("psg_groupnorm_fused_bwd", 3 * n_act * 2),
-                "adamw": ("psg_adamw_step", 30 * n_par), "grad_sumsq": ("psg_sumsq", 4 * n_par)}
+                "adamw": ("psg_adam_step", 30 * n_par), "grad_sumsq": ("psg_sumsq", 4 * n_par)}
         hbm_kernels = {"peak_gbs": peaks["hbm_gbs"], "peak_source": f"{peaks['src']} copy bandwidth"}
         for fam, (cname, nbytes) in fams.items():
             if tot.get(cname):
@@ -294,9 +432,47 @@ def main():
                 hbm_kernels[fam] = {"ms_per_step": round(tot[cname], 3), "algorithmic_gb": round(nbytes / 1e9, 3), "achieved_gbs": round(gbs, 1),
                                     "frac": round(gbs / peaks["hbm_gbs"], 3) if peaks["hbm_gbs"] else None}
 
+    # q_sample / SmoothL1 / DDPM reverse step at a roofline batch (at batch 256 they are L2-resident 10-20 us
+    # launches): batch 8192 => 191 MB per tensor (> the 126 MB L2), each kernel timed alone, 20 launches, CUDA events.
+    # algorithmic bytes per sample: q_sample 3 x 5832 x 4, SmoothL1 fwd+bwd 3 x 5832 x 4, DDPM step 4 x 5832 x 4
+    if hbm_kernels is not None:
+        try:
+            from pokemon_sprite_generator_b200.losses import smooth_l1_fwd_bwd
+            Bh = 8192
+            xs = [torch.randn(Bh, 8, 27, 27, device=dev) for _ in range(3)]
+            tt_h = torch.randint(0, 1000, (Bh,), device=dev)
+            per = 5832 * 4
+            small = {"q_sample": (lambda: ns.add_noise(xs[0], xs[1], tt_h, clamp=3.0), 3 * per * Bh),
+                     "smooth_l1_fwd_bwd": (lambda: smooth_l1_fwd_bwd(xs[0], xs[1], beta=0.1), 3 * per * Bh),
+                     "ddpm_step": (lambda: ns.ddpm_step(xs[0], xs[1], 500, xs[2]), 4 * per * Bh)}
+            for fam, (fn, nbytes) in small.items():
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for _ in range(20):
+                    fn()
+                s1.record()
+                torch.cuda.synchronize()
+                msk = s0.elapsed_time(s1) / 20
+                gbs = nbytes / (msk / 1e3) / 1e9
+                hbm_kernels[fam] = {"ms_per_launch": round(msk, 4), "batch": Bh, "algorithmic_gb": round(nbytes / 1e9, 3),
+                                    "achieved_gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 3) if peaks["hbm_gbs"] else None,
+                                    "note": "includes the torch.empty of the output (public API call)"}
+            del xs
+        except Exception as ex:
+            hbm_kernels["small_kernels_error"] = repr(ex)[:200]
+
     # ---- end-to-end through the public trainer API: pinned host inputs in, loss out, every step ----
-    trainer = DiffusionTrainer.__new__(DiffusionTrainer)       # public step API without the dataset / VAE set-up
-    trainer.unet, trainer.device, trainer._step = unet, dev, step_fn
+    # built through the constructor a user calls (synthetic pre-encoded batches injected in place of the dataset / frozen
+    # encoders, which are out of scope); it then adopts the warmed-up U-Net / optimiser so no second 13 GB model is built
+    import tempfile
+    cfg = {"experiment_dir": tempfile.mkdtemp(prefix="psg_bench_"), "model": {"latent_dim": 8, "text_embedding_dim": 256, "num_heads": args.heads},
+           "training": {"diffusion_epochs": 1}, "unet_optimization": {"learning_rate": 1e-4, "weight_decay": 1e-4, "max_grad_norm": 0.7}}
+    trainer = DiffusionTrainer(cfg, None, f"bench_rank{rank}", components={"data_loaders": {"train": [None] * total_sched, "val": [], "test": []},
+                                                                          "unet": unet, "optimizer": opt, "lr_scheduler": sched, "train_step": step_fn})
+    assert trainer.unet is unet and trainer._step is step_fn
     for i in range(2):
         trainer.train_step(host_lat[i % nb], host_txt[i % nb]).item()
     barrier()
@@ -351,8 +527,8 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_steps(3, 1)
-        cpu_baseline = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                        "sample": "3 steps of batch 2 after 1 warm-up (oracle port of the reference train step, fp32)"}
+        cpu_baseline = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                        "sample": f"3 steps of {r['batch']} samples after 1 warm-up ({r['what']})"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": Ksteps, "warmup": W,

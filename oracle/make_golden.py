@@ -144,5 +144,31 @@ def main():
     unet_golden(ref)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--b256" not in __import__("sys").argv:
     main()
+
+
+def unet_b256_golden(ref, batch: int = 256, seed: int = 4321, stride: int = 23):
+    """One reference golden AT THE BENCHMARK SHAPE (BASELINE config 2: batch 256, heads 4, 32 text tokens), seed-0 init and the
+    O(1)-gain re-init: loss, per-parameter gradient norms, gradient samples and a strided sample of the noise prediction
+    (every `stride`-th element of the flattened output + samples 0 and batch-1 in full).  ~10 CPU-minutes and ~40 GB per case
+    on 8 threads; written to tests/golden/unet_b256.pt (small).        python -m oracle.make_golden --b256"""
+    torch.manual_seed(0)
+    unet = ref.UNet(latent_dim=8, text_dim=256, time_emb_dim=128, num_heads=4).eval()
+    sd = {k: v.detach().clone() for k, v in unet.state_dict().items()}
+    golden = {"batch": batch, "seed": seed, "stride": stride, "heads": 4, "text_len": 32, "cases": {}}
+    for name, state in (("init", sd), ("amp", inputs.amplify_state_dict(sd))):
+        unet.load_state_dict(state)
+        case = _run_case(ref, unet, 4, batch, 32, True, seed=seed)
+        out = case.pop("output")
+        case["output_strided"] = out.flatten()[::stride].clone()
+        case["output_first"], case["output_last"] = out[0].clone(), out[-1].clone()
+        case["output_absmax"], case["output_std"] = float(out.abs().max()), float(out.std())
+        golden["cases"][name] = case
+        torch.save(golden, OUT / "unet_b256.pt")
+        print(f"wrote unet_b256.pt ({name})", flush=True)
+
+
+if __name__ == "__main__" and "--b256" in __import__("sys").argv:
+    torch.set_num_threads(8)
+    unet_b256_golden(ref_loader.load())

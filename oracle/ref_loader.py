@@ -1,4 +1,5 @@
-"""ORACLE helper: import the unmodified reference from /root/reference (only exists in the build container).
+"""ORACLE helper: import the unmodified reference -- from /root/reference in the build container, else from the byte-for-byte
+copy oracle/build_ref.py shipped as oracle/_ref (the GPU box has no /root/reference).
 
 `src/models/__init__.py` imports `diffusers` and the trainers import `matplotlib`; neither is
 installed, so both are stubbed in sys.modules before importing.  Nothing here is copied from the reference;
@@ -10,11 +11,26 @@ import sys
 import types
 from pathlib import Path
 
-REFERENCE_ROOT = Path("/root/reference")
+_CANDIDATES = (Path("/root/reference"), Path(__file__).resolve().parent / "_ref")
+
+
+def _root():
+    for c in _CANDIDATES:
+        if (c / "src" / "models" / "unet.py").exists():
+            return c
+    return None
+
+
+REFERENCE_ROOT = _root() or _CANDIDATES[0]
 
 
 def available() -> bool:
-    return (REFERENCE_ROOT / "src" / "models" / "unet.py").exists()
+    return _root() is not None
+
+
+def kind() -> str:
+    """'reference' when the unmodified reference can be executed here, else 'port' (callers fall back to oracle/*.py)."""
+    return "reference" if available() else "port"
 
 
 def _stub(name: str, **attrs):
@@ -47,11 +63,12 @@ def install_stubs() -> None:
 def load():
     """Returns a namespace with the reference's UNet, NoiseScheduler (cosine), ImprovedDiffusionTrainer,
     FinalNoiseScheduler (linear) and FinalPokemonGenerator."""
-    if not available():
-        raise RuntimeError("/root/reference is not present on this machine")
+    root = _root()
+    if root is None:
+        raise RuntimeError("neither /root/reference nor oracle/_ref (python -m oracle.build_ref) is present on this machine")
     install_stubs()
-    if str(REFERENCE_ROOT) not in sys.path:
-        sys.path.insert(0, str(REFERENCE_ROOT))
+    if str(root) not in sys.path:
+        sys.path.insert(0, str(root))
     from src.models.unet import UNet  # type: ignore
     from src.training.improved_diffusion_trainer import ImprovedDiffusionTrainer, NoiseScheduler  # type: ignore
     from src.training import final_trainer  # type: ignore

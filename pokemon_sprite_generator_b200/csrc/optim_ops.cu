@@ -55,8 +55,11 @@ sumsq_kernel(const float* __restrict__ x, size_t n, float* __restrict__ partials
   }
 }
 
-// state[0] = total_norm, state[1] = clip coefficient (<= 1), state[2] = 1.0 if finite else 0.0
-__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ state) {
+// state[0] = total_norm, state[1] = clip coefficient (<= 1), state[2] = 1.0 if finite else 0.0,
+// state[3] (when count_steps) = number of APPLIED optimiser steps so far: incremented only for finite gradients, so that
+// Adam's bias correction does not advance over skipped batches (the reference `continue`s before optimizer.step(),
+// src/training/improved_diffusion_trainer.py:395-397)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ state, int count_steps) {
   const float norm = sqrtf(*sumsq);
   const bool finite = isfinite(norm);
   float coef = 1.f;
@@ -64,26 +67,34 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
   state[0] = norm;
   state[1] = finite ? coef : 0.f;
   state[2] = finite ? 1.f : 0.f;
+  if (count_steps && finite) state[3] += 1.f;
 }
 
 __global__ void __launch_bounds__(kThreads)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
              float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
-             const float* __restrict__ state, __nv_bfloat16* __restrict__ shadow) {
+             const float* __restrict__ state, __nv_bfloat16* __restrict__ shadow, int coupled_l2, int step_from_state) {
   float gscale = 1.f;
   if (state != nullptr) {
     if (state[2] == 0.f) return;  // non-finite gradients: skip the whole step (the bf16 shadow stays valid)
     gscale = state[1];
+    if (step_from_state) {        // bias corrections from the device-side count of applied steps (state[3] >= 1 here)
+      const double t = (double)state[3];
+      bc1 = (float)(1.0 - pow((double)beta1, t));
+      bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+    }
   }
   const float step = lr / bc1;
-  const float decay = 1.f - lr * weight_decay;
+  // decoupled (torch.optim.AdamW): p *= 1 - lr*wd;  coupled (torch.optim.Adam(weight_decay=wd)): g += wd * p
+  const float decay = coupled_l2 ? 1.f : 1.f - lr * weight_decay;
+  const float l2 = coupled_l2 ? weight_decay : 0.f;
   const size_t n4 = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
-    gg *= gscale;
+    gg = gg * gscale + l2 * pp;
     pp *= decay;
     mm = beta1 * mm + (1.f - beta1) * gg;
     vv = beta2 * vv + (1.f - beta2) * gg * gg;
@@ -152,28 +163,49 @@ int psg_sumsq(const float* x, long long n, float* out_sumsq, int accumulate, voi
 // state (3 floats on device): total_norm, clip coefficient, finite flag.
 int psg_clip_coef(const float* sumsq, float max_norm, float* state, void* stream) {
   PSG_CHECK_ARG(sumsq && state, "psg_clip_coef: null pointer");
-  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, state);
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, state, 0);
   PSG_CHECK_LAUNCH("psg_clip_coef");
   return PSG_OK;
 }
 
-// torch.optim.AdamW (no amsgrad) over flat buffers; `step` is the 1-based step count (bias corrections computed
-// on the host in double, as PyTorch does); state may be null (no clipping / skipping).
-int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, long long step, const float* state, void* bf16_shadow, void* stream) {
-  PSG_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "psg_adamw_step: bad args");
+// Same, and state[3] (a 4th float) counts the steps that will actually be applied (finite gradients only).
+int psg_clip_coef_count(const float* sumsq, float max_norm, float* state4, void* stream) {
+  PSG_CHECK_ARG(sumsq && state4, "psg_clip_coef_count: null pointer");
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, state4, 1);
+  PSG_CHECK_LAUNCH("psg_clip_coef_count");
+  return PSG_OK;
+}
+
+// torch.optim.AdamW / torch.optim.Adam (no amsgrad) over flat buffers.  `step` is the 1-based step count (bias corrections
+// computed on the host in double, as PyTorch does); step <= 0: take the count of applied steps from state[3] (see
+// psg_clip_coef_count).  coupled_l2 = 0: decoupled decay (AdamW, improved_diffusion_trainer.py:277-283);
+// 1: L2 added to the gradient (the reference's `else` branch, torch.optim.Adam(weight_decay=...), :285-292).
+// state may be null (no clipping / skipping).
+int psg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, long long step, int coupled_l2, const float* state, void* bf16_shadow, void* stream) {
+  PSG_CHECK_ARG(p && g && m && v && n > 0, "psg_adam_step: bad args");
+  PSG_CHECK_ARG(step >= 1 || state != nullptr, "psg_adam_step: step <= 0 needs the device state (applied-step counter)");
   PSG_CHECK_ARG(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0),
-                "psg_adamw_step: buffers must be 16B aligned");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+                "psg_adam_step: buffers must be 16B aligned");
+  PSG_CHECK_ARG(bf16_shadow == nullptr || (uintptr_t)bf16_shadow % 8 == 0, "psg_adam_step: shadow must be 8B aligned");
+  const double st = step >= 1 ? (double)step : 1.0;
+  const double bc1 = 1.0 - pow((double)beta1, st);
+  const double bc2 = 1.0 - pow((double)beta2, st);
   long long g_ = (n / 4 + kThreads - 1) / kThreads;
   long long cap = (long long)psg_num_sms() * 16;
   if (g_ > cap) g_ = cap;
   if (g_ < 1) g_ = 1;
   adamw_kernel<<<(int)g_, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                              (float)sqrt(bc2), state, (__nv_bfloat16*)bf16_shadow);
-  PSG_CHECK_LAUNCH("psg_adamw_step");
+                                                              (float)sqrt(bc2), state, (__nv_bfloat16*)bf16_shadow, coupled_l2 ? 1 : 0,
+                                                              step >= 1 ? 0 : 1);
+  PSG_CHECK_LAUNCH("psg_adam_step");
   return PSG_OK;
+}
+
+int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, long long step, const float* state, void* bf16_shadow, void* stream) {
+  PSG_CHECK_ARG(step >= 1, "psg_adamw_step: step must be >= 1");
+  return psg_adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, 0, state, bf16_shadow, stream);
 }
 
 // y = bf16(x): refreshes the bf16 shadow of the flat parameter buffer after the parameters changed outside psg_adamw_step.

@@ -246,7 +246,11 @@ class UNetEngine:
         self.step_counter = 0
         self.dropout_enabled = True      # honoured only in train() mode
         self.cond_on_tensor_cores = True  # bf16 mode: all-blocks conditioning GEMMs on the tcgen05 engine (see _cond_all)
-        self.seed = 0x5EED
+        # Dropout RNG contract: masks are a stateless hash of (seed, step_counter, site, element).  `seed` defaults (lazily, at
+        # the first forward) to torch.initial_seed() mixed with the data-parallel rank, so torch.manual_seed(...) selects the
+        # mask sequence and replicas draw different masks; `step_counter` advances once per forward and is restored from
+        # `global_step` by DiffusionTrainer.load_checkpoint, so a resumed run continues the sequence instead of replaying it.
+        self.seed = None
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------------------------
@@ -442,6 +446,15 @@ class UNetEngine:
         return "umma" if (t.dtype == torch.bfloat16 and not edge) else "simt"
 
     def _seed(self, site: int) -> int:
+        if self.seed is None:
+            rank = 0
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    rank = dist.get_rank()
+            except Exception:  # pragma: no cover
+                rank = 0
+            self.seed = (torch.initial_seed() ^ (rank * 0x9E3779B97F4A7C15) ^ 0x5EED) & 0xFFFFFFFFFFFFFFFF
         return ((self.seed * 0x9E3779B1 + self.step_counter) * 0x85EBCA77 + site * 0xC2B2AE3D) & 0xFFFFFFFFFFFFFFFF
 
     # ---- convolution -------------------------------------------------------------------------------------------

@@ -279,16 +279,23 @@ def sumsq(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False) -> None:
     L.call("psg_sumsq", L.ptr(x), C.c_longlong(x.numel()), L.ptr(out), C.c_int(int(accumulate)), L.ptr(ws), L.stream_ptr())
 
 
-def clip_coef(sumsq_t: torch.Tensor, max_norm: float, state: torch.Tensor) -> None:
-    L.call("psg_clip_coef", L.ptr(sumsq_t), C.c_float(max_norm), L.ptr(state), L.stream_ptr())
+def clip_coef(sumsq_t: torch.Tensor, max_norm: float, state: torch.Tensor, count_steps: bool = False) -> None:
+    """state[0..2] = total norm, clip coefficient, finite flag; count_steps: state[3] += 1 when the step will be applied."""
+    if count_steps:
+        assert state.numel() >= 4
+        L.call("psg_clip_coef_count", L.ptr(sumsq_t), C.c_float(max_norm), L.ptr(state), L.stream_ptr())
+    else:
+        L.call("psg_clip_coef", L.ptr(sumsq_t), C.c_float(max_norm), L.ptr(state), L.stream_ptr())
 
 
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step: int, state: torch.Tensor | None,
-               shadow: torch.Tensor | None = None) -> None:
-    """shadow: optional bf16 buffer of p's size, rewritten with the updated parameters (what the tensor-core GEMMs read)."""
+               shadow: torch.Tensor | None = None, coupled_l2: bool = False) -> None:
+    """shadow: optional bf16 buffer of p's size, rewritten with the updated parameters (what the tensor-core GEMMs read).
+    step <= 0: bias corrections from the device-side applied-step counter state[3].  coupled_l2: torch.optim.Adam decay."""
     assert shadow is None or (shadow.dtype == torch.bfloat16 and shadow.numel() == p.numel())
-    L.call("psg_adamw_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), C.c_longlong(p.numel()), C.c_float(lr), C.c_float(beta1),
-           C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), L.ptr(state), L.ptr(shadow), L.stream_ptr())
+    L.call("psg_adam_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), C.c_longlong(p.numel()), C.c_float(lr), C.c_float(beta1),
+           C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), C.c_int(int(coupled_l2)), L.ptr(state),
+           L.ptr(shadow), L.stream_ptr())
 
 
 def cast_bf16(x: torch.Tensor, y: torch.Tensor) -> None:

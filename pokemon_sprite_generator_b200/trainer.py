@@ -34,10 +34,17 @@ from .unet import UNet
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    """torch.optim.AdamW semantics (decoupled weight decay, bias correction, eps outside the sqrt) as ONE kernel over
-    the U-Net's flat parameter / gradient buffers, fused with the global-norm clip coefficient and the
-    skip-on-non-finite predicate.  Exposes param_groups / state_dict like a torch optimizer so LR schedulers
-    (OneCycleLR, which also cycles beta1) and checkpoints keep working."""
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction, eps outside the sqrt) -- or, with
+    `adamw=False`, torch.optim.Adam's coupled L2 decay (the reference's `else` branch, improved_diffusion_trainer.py:285-292)
+    -- as ONE kernel over the U-Net's flat parameter / gradient buffers, fused with the global-norm clip coefficient and the
+    skip-on-non-finite predicate.  Exposes param_groups / state_dict like a torch optimizer so LR schedulers (OneCycleLR,
+    which also cycles beta1) and checkpoints keep working: `state[p]['exp_avg' / 'exp_avg_sq']` are views of the flat
+    moment buffers with the parameter's LOGICAL layout (tap-major conv weights through the same permute as the
+    parameter itself), so a reference `torch.optim.AdamW` state_dict loads and exports element for element.
+
+    Step counting: the device keeps the number of APPLIED steps (`clip_state[3]`, incremented only for finite gradients)
+    and the kernel derives Adam's bias corrections from it, so a skipped batch does not advance them -- the reference
+    `continue`s before `optimizer.step()` (:395-397).  `applied_steps()` reads it back (one sync; used by state_dict)."""
 
     def __init__(self, unet: UNet, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-4, max_grad_norm: float = 0.0,
                  adamw: bool = True):
@@ -48,8 +55,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self.decoupled = adamw
         self._m = self._v = None
         self._sumsq = None
-        self.clip_state = None      # device [3]: total_norm, clip coefficient, finite flag
-        self.step_count = 0
+        self.clip_state = None      # device [4]: total_norm, clip coefficient, finite flag, applied steps
+        self.step_count = 0         # step() calls issued (host side); see applied_steps() for the device-side truth
+        self._applied0 = 0          # applied steps to seed the device counter with when the state is (re)built
 
     def _ensure_state(self):
         eng = self.unet.engine()
@@ -64,12 +72,19 @@ class FusedAdamW(torch.optim.Optimizer):
             self._m = torch.zeros(store.total, dtype=torch.float32, device=dev)
             self._v = torch.zeros(store.total, dtype=torch.float32, device=dev)
             self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
-            self.clip_state = torch.zeros(3, dtype=torch.float32, device=dev)
+            self.clip_state = torch.zeros(4, dtype=torch.float32, device=dev)
+            self.clip_state[3] = float(self._applied0)
             for name, p in store.named:
-                off, n = store.offsets[name], p.numel()
-                self.state[p] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self._m[off:off + n].view(p.shape),
-                                 "exp_avg_sq": self._v[off:off + n].view(p.shape)}
+                off = store.offsets[name]
+                self.state[p] = {"step": torch.tensor(float(self._applied0)), "exp_avg": store._view(self._m, p, off),
+                                 "exp_avg_sq": store._view(self._v, p, off)}
         return store
+
+    def applied_steps(self) -> int:
+        """Number of optimiser steps actually applied (non-finite batches are skipped on the device).  Synchronises."""
+        if self.clip_state is None:
+            return self._applied0
+        return int(round(float(self.clip_state[3].item())))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -78,12 +93,9 @@ class FusedAdamW(torch.optim.Optimizer):
         g = self.param_groups[0]
         self.step_count += 1
         K.sumsq(store.grads, self._sumsq)
-        K.clip_coef(self._sumsq, float(self.max_grad_norm or 0.0), self.clip_state)
-        wd = g["weight_decay"]
-        if not self.decoupled and wd != 0.0:
-            raise L.PsgError("FusedAdamW: coupled (Adam-style) weight decay is not implemented; use adamw=True")
-        K.adamw_step(store.flat, store.grads, self._m, self._v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], wd,
-                     self.step_count, self.clip_state, shadow=store.shadow)
+        K.clip_coef(self._sumsq, float(self.max_grad_norm or 0.0), self.clip_state, count_steps=True)
+        K.adamw_step(store.flat, store.grads, self._m, self._v, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
+                     0, self.clip_state, shadow=store.shadow, coupled_l2=not self.decoupled)
         if store.shadow is not None:
             eng.mark_shadow_fresh()     # the kernel rewrote the bf16 shadow the GEMMs read
         else:
@@ -96,26 +108,36 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def state_dict(self):
         self._ensure_state()
+        n = float(self.applied_steps())
         for st in self.state.values():
-            st["step"] = torch.tensor(float(self.step_count))
+            st["step"] = torch.tensor(n)
         return super().state_dict()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
-        # torch replaced the per-parameter state tensors: fold them back into the flat buffers
-        store = self.unet.engine().store
+        # torch replaced the per-parameter state tensors: fold them back into the flat buffers (element for element in the
+        # parameter's logical layout -- the views permute tap-major conv weights exactly like the parameter view does)
         old = {p: dict(st) for p, st in self.state.items()}
+        steps = [int(float(st["step"])) for st in old.values() if "step" in st]
+        self._applied0 = max(steps) if steps else 0
+        self.step_count = self._applied0
         self._m = None
         self._ensure_state()
         for p, st in old.items():
             if "exp_avg" in st:
                 self.state[p]["exp_avg"].copy_(st["exp_avg"])
                 self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
-                self.step_count = int(float(st.get("step", self.step_count)))
 
 
 class TrainStep:
-    """One data-parallel optimisation step on device-resident tensors (the unit bench.py times)."""
+    """One data-parallel optimisation step on device-resident tensors (the unit bench.py times).
+
+    Data parallel (world > 1): rank 0's parameters and optimiser moments are broadcast once at construction, so replicas
+    start identical whatever each rank's RNG state was at `UNet()` time; from then on identical averaged gradients keep
+    them identical.  Skipped (non-finite) batches: the device skips the update and does not count the step; the host LR
+    scheduler learns about it one step late through an asynchronous copy of the finite flag (no synchronisation inside the
+    step) and then holds the schedule back by one tick, so schedule position == applied steps again from the next step on
+    (the reference `continue`s before `scheduler.step()`, improved_diffusion_trainer.py:395-397,413)."""
 
     def __init__(self, unet: UNet, noise_scheduler: NoiseScheduler, optimizer: FusedAdamW, lr_scheduler=None, beta: float = 0.1,
                  clamp: float = 3.0, process_group=None):
@@ -127,12 +149,35 @@ class TrainStep:
         # overlap="backward": bucketed all-reduce issued from inside backward (parallel.GradSync); "none": after backward
         self.overlap = os.environ.get("PSG_GRAD_OVERLAP", "backward")
         self.grad_sync = None
+        self._flag_host = None      # pinned copy of the previous step's finite flag + the event that says it has landed
+        self._flag_event = None
+        self.skipped_steps = 0
         if self.world > 1 and self.overlap == "backward":
             reserve = int(os.environ.get("PSG_COMM_SMS", os.environ.get("NCCL_MAX_CTAS", "16")))
             lib = L.load()
             self.grad_sync = GradSync(process_group, bucket_bytes=int(os.environ.get("PSG_BUCKET_MB", "128")) << 20,
                                       reserve_sms=reserve, reserve_hook=lambda n: lib.psg_umma_reserve_sms(int(n)), prescaled=True,
                                       window_entries=int(os.environ.get("PSG_COMM_WINDOW", "4")))
+        if self.world > 1:
+            self.sync_replicas()
+
+    def sync_replicas(self, src: int = 0) -> None:
+        """Broadcast rank `src`'s flat parameters and AdamW state to every replica (start-up / after load_checkpoint)."""
+        dev = next(self.unet.parameters()).device
+        if dev.type != "cuda":
+            return      # the U-Net has not been moved to its GPU yet; the owner calls sync_replicas() once it has
+        eng = self.unet.engine()
+        eng.prepare(dev)
+        store = self.opt._ensure_state()
+        for buf in (store.flat, self.opt._m, self.opt._v, self.opt.clip_state):
+            dist.broadcast(buf, src=src, group=self.pg)
+        eng.mark_params_dirty()
+
+    def _previous_step_was_skipped(self) -> bool:
+        if self._flag_event is None:
+            return False
+        self._flag_event.synchronize()      # recorded a whole step ago: never waits in steady state
+        return float(self._flag_host[0]) == 0.0
 
     def __call__(self, latent: torch.Tensor, text_emb: torch.Tensor, timesteps: Optional[torch.Tensor] = None,
                  noise: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -153,8 +198,16 @@ class TrainStep:
             eng.backward(ctx, dpred)
             if self.world > 1:
                 allreduce_mean_(eng.store.grads, group=self.pg, prescaled=True, buckets=self.buckets)
+        skipped_before = self._previous_step_was_skipped()
         self.opt.step()
-        if self.lr_sched is not None:
+        if self._flag_host is None:
+            self._flag_host = torch.ones(1, dtype=torch.float32).pin_memory()
+            self._flag_event = torch.cuda.Event()
+        self._flag_host.copy_(self.opt.clip_state[2:3], non_blocking=True)
+        self._flag_event.record()
+        if skipped_before:
+            self.skipped_steps += 1
+        elif self.lr_sched is not None:
             self.lr_sched.step()
         return loss
 
@@ -239,9 +292,11 @@ class DiffusionTrainer:
                     p.requires_grad = False
                 m.eval()
             self.vae_encoder, self.vae_decoder = enc, dec
-        self.unet = UNet(latent_dim=mc.get("latent_dim", 8), text_dim=mc.get("text_embedding_dim", 256),
-                         time_emb_dim=mc.get("time_emb_dim", 128), num_heads=mc.get("num_heads", 4),
-                         compute_dtype=self.compute_dtype).to(self.device)
+        self.unet = self.components.get("unet")         # an already-built (e.g. warmed-up) drop-in U-Net may be injected
+        if self.unet is None:
+            self.unet = UNet(latent_dim=mc.get("latent_dim", 8), text_dim=mc.get("text_embedding_dim", 256),
+                             time_emb_dim=mc.get("time_emb_dim", 128), num_heads=mc.get("num_heads", 4),
+                             compute_dtype=self.compute_dtype).to(self.device)
         self.noise_scheduler = NoiseScheduler(num_timesteps=mc.get("num_timesteps", 1000), beta_start=mc.get("beta_start", 0.0001),
                                               beta_end=mc.get("beta_end", 0.02))
         self.logger.info(f"U-Net initialized with {sum(p.numel() for p in self.unet.parameters())} parameters")
@@ -265,6 +320,11 @@ class DiffusionTrainer:
         lr = get("learning_rate", 1e-4)
         self.max_grad_norm = get("max_grad_norm", 0.7)
         opt_type = get("optimizer", "adamw")
+        self.scheduler_config = {"type": get("scheduler", "cosine"), "lr": lr}
+        self.criterion = SmoothL1Loss(beta=0.1)
+        if "optimizer" in self.components:
+            self.optimizer = self.components["optimizer"]
+            return
         self.optimizer = FusedAdamW(self.unet, lr=lr, betas=(get("beta1", 0.9), get("beta2", 0.999)), eps=1e-6,
                                     weight_decay=get("weight_decay", 1e-4), max_grad_norm=self.max_grad_norm,
                                     adamw=(opt_type == "adamw"))
@@ -273,13 +333,17 @@ class DiffusionTrainer:
 
     def setup_scheduler(self):
         lr = self.scheduler_config["lr"]
-        if self.scheduler_config["type"] == "cosine":
+        if "lr_scheduler" in self.components:
+            self.scheduler = self.components["lr_scheduler"]
+        elif self.scheduler_config["type"] == "cosine":
             total = self.config.get("training", {}).get("diffusion_epochs", 1) * max(1, len(self.data_loaders["train"]))
             self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, max_lr=lr, total_steps=total, pct_start=0.1,
                                                                  anneal_strategy="cos")
         else:
             self.scheduler = torch.optim.lr_scheduler.ConstantLR(self.optimizer, factor=1.0)
-        self._step = TrainStep(self.unet, self.noise_scheduler, self.optimizer, self.scheduler)
+        self._step = self.components.get("train_step") or TrainStep(self.unet, self.noise_scheduler, self.optimizer, self.scheduler)
+        self.world = self._step.world
+        self.rank = dist.get_rank() if self.world > 1 else 0
 
     def setup_monitoring(self):
         try:
@@ -310,6 +374,8 @@ class DiffusionTrainer:
         losses = []
         log_every = self.config.get("training", {}).get("log_every", 50)
         for batch_idx, batch in enumerate(self.data_loaders["train"]):
+            if self.world > 1 and not self.config.get("data", {}).get("presharded", False) and batch_idx % self.world != self.rank:
+                continue        # data parallel over an unsharded (reference) loader: rank r takes batches r, r + world, ...
             latent, text_emb = self._encode(batch)
             loss = self._step(latent, text_emb)
             losses.append(loss)
@@ -331,13 +397,19 @@ class DiffusionTrainer:
         return {"train_loss": avg}
 
     @torch.no_grad()
-    def validate_epoch(self, epoch: int) -> Dict[str, float]:
+    def validate_epoch(self, epoch: int, draws: Optional[Callable[[torch.Tensor], tuple]] = None) -> Dict[str, float]:
+        """reference :447-506.  `draws(latent) -> (timesteps, noise)` overrides the per-batch random draws (parity tests
+        inject the tensors the oracle uses); by default they come from the device generator in the reference's order."""
         self.unet.eval()
         losses = []
         for batch in self.data_loaders["val"]:
             latent, text_emb = self._encode(batch)
-            t = torch.randint(0, self.noise_scheduler.num_timesteps, (latent.shape[0],), device=self.device)
-            noise = torch.randn_like(latent)
+            if draws is not None:
+                t, noise = draws(latent)
+                t, noise = t.to(self.device), noise.to(self.device)
+            else:
+                t = torch.randint(0, self.noise_scheduler.num_timesteps, (latent.shape[0],), device=self.device)
+                noise = torch.randn_like(latent)
             noisy = self.noise_scheduler.add_noise(latent, noise, t, clamp=3.0)
             pred = self.unet(noisy, t, text_emb)
             loss, _ = smooth_l1_fwd_bwd(pred, noise, beta=0.1, want_grad=False)
@@ -387,7 +459,7 @@ class DiffusionTrainer:
                 "unet_state_dict": {k: v.detach().clone() for k, v in self.unet.state_dict().items()},
                 "optimizer_state_dict": self.optimizer.state_dict(), "scheduler_state_dict": self.scheduler.state_dict(),
                 "best_val_loss": self.best_val_loss, "config": self.config}
-        if is_best:
+        if is_best and self.rank == 0:      # replicas are identical: one writer
             torch.save(ckpt, self.checkpoint_dir / "diffusion_best_model.pth")
             self.logger.info(f"New best model saved at epoch {epoch}")
 
@@ -400,6 +472,7 @@ class DiffusionTrainer:
         self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
         if self.scheduler and ckpt.get("scheduler_state_dict"):
             self.scheduler.load_state_dict(ckpt["scheduler_state_dict"])
+        self.unet.engine().step_counter = int(self.global_step)      # dropout masks continue where the saved run stopped
         self.logger.info(f"Checkpoint loaded from {checkpoint_path}")
 
     def train(self):

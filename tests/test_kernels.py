@@ -302,6 +302,39 @@ def test_optimizer_kernels(cuda_device):
     assert torch.equal(mine, before) and state[2].item() == 0.0
 
 
+def test_adam_coupled_decay_and_device_step_counter(cuda_device):
+    """psg_adam_step: coupled L2 decay == torch.optim.Adam(weight_decay) (reference improved_diffusion_trainer.py:285-292), and
+    bias corrections taken from the device-side applied-step counter (psg_clip_coef_count) skip non-finite steps."""
+    K = _ops()
+    n = 300_001
+    g = torch.Generator(device="cuda").manual_seed(2)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    grad = torch.randn(n, device="cuda", generator=g) * 0.1
+    for coupled, cls in ((True, torch.optim.Adam), (False, torch.optim.AdamW)):
+        pr = torch.nn.Parameter(p0.clone())
+        opt = cls([pr], lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-2)
+        m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+        mine = p0.clone()
+        ss = torch.zeros(1, device="cuda")
+        state = torch.zeros(4, device="cuda")
+        for step in range(1, 5):
+            gstep = grad * step
+            if step == 3:       # a non-finite batch in the middle: skipped by both sides, and not counted
+                bad = gstep.clone(); bad[7] = float("inf")
+                K.sumsq(bad, ss); K.clip_coef(ss, 0.7, state, count_steps=True)
+                K.adamw_step(mine, bad, m, v, 1e-3, 0.9, 0.999, 1e-6, 1e-2, 0, state, coupled_l2=coupled)
+                assert state[2].item() == 0.0 and state[3].item() == 2.0
+                continue
+            pr.grad = gstep.clone()
+            torch.nn.utils.clip_grad_norm_([pr], 0.7)
+            opt.step()
+            K.sumsq(gstep, ss)
+            K.clip_coef(ss, 0.7, state, count_steps=True)
+            K.adamw_step(mine, gstep, m, v, 1e-3, 0.9, 0.999, 1e-6, 1e-2, 0, state, coupled_l2=coupled)
+        assert state[3].item() == 3.0
+        assert torch.allclose(mine, pr.data, rtol=1e-5, atol=1e-6), (coupled, (mine - pr.data).abs().max())
+
+
 @pytest.mark.parametrize("B,H,Lq,Lk,hd,p", [(2, 8, 196, 196, 80, 0.0), (2, 4, 196, 32, 160, 0.0), (3, 8, 49, 49, 160, 0.0), (2, 4, 16, 7, 320, 0.0),
                                             (1, 8, 196, 256, 80, 0.0), (2, 4, 16, 16, 320, 0.0), (2, 8, 49, 32, 160, 0.25), (3, 4, 196, 77, 160, 0.1)])
 def test_attention_tensor_core(cuda_device, B, H, Lq, Lk, hd, p):

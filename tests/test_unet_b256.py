@@ -1,0 +1,84 @@
+"""Parity AT THE BENCHMARK SHAPE (BASELINE config 2: batch 256, heads 4, 32 text tokens) against a golden produced by
+executing the unmodified reference at that shape (oracle/make_golden.py --b256: loss, per-parameter gradient norms,
+gradient samples and a strided sample of the noise prediction).  At this batch the GEMM planner picks the 256-row CTA-pair
+tiles, stream-K remainders, aligned split-K wgrad and multi-CTA GroupNorm clusters that the small-batch goldens never
+reach, so this is the one reference-pinned point on the configuration bench.py times.
+"""
+from pathlib import Path
+
+import pytest
+import torch
+
+from conftest import record_metric
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden" / "unet_b256.pt"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    if not GOLD.exists():
+        pytest.skip("tests/golden/unet_b256.pt not generated (python -m oracle.make_golden --b256)")
+    return torch.load(GOLD)
+
+
+# bounds: (output max-abs / scale, loss rel, total grad norm rel, worst per-parameter grad-norm rel, worst grad sample rel)
+# fp32 rows are bounded by the reference's OWN fp32 CPU accuracy at this batch (oneDNN weight-gradients)
+BOUNDS = {
+    ("init", "fp32"): (1e-4, 1e-5, 2e-3, 2e-2, 2e-2),
+    ("init", "bf16"): (2e-2, 1e-2, 3e-2, 0.15, 0.2),
+    ("amp", "fp32"): (1e-4, 1e-5, 2e-3, 2e-2, 2e-2),
+    ("amp", "bf16"): (4e-2, 1e-2, 3e-2, 0.15, 0.2),
+}
+
+
+@pytest.mark.parametrize("case_name", ["init", "amp"])
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_b256_matches_reference(cuda_device, gold, case_name, mode):
+    from oracle import inputs
+    from pokemon_sprite_generator_b200.losses import SmoothL1Loss
+    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
+    from pokemon_sprite_generator_b200.unet import UNet
+    if case_name not in gold["cases"]:
+        pytest.skip(f"golden case {case_name} not generated")
+    case = gold["cases"][case_name]
+    B, stride = gold["batch"], gold["stride"]
+    torch.manual_seed(0)
+    m = UNet(num_heads=gold["heads"], compute_dtype=torch.float32 if mode == "fp32" else torch.bfloat16)
+    if case_name == "amp":
+        m.load_state_dict(inputs.amplify_state_dict({k: v.detach().clone() for k, v in m.state_dict().items()}))
+    m = m.to(cuda_device).eval()
+    latent, text, t, noise = (a.to(cuda_device) for a in inputs.make_inputs(B, gold["text_len"], gold["seed"]))
+    noisy = NoiseScheduler().add_noise(latent, noise, t)
+    pred = m(noisy, t, text)
+    loss = SmoothL1Loss(beta=0.1)(pred, noise)
+    loss.backward()
+    b_out, b_loss, b_tot, b_norm, b_samp = BOUNDS[(case_name, mode)]
+    y = pred.detach().cpu()
+    scale = max(case["output_absmax"], 1.0) if case_name == "amp" else 1.0
+    e_out = max((y.flatten()[::stride] - case["output_strided"]).abs().max().item(),
+                (y[0] - case["output_first"]).abs().max().item(), (y[-1] - case["output_last"]).abs().max().item())
+    e_loss = abs(loss.item() - case["loss"]) / case["loss"]
+    named = dict(m.named_parameters())
+    tot = torch.sqrt(sum(p.grad.double().pow(2).sum() for p in m.parameters())).item()
+    e_tot = abs(tot - case["grad_total_norm"]) / case["grad_total_norm"]
+    per = {k: abs(named[k].grad.norm().item() - n) / (n + 1e-12) for k, n in case["grad_norms"].items()}
+    worst_key = max(per, key=per.get)
+    e_samp, samp_key = 0.0, None
+    for k in inputs.GRAD_KEYS:
+        g = named[k].grad.flatten()
+        samp = g[:: max(1, g.numel() // 64)][:64].cpu()
+        ref = case["grad_samples"][k]
+        e = (samp - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
+        if e > e_samp:
+            e_samp, samp_key = e, k
+    print(f"[b256 {case_name} {mode}] out err {e_out:.3e} (scale {scale:.3f}, ref absmax {case['output_absmax']:.3f}) loss {loss.item():.6f} vs "
+          f"{case['loss']:.6f} (rel {e_loss:.2e}) total-grad-norm rel {e_tot:.2e} worst per-param norm rel {per[worst_key]:.3e} ({worst_key}) "
+          f"worst grad sample rel {e_samp:.3e} ({samp_key})")
+    record_metric(f"b256_{case_name}_{mode}", out_err=e_out, scale=scale, loss_rel=e_loss, grad_total_rel=e_tot,
+                  grad_norm_worst=per[worst_key], grad_norm_worst_key=worst_key, grad_sample_worst=e_samp, grad_sample_key=samp_key)
+    assert e_out <= b_out * scale
+    assert e_loss <= b_loss
+    assert e_tot <= b_tot
+    assert per[worst_key] <= b_norm, worst_key
+    assert e_samp <= b_samp, samp_key

@@ -10,6 +10,8 @@ from pathlib import Path
 import pytest
 import torch
 
+from conftest import record_metric
+
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
 
@@ -48,29 +50,48 @@ def _inputs(case, dev):
     return noisy, text, t, noise
 
 
-def _check_grads(m, case, mode):
+# bf16 gradient bounds = 2x the worst figure measured on B200 over all golden cases (profiles/r02_parity_metrics.jsonl)
+BF16_GRAD_NORM_BOUND = 0.15
+BF16_GRAD_SAMPLE_BOUND = 0.2
+BF16_GRAD_TOTAL_BOUND = 3e-2
+
+
+def _check_grads(m, case, mode, tag=""):
     """Per-parameter gradient parity.  Two oracles: the reference's own fp32 CPU run (whose conv weight-gradients on the
     deep levels are only good to ~3e-3 of a parameter's grad norm) and, where recorded, an fp64 run of the same reference
     module, which pins the exact values: the fp32 CUDA mode must sit on the fp64 numbers."""
     from oracle import inputs
     named = dict(m.named_parameters())
-    worst32 = max(abs(named[k].grad.norm().item() - n) / (n + 1e-12) for k, n in case["grad_norms"].items())
-    print(f"[{mode}] worst per-parameter grad-norm rel err vs reference fp32 = {worst32:.3e}")
-    assert worst32 <= (5e-3 if mode == "fp32" else 0.15)
+    per32 = {k: abs(named[k].grad.norm().item() - n) / (n + 1e-12) for k, n in case["grad_norms"].items()}
+    k32 = max(per32, key=per32.get)
+    worst32 = per32[k32]
+    print(f"[{mode}] worst per-parameter grad-norm rel err vs reference fp32 = {worst32:.3e} ({k32})")
     tot = torch.sqrt(sum(p.grad.double().pow(2).sum() for p in m.parameters())).item()
-    assert abs(tot - case["grad_total_norm"]) / case["grad_total_norm"] <= (2e-4 if mode == "fp32" else 3e-2)
+    e_tot = abs(tot - case["grad_total_norm"]) / case["grad_total_norm"]
     samples, norms = case["grad_samples"], None
+    worst64 = k64 = None
     if "grad_norms_fp64" in case:
         norms, samples = case["grad_norms_fp64"], case["grad_samples_fp64"]
-        worst64 = max(abs(named[k].grad.norm().item() - n) / (n + 1e-12) for k, n in norms.items())
-        print(f"[{mode}] worst per-parameter grad-norm rel err vs reference fp64 = {worst64:.3e}")
-        assert worst64 <= (5e-5 if mode == "fp32" else 0.15)
+        per64 = {k: abs(named[k].grad.norm().item() - n) / (n + 1e-12) for k, n in norms.items()}
+        k64 = max(per64, key=per64.get)
+        worst64 = per64[k64]
+        print(f"[{mode}] worst per-parameter grad-norm rel err vs reference fp64 = {worst64:.3e} ({k64})")
+    e_samp, k_samp = 0.0, None
     for k in inputs.GRAD_KEYS:
         g = named[k].grad.flatten()
         samp = g[:: max(1, g.numel() // 64)][:64].cpu()
         ref = samples[k]
         e = (samp - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
-        assert e <= ((2e-4 if norms is not None else 2e-3) if mode == "fp32" else 0.2), (k, e)
+        if e > e_samp:
+            e_samp, k_samp = e, k
+    print(f"[{mode}] total grad norm rel err {e_tot:.3e}; worst gradient sample rel err {e_samp:.3e} ({k_samp})")
+    record_metric(f"grads_{tag}_{mode}", grad_norm_worst_fp32ref=worst32, key32=k32, grad_norm_worst_fp64ref=worst64, key64=k64,
+                  grad_total_rel=e_tot, grad_sample_worst=e_samp, grad_sample_key=k_samp)
+    assert worst32 <= (5e-3 if mode == "fp32" else BF16_GRAD_NORM_BOUND), k32
+    assert e_tot <= (2e-4 if mode == "fp32" else BF16_GRAD_TOTAL_BOUND)
+    if worst64 is not None:
+        assert worst64 <= (5e-5 if mode == "fp32" else BF16_GRAD_NORM_BOUND), k64
+    assert e_samp <= ((2e-4 if norms is not None else 2e-3) if mode == "fp32" else BF16_GRAD_SAMPLE_BOUND), (k_samp, e_samp)
 
 
 def _load(m, state):
@@ -91,6 +112,7 @@ def test_forward_matches_reference(cuda_device, gold, unets, base_state, case_na
     assert y.shape == noisy.shape and y.dtype == torch.float32 and y.is_contiguous()
     err = (y.cpu() - case["output"]).abs().max().item()
     print(f"[{case_name} {mode}] max_abs_err={err:.3e} (ref std {case['output'].std():.3e})")
+    record_metric(f"fwd_{case_name}_{mode}", out_err=err, ref_std=float(case["output"].std()))
     assert err <= tol
     if mode == "fp32":
         assert err <= 5e-6, "fp32 mode should sit at accumulation-order noise"
@@ -110,7 +132,7 @@ def test_loss_and_gradients_match_reference(cuda_device, gold, unets, base_state
     rel = abs(loss.item() - case["loss"]) / case["loss"]
     print(f"[{mode}] loss={loss.item():.6f} ref={case['loss']:.6f} rel={rel:.2e}")
     assert rel <= (1e-5 if mode == "fp32" else 1e-2)
-    _check_grads(m, case, mode)
+    _check_grads(m, case, mode, "init_h8_b2_l32")
 
 
 @pytest.mark.parametrize("case_name", ["amp_h8_b2_l32", "amp_h4_b2_l32"])
@@ -133,7 +155,8 @@ def test_amplified_init_forward_backward(cuda_device, gold, unets, base_state, c
     print(f"[{case_name} {mode}] out err={err:.3e} / scale {scale:.3f}; loss {loss.item():.6f} vs {case['loss']:.6f}")
     assert err <= (2e-5 if mode == "fp32" else 4e-2) * scale
     assert abs(loss.item() - case["loss"]) / case["loss"] <= (1e-5 if mode == "fp32" else 1e-2)
-    _check_grads(m, case, mode)
+    record_metric(f"fwd_{case_name}_{mode}", out_err=err, scale=scale, loss_rel=abs(loss.item() - case["loss"]) / case["loss"])
+    _check_grads(m, case, mode, case_name)
 
 
 def test_module_contract(cuda_device, unets, base_state):

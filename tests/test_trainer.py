@@ -9,7 +9,7 @@ import torch
 from conftest import record_metric
 
 pytestmark = pytest.mark.gpu
-UPDATE_REL_BOUND = 0.05     # 2x the measured figure (profiles/r02_parity_metrics.jsonl)
+UPDATE_REL_BOUND = 3e-4     # measured 1.1e-4 / 1.2e-4 (profiles/r02_parity_metrics.jsonl); round 1 allowed 5e-2
 
 
 def _reference_steps(sd0, emb_coeff, latent, text, ts, noises, lrs, heads, coupled=False):
@@ -79,9 +79,9 @@ def test_train_step_matches_reference_algorithm(cuda_device, coupled):
     assert opt.applied_steps() == steps
     ref_losses, ref_norms, ref_params = _reference_steps(sd0, emb_coeff, latent, text, ts, noises, lrs, heads, coupled)
     for a, b in zip(losses, ref_losses):
-        assert abs(a - b) <= 2e-4 * abs(b), (losses, ref_losses)
+        assert abs(a - b) <= 2e-6 * abs(b), (losses, ref_losses)    # measured 5e-7
     for a, b in zip(norms, ref_norms):
-        assert abs(a - b) <= 5e-3 * abs(b), (norms, ref_norms)
+        assert abs(a - b) <= 1e-3 * abs(b), (norms, ref_norms)      # measured 3.8e-4 (the reference's own fp32 CPU wgrad accuracy)
     # parameter updates: compared as one vector over the whole model (Adam's g / (sqrt(v) + eps) amplifies fp32 noise on the
     # few entries whose gradient is near eps, so the bound is on the update's direction and size, not element by element)
     num = den = dot = n_ours = 0.0
@@ -196,7 +196,8 @@ def test_reference_adamw_state_dict_loads_element_for_element(cuda_device):
         d = (p.detach() - r.detach()).abs().max().item()
         worst = max(worst, d)
         assert d <= 2e-6, (names[i], d)      # lr 1e-3 * O(1) update, fp32 rounding of the fused vs foreach formulation
-        assert torch.allclose(opt.state[p]["exp_avg"], ref_opt.state[r]["exp_avg"], rtol=1e-5, atol=1e-9), names[i]
+        assert torch.allclose(opt.state[p]["exp_avg"], ref_opt.state[r]["exp_avg"], rtol=1e-5, atol=1e-8), names[i]
+        assert torch.allclose(opt.state[p]["exp_avg_sq"], ref_opt.state[r]["exp_avg_sq"], rtol=1e-5, atol=1e-12), names[i]
     print(f"[adamw state] worst parameter difference after the step: {worst:.3e}")
     # export -> a fresh torch AdamW accepts it and carries the same moments
     back = torch.optim.AdamW([p.detach().clone().requires_grad_(True) for p in unet.parameters()], lr=1e-3)

@@ -50,10 +50,11 @@ def _inputs(case, dev):
     return noisy, text, t, noise
 
 
-# bf16 gradient bounds = 2x the worst figure measured on B200 over all golden cases (profiles/r02_parity_metrics.jsonl)
-BF16_GRAD_NORM_BOUND = 0.15
-BF16_GRAD_SAMPLE_BOUND = 0.2
-BF16_GRAD_TOTAL_BOUND = 3e-2
+# bf16 gradient bounds = 2x the worst figure measured on B200 over all golden cases (profiles/r02_parity_metrics.jsonl:
+# per-parameter grad-norm rel. err 1.03e-2, gradient samples 7.3e-2, total grad norm 4.6e-3; round 1 allowed 0.15 / 0.2 / 3e-2)
+BF16_GRAD_NORM_BOUND = 0.02
+BF16_GRAD_SAMPLE_BOUND = 0.15
+BF16_GRAD_TOTAL_BOUND = 1e-2
 
 
 def _check_grads(m, case, mode, tag=""):

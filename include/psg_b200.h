@@ -118,6 +118,19 @@ int psg_attn_fused_bwd(const void* q, long long ldq, const void* k, long long ld
                        void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Lq, int Lk, int hd, float scale,
                        unsigned long long drop_seed, float drop_p, void* stream);
 
+/* tcgen05 / TMEM attention (csrc/attention_umma.cu): every product on the 5th-generation tensor cores, scores in TMEM.  Takes the
+ * problems with 65..256 queries, <= 256 keys, head_dim % 16 == 0 and <= 256; psg_attn_fused_* route to it when psg_attn_umma_ok. */
+int psg_attn_umma_enable(int on);  /* test / measurement hook: 0 = never route to these kernels, 1 = default; returns the previous value */
+int psg_attn_umma_ok(int B, int H, int Lq, int Lk, int hd);
+int psg_attn_umma_timeout_flag(void); /* test hook: 1 if a bounded barrier wait of these kernels expired since the last call */
+int psg_attn_umma_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                      float* lse, int B, int H, int Lq, int Lk, int hd, float scale, unsigned long long drop_seed, float drop_p,
+                      void* stream);
+int psg_attn_umma_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,
+                      long long ldo, const void* dout, long long lddo, const float* lse, float* delta, void* dq, long long lddq,
+                      void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Lq, int Lk, int hd, float scale,
+                      unsigned long long drop_seed, float drop_p, void* stream);
+
 /* ---- GroupNorm (+SiLU)  nn.GroupNorm + F.silu, src/models/unet.py:79,89,115,127,156-157,214,231,397-398 ---------- */
 int psg_groupnorm_slices(int B, int HW);
 int psg_groupnorm_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,

@@ -794,6 +794,16 @@ static int configure(Kern kern, bool& done, const char* name) {
 
 extern "C" {
 
+// attention_umma.cu: the tcgen05 / TMEM kernels that take the problems with >= 65 queries (the 196-token level)
+int psg_attn_umma_ok(int B, int H, int Lq, int Lk, int hd);
+int psg_attn_umma_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                      float* lse, int B, int H, int Lq, int Lk, int hd, float scale, unsigned long long drop_seed, float drop_p,
+                      void* stream);
+int psg_attn_umma_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,
+                      long long ldo, const void* dout, long long lddo, const float* lse, float* delta, void* dq, long long lddq,
+                      void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Lq, int Lk, int hd, float scale,
+                      unsigned long long drop_seed, float drop_p, void* stream);
+
 // Test / measurement hook: CTAs per (batch, head) of the fused attention kernels (0 = by problem size).  Returns the previous value.
 int psg_attn_fused_split(int n) {
   const int prev = fattn::g_split;
@@ -811,6 +821,7 @@ int psg_attn_fused_small_bwd(int on) {
 
 // 1 if the fused kernels take this problem (bf16; head_dim % 16 == 0; Lk <= 256; everything fits in shared memory).
 int psg_attn_fused_ok(int B, int H, int Lq, int Lk, int hd) {
+  if (psg_attn_umma_ok(B, H, Lq, Lk, hd)) return 1;
   fattn::Params p;
   if (fattn::fill(p, B, H, Lq, Lk, hd, 1.f, 0, 0.f) != 0) return 0;
   // the S = Q K^T / dPd = dO V^T chunk loops may read 16 rows past the K (V, Q, dO) tile: the next tile must exist (it does)
@@ -823,6 +834,8 @@ int psg_attn_fused_fwd(const void* q, long long ldq, const void* k, long long ld
                        void* stream) {
   using namespace fattn;
   PSG_CHECK_ARG(q && k && v && o, "psg_attn_fused_fwd: null pointer");
+  if (psg_attn_umma_ok(B, H, Lq, Lk, hd) && ldo % 8 == 0 && ((uintptr_t)o % 16 == 0))
+    return psg_attn_umma_fwd(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Lq, Lk, hd, scale, drop_seed, drop_p, stream);
   Params p;
   memset(&p, 0, sizeof(p));
   PSG_CHECK_ARG(fill(p, B, H, Lq, Lk, hd, scale, drop_seed, drop_p) == 0 && fwd_smem(p) <= kSmemLimit,
@@ -849,6 +862,10 @@ int psg_attn_fused_bwd(const void* q, long long ldq, const void* k, long long ld
                        unsigned long long drop_seed, float drop_p, void* stream) {
   using namespace fattn;
   PSG_CHECK_ARG(q && k && v && o && dout && lse && delta && dq && dk && dv, "psg_attn_fused_bwd: null pointer");
+  if (psg_attn_umma_ok(B, H, Lq, Lk, hd) && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && ((uintptr_t)dq % 16 == 0) &&
+      ((uintptr_t)dk % 16 == 0) && ((uintptr_t)dv % 16 == 0))
+    return psg_attn_umma_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, lse, delta, dq, lddq, dk, lddk, dv, lddv, B, H, Lq, Lk, hd, scale,
+                             drop_seed, drop_p, stream);
   Params p;
   memset(&p, 0, sizeof(p));
   PSG_CHECK_ARG(fill(p, B, H, Lq, Lk, hd, scale, drop_seed, drop_p) == 0 && dq_smem(p) <= kSmemLimit && dkv_smem(p) <= kSmemLimit,

@@ -1,0 +1,142 @@
+"""Diagnostic for the tcgen05 attention kernels (csrc/attention_umma.cu): per-output max error against an fp32 PyTorch
+reference on a ladder of shapes (simplest first), the barrier-timeout flag after each call, then timings.
+Usage: python tools/check_attn_umma.py [--bench]"""
+import ctypes as C
+import math
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from pokemon_sprite_generator_b200 import ops as K  # noqa: E402
+
+L = K.L
+lib = L.load()
+dev = torch.device("cuda:0")
+
+
+def call_fwd(q, k, v, o, lse, B, H, Lq, Lk, hd, seed, p):
+    L.call("psg_attn_umma_fwd", L.ptr(q), C.c_longlong(q.stride(0)), L.ptr(k), C.c_longlong(k.stride(0)), L.ptr(v),
+           C.c_longlong(v.stride(0)), L.ptr(o), C.c_longlong(o.stride(0)), L.ptr(lse), C.c_int(B), C.c_int(H), C.c_int(Lq),
+           C.c_int(Lk), C.c_int(hd), C.c_float(1.0 / math.sqrt(hd)), C.c_ulonglong(seed), C.c_float(p), L.stream_ptr())
+
+
+def call_bwd(q, k, v, o, do, lse, delta, dq, dk, dv, B, H, Lq, Lk, hd, seed, p):
+    L.call("psg_attn_umma_bwd", L.ptr(q), C.c_longlong(q.stride(0)), L.ptr(k), C.c_longlong(k.stride(0)), L.ptr(v),
+           C.c_longlong(v.stride(0)), L.ptr(o), C.c_longlong(o.stride(0)), L.ptr(do), C.c_longlong(do.stride(0)), L.ptr(lse),
+           L.ptr(delta), L.ptr(dq), C.c_longlong(dq.stride(0)), L.ptr(dk), C.c_longlong(dk.stride(0)), L.ptr(dv),
+           C.c_longlong(dv.stride(0)), C.c_int(B), C.c_int(H), C.c_int(Lq), C.c_int(Lk), C.c_int(hd),
+           C.c_float(1.0 / math.sqrt(hd)), C.c_ulonglong(seed), C.c_float(p), L.stream_ptr())
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def case(B, H, Lq, Lk, hd, p=0.0):
+    Cc = H * hd
+    g = torch.Generator(device="cuda").manual_seed(Lq * Lk + hd)
+    qkv = torch.randn(B * Lq, 3 * Cc, device=dev, generator=g).bfloat16()
+    kvb = torch.randn(B * Lk, 2 * Cc, device=dev, generator=g).bfloat16()
+    qb, kb, vb = qkv[:, :Cc], kvb[:, :Cc], kvb[:, Cc:]
+    do = torch.randn(B * Lq, Cc, device=dev, generator=g).bfloat16()
+    o = torch.zeros(B * Lq, Cc, device=dev, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, Lq, device=dev)
+    seed = 987654321
+    tag = f"B={B} H={H} Lq={Lq} Lk={Lk} hd={hd} p={p}"
+    try:
+        call_fwd(qb, kb, vb, o, lse, B, H, Lq, Lk, hd, seed, p)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(f"{tag}: FWD FAILED {e}", flush=True)
+        return
+    tf = lib.psg_attn_umma_timeout_flag()
+    q = qb.float().reshape(B, Lq, H, hd).transpose(1, 2).requires_grad_(True)
+    k = kb.float().reshape(B, Lk, H, hd).transpose(1, 2).requires_grad_(True)
+    v = vb.float().reshape(B, Lk, H, hd).transpose(1, 2).requires_grad_(True)
+    s = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    pr = torch.softmax(s, dim=-1)
+    if p > 0:
+        # recover the mask with the mma.sync kernel family (same stateless rule) through an identity V
+        prev = lib.psg_attn_umma_enable(0)
+        mask = torch.zeros(B, H, Lq, Lk, device=dev)
+        for k0 in range(0, Lk, hd):          # hd keys at a time: V = the identity on keys [k0, k0 + hd)
+            n = min(hd, Lk - k0)
+            eye = torch.zeros(B, Lk, 2 * Cc, device=dev, dtype=torch.bfloat16)
+            for h in range(H):
+                eye[:, k0:k0 + n, Cc + h * hd: Cc + h * hd + n] = torch.eye(n, device=dev, dtype=torch.bfloat16)
+            eye = eye.view(B * Lk, 2 * Cc)
+            om = torch.empty_like(o)
+            K.attn_fused_fwd(qb, kb, eye[:, Cc:], om, None, B, H, Lq, Lk, hd, seed, p)
+            mask[..., k0:k0 + n] = (om.float().view(B, Lq, H, hd).transpose(1, 2)[..., :n] > 0).float()
+        lib.psg_attn_umma_enable(prev)
+        pr_used = pr * mask / (1.0 - p)
+    else:
+        pr_used = pr
+    oref = pr_used @ v
+    oref.backward(do.float().view(B, Lq, H, hd).transpose(1, 2))
+    e_o = rel(o, oref.detach().transpose(1, 2).reshape(B * Lq, Cc))
+    e_l = (lse - torch.logsumexp(s, dim=-1).detach()).abs().max().item()
+    dqkv = torch.zeros_like(qkv)
+    dkv = torch.zeros_like(kvb)
+    delta = torch.zeros(B * H * Lq, device=dev)
+    try:
+        call_bwd(qb, kb, vb, o, do, lse, delta, dqkv[:, :Cc], dkv[:, :Cc], dkv[:, Cc:], B, H, Lq, Lk, hd, seed, p)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(f"{tag}: fwd o {e_o:.2e} lse {e_l:.2e} timeout {tf} | BWD FAILED {e}", flush=True)
+        return
+    tb = lib.psg_attn_umma_timeout_flag()
+    e_q = rel(dqkv[:, :Cc], q.grad.transpose(1, 2).reshape(B * Lq, Cc))
+    e_k = rel(dkv[:, :Cc], k.grad.transpose(1, 2).reshape(B * Lk, Cc))
+    e_v = rel(dkv[:, Cc:], v.grad.transpose(1, 2).reshape(B * Lk, Cc))
+    ok = max(e_o, e_q, e_k, e_v) < 3e-2 and e_l < 1e-3 and not tf and not tb
+    print(f"{tag}: fwd o {e_o:.2e} lse {e_l:.2e} timeout {tf} | bwd dq {e_q:.2e} dk {e_k:.2e} dv {e_v:.2e} timeout {tb} "
+          f"{'OK' if ok else 'MISMATCH'}", flush=True)
+    if tf or tb:
+        print("barrier timeout: stopping the ladder", flush=True)
+        sys.exit(3)
+
+
+def bench(B=256, H=4):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, n=7):
+        fn()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    for (lq, lk, c) in [(196, 196, 640), (196, 32, 640)]:
+        hd = c // H
+        q = torch.randn(B * lq, 3 * c, device=dev).bfloat16()
+        kv = torch.randn(B * lk, 2 * c, device=dev).bfloat16()
+        o = torch.empty(B * lq, c, device=dev, dtype=torch.bfloat16)
+        do = torch.randn(B * lq, c, device=dev).bfloat16()
+        lse = torch.empty(B, H, lq, device=dev)
+        dq = torch.empty_like(q); dkv = torch.empty_like(kv)
+        fl = 4.0 * B * H * lq * lk * hd
+        for on in (0, 1):
+            lib.psg_attn_umma_enable(on)
+            for p in (0.0, 0.05):
+                tf = timeit(lambda: K.attn_fused_fwd(q[:, :c], kv[:, :c], kv[:, c:], o, lse, B, H, lq, lk, hd, 7, p))
+                tb = timeit(lambda: K.attn_fused_bwd(q[:, :c], kv[:, :c], kv[:, c:], o, do, lse, dq[:, :c], dkv[:, :c], dkv[:, c:], B, H, lq, lk, hd, 7, p))
+                print(f"{'tcgen05 ' if on else 'mma.sync'} Lq={lq:4d} Lk={lk:4d} hd={hd:4d} p={p:.2f} | fwd {tf * 1e3:8.1f} us {fl / tf / 1e9:7.1f} TF/s"
+                      f" | bwd {tb * 1e3:8.1f} us {2.5 * fl / tb / 1e9:7.1f} TF/s  timeout {lib.psg_attn_umma_timeout_flag()}", flush=True)
+    lib.psg_attn_umma_enable(1)
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), flush=True)
+    for args in [(1, 1, 128, 64, 64), (1, 1, 128, 128, 128), (1, 1, 128, 32, 160), (2, 2, 128, 64, 160), (2, 4, 196, 196, 160),
+                 (3, 4, 196, 32, 160), (2, 8, 196, 196, 80), (5, 8, 100, 70, 48), (2, 8, 196, 64, 80, 0.25), (2, 4, 196, 196, 160, 0.05),
+                 (200, 4, 196, 196, 160, 0.05)]:
+        case(*args)
+    if "--bench" in sys.argv:
+        bench()

@@ -212,14 +212,15 @@ int psg_sum_partials(const float* partial, int splits, long long split_stride, f
  *                  src/training/improved_diffusion_trainer.py:277-283,399-413) ------------------------------------- */
 int psg_sumsq(const float* x, long long n, float* out_sumsq, int accumulate, void* workspace, void* stream);
 int psg_clip_coef(const float* sumsq, float max_norm, float* state /* [3]: norm, coef, finite */, void* stream);
-int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+/* betas are doubles, as torch holds them: the kernel uses float(beta) and float(1 - beta), the latter formed in double */
+int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, double beta1, double beta2, float eps,
                    float weight_decay, long long step, const float* state, void* bf16_shadow /* nullable: bf16 copy of p */,
                    void* stream);
 /* generalisation: step <= 0 takes the applied-step count from state[3] (written by psg_clip_coef_count, which skips
  * non-finite steps like the reference's `continue`, :395-397); coupled_l2 = 1 is torch.optim.Adam(weight_decay) (:285-292) */
 int psg_clip_coef_count(const float* sumsq, float max_norm, float* state4 /* [4]: norm, coef, finite, applied steps */,
                         void* stream);
-int psg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+int psg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, double beta1, double beta2, float eps,
                   float weight_decay, long long step, int coupled_l2, const float* state, void* bf16_shadow, void* stream);
 int psg_cast_bf16(const float* x, void* y_bf16, long long n, void* stream);
 int psg_scale_inplace(float* x, long long n, const float* state, float extra, void* stream);

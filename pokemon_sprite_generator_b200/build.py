@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-cudart", "static",
 ]
+# tuning builds only (e.g. PSG_EXTRA_NVCC_FLAGS=-DUATTN_PROF): part of the object digests, so a change of it recompiles
+NVCC_FLAGS += os.environ.get("PSG_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -72,16 +72,16 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
 
 __global__ void __launch_bounds__(kThreads)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
-             float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
-             const float* __restrict__ state, __nv_bfloat16* __restrict__ shadow, int coupled_l2, int step_from_state) {
+             float lr, float beta1, float beta2, float omb1, float omb2, double beta1_d, double beta2_d, float eps, float weight_decay,
+             float bc1, float bc2_sqrt, const float* __restrict__ state, __nv_bfloat16* __restrict__ shadow, int coupled_l2, int step_from_state) {
   float gscale = 1.f;
   if (state != nullptr) {
     if (state[2] == 0.f) return;  // non-finite gradients: skip the whole step (the bf16 shadow stays valid)
     gscale = state[1];
     if (step_from_state) {        // bias corrections from the device-side count of applied steps (state[3] >= 1 here)
       const double t = (double)state[3];
-      bc1 = (float)(1.0 - pow((double)beta1, t));
-      bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+      bc1 = (float)(1.0 - pow(beta1_d, t));
+      bc2_sqrt = (float)sqrt(1.0 - pow(beta2_d, t));
     }
   }
   const float step = lr / bc1;
@@ -96,8 +96,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg = gg * gscale + l2 * pp;
     pp *= decay;
-    mm = beta1 * mm + (1.f - beta1) * gg;
-    vv = beta2 * vv + (1.f - beta2) * gg * gg;
+    mm = beta1 * mm + omb1 * gg;          // 1 - beta formed in double on the host, as torch does (1.f - 0.999f is off by 5e-5)
+    vv = beta2 * vv + omb2 * gg * gg;
     const float denom = sqrtf(vv) / bc2_sqrt + eps;
     pp -= step * (mm / denom);
   };
@@ -181,7 +181,7 @@ int psg_clip_coef_count(const float* sumsq, float max_norm, float* state4, void*
 // psg_clip_coef_count).  coupled_l2 = 0: decoupled decay (AdamW, improved_diffusion_trainer.py:277-283);
 // 1: L2 added to the gradient (the reference's `else` branch, torch.optim.Adam(weight_decay=...), :285-292).
 // state may be null (no clipping / skipping).
-int psg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+int psg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, double beta1, double beta2, float eps,
                   float weight_decay, long long step, int coupled_l2, const float* state, void* bf16_shadow, void* stream) {
   PSG_CHECK_ARG(p && g && m && v && n > 0, "psg_adam_step: bad args");
   PSG_CHECK_ARG(step >= 1 || state != nullptr, "psg_adam_step: step <= 0 needs the device state (applied-step counter)");
@@ -189,20 +189,20 @@ int psg_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
                 "psg_adam_step: buffers must be 16B aligned");
   PSG_CHECK_ARG(bf16_shadow == nullptr || (uintptr_t)bf16_shadow % 8 == 0, "psg_adam_step: shadow must be 8B aligned");
   const double st = step >= 1 ? (double)step : 1.0;
-  const double bc1 = 1.0 - pow((double)beta1, st);
-  const double bc2 = 1.0 - pow((double)beta2, st);
+  const double bc1 = 1.0 - pow(beta1, st);
+  const double bc2 = 1.0 - pow(beta2, st);
   long long g_ = (n / 4 + kThreads - 1) / kThreads;
   long long cap = (long long)psg_num_sms() * 16;
   if (g_ > cap) g_ = cap;
   if (g_ < 1) g_ = 1;
-  adamw_kernel<<<(int)g_, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+  adamw_kernel<<<(int)g_, kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), beta1, beta2, eps, weight_decay, (float)bc1,
                                                               (float)sqrt(bc2), state, (__nv_bfloat16*)bf16_shadow, coupled_l2 ? 1 : 0,
                                                               step >= 1 ? 0 : 1);
   PSG_CHECK_LAUNCH("psg_adam_step");
   return PSG_OK;
 }
 
-int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+int psg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, double beta1, double beta2, float eps,
                    float weight_decay, long long step, const float* state, void* bf16_shadow, void* stream) {
   PSG_CHECK_ARG(step >= 1, "psg_adamw_step: step must be >= 1");
   return psg_adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, 0, state, bf16_shadow, stream);

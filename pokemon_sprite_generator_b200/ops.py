@@ -293,8 +293,8 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step: int, state
     """shadow: optional bf16 buffer of p's size, rewritten with the updated parameters (what the tensor-core GEMMs read).
     step <= 0: bias corrections from the device-side applied-step counter state[3].  coupled_l2: torch.optim.Adam decay."""
     assert shadow is None or (shadow.dtype == torch.bfloat16 and shadow.numel() == p.numel())
-    L.call("psg_adam_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), C.c_longlong(p.numel()), C.c_float(lr), C.c_float(beta1),
-           C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), C.c_int(int(coupled_l2)), L.ptr(state),
+    L.call("psg_adam_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), C.c_longlong(p.numel()), C.c_float(lr), C.c_double(beta1),
+           C.c_double(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_longlong(step), C.c_int(int(coupled_l2)), L.ptr(state),
            L.ptr(shadow), L.stream_ptr())
 
 

@@ -386,17 +386,62 @@ def test_attention_tensor_core(cuda_device, B, H, Lq, Lk, hd, p):
                                             (2, 4, 49, 32, 320, 0.25), (2, 8, 196, 64, 80, 0.25)])
 @pytest.mark.parametrize("split", [0, 1, 2])
 def test_attention_fused(cuda_device, B, H, Lq, Lk, hd, p, split):
-    """Fused bf16 attention (scores on chip, LSE saved, probabilities recomputed in backward) vs an fp32 PyTorch reference.
-    split: CTAs per (batch, head); 1 and 2 make one CTA walk several 64-row blocks (the large-batch configuration)."""
+    """Fused bf16 attention, mma.sync family (scores on chip, LSE saved, probabilities recomputed in backward) vs an fp32 PyTorch
+    reference.  split: CTAs per (batch, head); 1 and 2 make one CTA walk several 64-row blocks (the large-batch configuration).
+    The tcgen05 family is switched off here (it has its own test below) so that these kernels stay covered on every shape."""
     K = _ops()
     dtype = torch.bfloat16
-    prev = K.L.load().psg_attn_fused_split(split)
-    prev_small = K.L.load().psg_attn_fused_small_bwd(0 if split == 2 else 1)   # split 2 also keeps the dQ + dK/dV pair covered at Lq, Lk <= 64
+    lib = K.L.load()
+    prev_umma = lib.psg_attn_umma_enable(0)
+    prev = lib.psg_attn_fused_split(split)
+    prev_small = lib.psg_attn_fused_small_bwd(0 if split == 2 else 1)   # split 2 also keeps the dQ + dK/dV pair covered at Lq, Lk <= 64
     try:
         _attention_fused_case(K, dtype, B, H, Lq, Lk, hd, p)
     finally:
-        K.L.load().psg_attn_fused_split(prev)
-        K.L.load().psg_attn_fused_small_bwd(prev_small)
+        lib.psg_attn_fused_split(prev)
+        lib.psg_attn_fused_small_bwd(prev_small)
+        lib.psg_attn_umma_enable(prev_umma)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,hd,p", [(2, 4, 196, 196, 160, 0.0), (2, 8, 196, 196, 80, 0.0), (3, 4, 196, 32, 160, 0.0), (5, 8, 100, 70, 48, 0.0),
+                                            (1, 1, 128, 128, 128, 0.0), (2, 2, 65, 77, 64, 0.0), (2, 4, 196, 196, 160, 0.05),
+                                            (2, 8, 196, 64, 80, 0.25), (3, 4, 196, 49, 160, 0.25), (300, 4, 196, 196, 160, 0.05)])
+def test_attention_umma(cuda_device, B, H, Lq, Lk, hd, p):
+    """tcgen05 / TMEM attention (csrc/attention_umma.cu: S, P, dS in tensor memory, TS-form MMAs) through the same entry points,
+    against the same fp32 PyTorch reference: ragged tiles (196 = 128 + 68 rows), both swizzle geometries (head_dim % 64 == 0 or
+    not), odd key counts (per-element dropout hashes), more (batch, head) units than SMs (persistent walk), dropout."""
+    K = _ops()
+    lib = K.L.load()
+    assert lib.psg_attn_umma_ok(B, H, Lq, Lk, hd) == 1
+    lib.psg_attn_umma_timeout_flag()
+    _attention_fused_case(K, torch.bfloat16, B, H, Lq, Lk, hd, p)
+    assert lib.psg_attn_umma_timeout_flag() == 0, "a bounded barrier wait expired inside the tcgen05 attention kernels"
+
+
+def test_attention_umma_dropout_mask_matches_the_mma_sync_family(cuda_device):
+    """Both fused families realise the library-wide stateless dropout rule: the same (seed, element) pairs are dropped."""
+    K = _ops()
+    lib = K.L.load()
+    B, H, Lq, Lk, hd, p, seed = 2, 4, 196, 160, 160, 0.25, 1234567
+    C_ = H * hd
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(B * Lq, C_, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B * Lk, C_, device="cuda", generator=g).bfloat16()
+    eye = torch.zeros(B, Lk, C_, device="cuda", dtype=torch.bfloat16)
+    for h in range(H):
+        eye[:, :, h * hd:h * hd + Lk] = torch.eye(Lk, device="cuda", dtype=torch.bfloat16)
+    eye = eye.view(B * Lk, C_)
+    outs = []
+    for on in (0, 1):
+        prev = lib.psg_attn_umma_enable(on)
+        try:
+            o = torch.empty(B * Lq, C_, device="cuda", dtype=torch.bfloat16)
+            K.attn_fused_fwd(q, k, eye, o, None, B, H, Lq, Lk, hd, seed, p)
+            outs.append(o.float() > 0)
+        finally:
+            lib.psg_attn_umma_enable(prev)
+    assert torch.equal(outs[0], outs[1])
+    assert abs(1.0 - outs[0].float().view(B, Lq, H, hd)[..., :Lk].mean().item() - p) < 0.02
 
 
 def _attention_fused_case(K, dtype, B, H, Lq, Lk, hd, p):
@@ -418,14 +463,16 @@ def _attention_fused_case(K, dtype, B, H, Lq, Lk, hd, p):
     pr = torch.softmax(s, dim=-1)
     _cmp(lse, torch.logsumexp(s, dim=-1).detach(), torch.float32, "fused lse", 100.0)
     if p > 0:
-        assert Lk <= hd
-        eye = torch.zeros(B * Lk, 2 * C_, device="cuda", dtype=dtype)
-        for h in range(H):
-            eye[:, C_ + h * hd: C_ + h * hd + Lk] = torch.eye(Lk, device="cuda", dtype=dtype).repeat(B, 1)
-        om = torch.empty_like(o)
-        K.attn_fused_fwd(qb, kvb[:, :C_], eye[:, C_:], om, None, B, H, Lq, Lk, hd, seed, p)
-        pm = om.float().view(B, Lq, H, hd).transpose(1, 2)[..., :Lk]
-        mask = (pm > 0).float()
+        mask = torch.zeros(B, H, Lq, Lk, device="cuda")
+        for k0 in range(0, Lk, hd):          # hd keys at a time: V = the identity on keys [k0, k0 + hd)
+            n = min(hd, Lk - k0)
+            eye = torch.zeros(B, Lk, 2 * C_, device="cuda", dtype=dtype)
+            for h in range(H):
+                eye[:, k0:k0 + n, C_ + h * hd: C_ + h * hd + n] = torch.eye(n, device="cuda", dtype=dtype)
+            eye = eye.view(B * Lk, 2 * C_)
+            om = torch.empty_like(o)
+            K.attn_fused_fwd(qb, kvb[:, :C_], eye[:, C_:], om, None, B, H, Lq, Lk, hd, seed, p)
+            mask[..., k0:k0 + n] = (om.float().view(B, Lq, H, hd).transpose(1, 2)[..., :n] > 0).float()
         assert abs((1.0 - mask.mean().item()) - p) < 0.03
         pr_used = pr * mask / (1.0 - p)
     else:

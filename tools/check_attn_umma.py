@@ -132,8 +132,74 @@ def bench(B=256, H=4):
     lib.psg_attn_umma_enable(1)
 
 
+def prof(B=256, H=4, lq=196, lk=196, c=640, p=0.05):
+    """per-role cycle accounting (library built with PSG_EXTRA_NVCC_FLAGS=-DUATTN_PROF): mean over CTAs, in microseconds at 1.9 GHz"""
+    import numpy as np
+    hd = c // H
+    q = torch.randn(B * lq, 3 * c, device=dev).bfloat16()
+    kv = torch.randn(B * lk, 2 * c, device=dev).bfloat16()
+    o = torch.empty(B * lq, c, device=dev, dtype=torch.bfloat16)
+    do = torch.randn(B * lq, c, device=dev).bfloat16()
+    lse = torch.empty(B, H, lq, device=dev)
+    delta = torch.empty(B * H * lq, device=dev)
+    dq = torch.empty_like(q); dkv = torch.empty_like(kv)
+    buf = (C.c_longlong * (160 * 32))()
+    names = {"fwd": (["mma: wait K/Q", "mma: wait P_FULL", "mma: issue S", "mma: PV", "", "", "", "",
+                      "smx: wait S_FULL", "smx: pass 1", "smx: pair barrier", "smx: wait P_EMPTY", "smx: pass 2", "smx: tail", "", "",
+                      "epi: wait O_FULL", "epi: drain"]),
+             "dq": (["mma: wait KV/QD", "mma: wait T_EMPTY", "mma: issue S,dP", "mma: wait DS_FULL", "mma: issue dQ", "", "", "",
+                     "cmp: wait stats", "cmp: wait SD_FULL", "cmp: elementwise", "cmp: wait DQ_FULL", "cmp: drain", "", "", "",
+                     "stat: wait ST_EMPTY", "stat: compute"]),
+             "dkv": (["mma: wait QD/KV", "mma: issue ST", "mma: wait PD_FULL", "mma: issue acc", "", "", "", "",
+                      "cmp: wait stats", "cmp: wait ST_FULL", "cmp: elementwise", "cmp: wait ACC_FULL", "cmp: drain"])}
+
+    def report(tag):
+        torch.cuda.synchronize()
+        lib.psg_attn_umma_prof(buf)
+        a = np.ctypeslib.as_array(buf).reshape(160, 32)[:148].astype(np.float64) / 1.9e3
+        print(f"--- {tag} (us per CTA, mean over 148 CTAs)")
+        for i, n in enumerate(names[tag]):
+            if n:
+                print(f"   {n:22s} {a[:, i].mean():8.1f}")
+
+    for _ in range(2):
+        call_fwd(q[:, :c], kv[:, :c], kv[:, c:], o, lse, B, H, lq, lk, hd, 7, p)
+    report("fwd")
+    # the two backward kernels are launched by one call: run it, then only the stats of the LAST kernel (dK/dV) remain;
+    # the dQ kernel's numbers are read with the dK/dV launch suppressed through Lk-side trick is not possible, so run twice
+    call_bwd(q[:, :c], kv[:, :c], kv[:, c:], o, do, lse, delta, dq[:, :c], dkv[:, :c], dkv[:, c:], B, H, lq, lk, hd, 7, p)
+    report("dkv")
+    lib.psg_attn_umma_prof_only(1)
+    call_bwd(q[:, :c], kv[:, :c], kv[:, c:], o, do, lse, delta, dq[:, :c], dkv[:, :c], dkv[:, c:], B, H, lq, lk, hd, 7, p)
+    report("dq")
+    lib.psg_attn_umma_prof_only(0)
+
+
+def one(B=256, H=4, lq=196, lk=196, c=640, p=0.05, reps=2):
+    """the benchmark-shape problem, forward + backward `reps` times (for ncu: -k regex:uattn -s 3 -c 3)"""
+    hd = c // H
+    q = torch.randn(B * lq, 3 * c, device=dev).bfloat16()
+    kv = torch.randn(B * lk, 2 * c, device=dev).bfloat16()
+    o = torch.empty(B * lq, c, device=dev, dtype=torch.bfloat16)
+    do = torch.randn(B * lq, c, device=dev).bfloat16()
+    lse = torch.empty(B, H, lq, device=dev)
+    dq = torch.empty_like(q); dkv = torch.empty_like(kv)
+    for _ in range(reps):
+        K.attn_fused_fwd(q[:, :c], kv[:, :c], kv[:, c:], o, lse, B, H, lq, lk, hd, 7, p)
+        K.attn_fused_bwd(q[:, :c], kv[:, :c], kv[:, c:], o, do, lse, dq[:, :c], dkv[:, :c], dkv[:, c:], B, H, lq, lk, hd, 7, p)
+    torch.cuda.synchronize()
+    print("one: timeout", lib.psg_attn_umma_timeout_flag(), flush=True)
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
+    if "--prof" in sys.argv:
+        prof(lk=32 if "--cross" in sys.argv else 196)
+        sys.exit(0)
+    if "--one" in sys.argv:
+        lk = 32 if "--cross" in sys.argv else 196
+        one(lk=lk)
+        sys.exit(0)
     for args in [(1, 1, 128, 64, 64), (1, 1, 128, 128, 128), (1, 1, 128, 32, 160), (2, 2, 128, 64, 160), (2, 4, 196, 196, 160),
                  (3, 4, 196, 32, 160), (2, 8, 196, 196, 80), (5, 8, 100, 70, 48), (2, 8, 196, 64, 80, 0.25), (2, 4, 196, 196, 160, 0.05),
                  (200, 4, 196, 196, 160, 0.05)]:

@@ -397,7 +397,7 @@ def main():
     final_loss = loss.item()
 
     # roofline of the dominant kernel (umma_gemm_kernel: every conv / linear fwd, dgrad, wgrad)
-    um = [(s.elapsed_time(e), fl) for (s, e, fl, engn, _) in prof if engn == "umma"]
+    um = [(s.elapsed_time(e), fl) for (s, e, fl, engn, *_) in prof if engn == "umma"]
     um_ms = sum(x[0] for x in um)
     um_flops = sum(x[1] for x in um)
     peaks = _peaks()

@@ -105,6 +105,11 @@ int psg_smooth_l1_fwd_bwd(const float* pred, const float* target, float* dpred, 
 int psg_ddpm_step(const float* x, const float* eps, const float* z, float* out, long long n, int mode, const float* tab0,
                   const float* tab1, const float* tab2, const float* tab3, int t, int num_t, void* stream);
 
+/* the reference's two other reverse-step formulas: mode 2 = src/training/diffusers_trainer.py:76-100, mode 3 = gradio_app.py:324-361;
+ * coef5 is a HOST array of the per-step scalars evaluated as the reference evaluates them (see csrc/diffusion_ops.cu) */
+int psg_reverse_step(const float* x, const float* eps, const float* z, float* out, long long n, int mode, const float* coef5,
+                     void* stream);
+
 /* ---- fused tensor-core attention (bf16): scores stay on chip, forward saves only the row log-sum-exp ------------------
  * replaces the nn.MultiheadAttention core, src/models/unet.py:160-173,217,235 (softmax over keys, dropout on probabilities) */
 int psg_attn_fused_ok(int B, int H, int Lq, int Lk, int hd);
@@ -180,6 +185,9 @@ int psg_softmax_bwd(const void* P, const float* dPd, void* dS, void* Pd, long lo
 /* ---- layout, resize, reductions, conditioning inputs, weight packing ---------------------------------------------
  * upsample: nn.Upsample(bilinear, align_corners=False) unet.py:365,375,385; timestep embedding unet.py:47-50;
  * mean pool: AdaptiveAvgPool1d(1) unet.py:322,445; copy_strided: torch.cat unet.py:482-503; colsum: bias gradients. */
+/* VAE decoder (src/models/vae_decoder.py:33-65,128-222): per-sample transpose (the raw-reshape K / V of its cross-attention), tanh */
+int psg_batched_transpose(const void* in, void* out, int B, int R, int Cc, int dtype, void* stream);
+int psg_tanh(const float* x, float* y, long long n, void* stream);
 int psg_nchw_to_tokens(const float* src, void* dst, long long ld, int B, int C, int HW, int dtype, void* stream);
 int psg_tokens_to_nchw(const void* src, long long ld, float* dst, int B, int C, int HW, int dtype, void* stream);
 int psg_copy_strided(const void* src, long long lds, void* dst, long long ldd, long long rows, int C, int accumulate,

@@ -5,6 +5,8 @@
 //   smooth_l1   : nn.SmoothL1Loss(beta=0.1)  src/training/improved_diffusion_trainer.py:300,388
 //   ddpm_step 0 : ddpm_sample update         src/training/improved_diffusion_trainer.py:543-567
 //   ddpm_step 1 : sample_previous_timestep   src/training/final_trainer.py:52-71
+//   reverse_step 2 : sample_prev_timestep    src/training/diffusers_trainer.py:76-100  (x0-prediction form)
+//   reverse_step 3 : gradio sampling loop    gradio_app.py:324-361                     (denoise, then re-noise to the next step)
 //
 // Bit-exactness: eager PyTorch evaluates each tensor op separately (no FMA contraction), so the
 // arithmetic here is spelled with __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn in the reference's order.
@@ -213,6 +215,42 @@ int psg_smooth_l1_fwd_bwd(const float* pred, const float* target, float* dpred, 
   smooth_l1_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(pred, target, dpred, loss, partials, counter,
                                                                  (size_t)n, beta, grad_scale);
   PSG_CHECK_LAUNCH("psg_smooth_l1_fwd_bwd");
+  return PSG_OK;
+}
+
+// The two remaining reverse-step variants of the reference, each elementwise operation rounded separately and in the reference's
+// order (no FMA contraction), with the per-step scalars `c` evaluated by the caller exactly as the reference evaluates them:
+//   mode 2: pred = (x - c0 * eps) / c1;  prev = c2 * pred + c3 * eps;  [+ c4 * z]
+//           c = {sqrt(1-abar_t), sqrt(abar_t), sqrt(abar_prev), sqrt(1-abar_prev), sqrt(posterior_variance_t)}
+//   mode 3: lat = (x - c0 * eps) / c1;   [lat = c2 * lat + c3 * z]
+//           c = {(1-alpha_t)/sqrt(1-abar_t), sqrt(alpha_t), sqrt(alpha_next), sqrt(1-alpha_next)}
+struct RevCoef { float c[5]; };
+__global__ void __launch_bounds__(kThreads)
+reverse_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z, float* __restrict__ out,
+                    size_t n, int mode, RevCoef k) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+    const float xv = x[i], ev = eps[i];
+    float r = __fdiv_rn(__fsub_rn(xv, __fmul_rn(k.c[0], ev)), k.c[1]);
+    if (mode == 2) {
+      r = __fadd_rn(__fmul_rn(k.c[2], r), __fmul_rn(k.c[3], ev));
+      if (z != nullptr) r = __fadd_rn(r, __fmul_rn(k.c[4], z[i]));
+    } else if (z != nullptr) {
+      r = __fadd_rn(__fmul_rn(k.c[2], r), __fmul_rn(k.c[3], z[i]));
+    }
+    out[i] = r;
+  }
+}
+
+int psg_reverse_step(const float* x, const float* eps, const float* z, float* out, long long n, int mode, const float* coef5,
+                     void* stream) {
+  if (n <= 0) return PSG_OK;
+  PSG_CHECK_ARG(x && eps && out && coef5, "psg_reverse_step: null pointer");
+  PSG_CHECK_ARG(mode == 2 || mode == 3, "psg_reverse_step: mode must be 2 (diffusers_trainer) or 3 (gradio loop)");
+  RevCoef k;
+  for (int i = 0; i < 5; ++i) k.c[i] = coef5[i];      // host array
+  int grid = grid_for((size_t)n, psg_num_sms() * 8);
+  reverse_step_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, eps, z, out, (size_t)n, mode, k);
+  PSG_CHECK_LAUNCH("psg_reverse_step");
   return PSG_OK;
 }
 

@@ -438,12 +438,56 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int S, lo
 
 }  // namespace
 
+// ---- per-sample transpose in[b][r][c] -> out[b][c][r] (the VAE decoder's raw-reshape K / V, src/models/vae_decoder.py:54-55) ----
+template <typename T>
+__global__ void batched_transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int Cc) {
+  __shared__ T tile[32][33];
+  const long long base = (long long)blockIdx.z * R * Cc;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = in[base + (long long)r * Cc + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) out[base + (long long)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void tanh_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = tanhf(x[i]);
+}
+
 #define DISPATCH_T(dtype, ...)                                           \
   if ((dtype) == PSG_DTYPE_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
   else if ((dtype) == PSG_DTYPE_F32) { using T = float; __VA_ARGS__; }     \
   else { psg_set_error("bad dtype %d", (int)(dtype)); return PSG_ERR_INVALID; }
 
 extern "C" {
+
+// out[b][c][r] = in[b][r][c], b < B (contiguous [B, R, Cc] in, [B, Cc, R] out)
+int psg_batched_transpose(const void* in, void* out, int B, int R, int Cc, int dtype, void* stream) {
+  PSG_CHECK_ARG(B >= 0 && R > 0 && Cc > 0 && B <= 65535, "psg_batched_transpose: bad sizes");
+  if (B == 0) return PSG_OK;
+  PSG_CHECK_ARG(in && out && in != out, "psg_batched_transpose: null or aliased pointer");
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, B), block(32, 8);
+  DISPATCH_T(dtype, (batched_transpose_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)in, (T*)out, R, Cc)));
+  PSG_CHECK_LAUNCH("psg_batched_transpose");
+  return PSG_OK;
+}
+
+// y = tanh(x), fp32 (the VAE decoder's output activation, src/models/vae_decoder.py:174); in place allowed
+int psg_tanh(const float* x, float* y, long long n, void* stream) {
+  if (n <= 0) return PSG_OK;
+  PSG_CHECK_ARG(x && y, "psg_tanh: null pointer");
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)psg_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  tanh_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, (size_t)n);
+  PSG_CHECK_LAUNCH("psg_tanh");
+  return PSG_OK;
+}
 
 int psg_nchw_to_tokens(const float* src, void* dst, long long ld, int B, int C, int HW, int dtype, void* stream) {
   PSG_CHECK_ARG(B >= 0 && C > 0 && HW > 0, "psg_nchw_to_tokens: bad sizes");

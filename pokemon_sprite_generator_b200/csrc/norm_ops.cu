@@ -32,6 +32,39 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, long long ld, GNShape s
   const int b = blockIdx.y, sl = blockIdx.x;
   const int v = threadIdx.x % s.vpp, row = threadIdx.x / s.vpp;
   const int p0 = sl * s.pix_per_slice, p1 = min(s.HW, p0 + s.pix_per_slice);
+  if (s.cpg & 1) {
+    // odd channels per group (the VAE decoder's GroupNorm(32, 32): one channel per group): per-channel sums,
+    // [rows*vpp][16] floats of shared memory
+    if (row < s.rows) {
+      float sum[8], sq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
+      const T* base = x + ((long long)b * s.HW) * ld + v * 8;
+      for (int p = p0 + row; p < p1; p += s.rows) {
+        Vec8<T> t;
+        t.load(base + (long long)p * ld);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sum[j] += t.v[j]; sq[j] += t.v[j] * t.v[j]; }
+      }
+      float* mine = sm + (size_t)threadIdx.x * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { mine[j] = sum[j]; mine[8 + j] = sq[j]; }
+    }
+    __syncthreads();
+    float* out = partial + ((long long)(b * s.S + sl) * s.G) * 2;
+    for (int g = threadIdx.x; g < s.G; g += blockDim.x) {
+      float su = 0.f, sq = 0.f;
+      for (int r = 0; r < s.rows; ++r)
+        for (int c = g * s.cpg; c < (g + 1) * s.cpg; ++c) {
+          const float* src = sm + (size_t)(r * s.vpp + (c >> 3)) * 16;
+          su += src[c & 7];
+          sq += src[8 + (c & 7)];
+        }
+      out[2 * g] = su;
+      out[2 * g + 1] = sq;
+    }
+    return;
+  }
   if (row < s.rows) {
     float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
     const T* base = x + ((long long)b * s.HW) * ld + v * 8;
@@ -252,7 +285,6 @@ __global__ void __launch_bounds__(256) gn_param_grad_kernel(const float* __restr
 int make_shape(GNShape& s, int B, int HW, int C, int G, int slices, int* threads) {
   if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G != 0 || C % 8 != 0) return -1;
   s.B = B; s.HW = HW; s.C = C; s.G = G; s.cpg = C / G;
-  if (s.cpg % 2 != 0) return -1;
   s.vpp = C / 8;
   if (s.vpp > kMaxThreads) return -1;
   s.rows = kMaxThreads / s.vpp;
@@ -289,14 +321,14 @@ int psg_groupnorm_fwd(const void* x, long long ld_x, void* y, long long ld_y, co
   GNShape s;
   int threads;
   PSG_CHECK_ARG(make_shape(s, B, HW, C, G, psg_groupnorm_slices(B, HW), &threads) == 0,
-                "psg_groupnorm_fwd: unsupported shape B=%d HW=%d C=%d G=%d (need C%%8==0, even channels/group)", B, HW, C, G);
+                "psg_groupnorm_fwd: unsupported shape B=%d HW=%d C=%d G=%d (need C%%8==0)", B, HW, C, G);
   PSG_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0),
                 "psg_groupnorm_fwd: pitches/pointers must be 16B aligned");
   PSG_CHECK_ARG(B <= 65535, "psg_groupnorm_fwd: B too large");
   dim3 grid(s.S, B);
   cudaStream_t st = (cudaStream_t)stream;
   size_t smem = 2 * G * sizeof(float);
-  size_t smem_stats = (size_t)threads * 8 * sizeof(float);
+  size_t smem_stats = (size_t)threads * ((s.cpg & 1) ? 16 : 8) * sizeof(float);
   if (dtype == PSG_DTYPE_BF16) {
     gn_stats_kernel<__nv_bfloat16><<<grid, threads, smem_stats, st>>>((const __nv_bfloat16*)x, ld_x, s, workspace);
     gn_apply_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)x, ld_x, (__nv_bfloat16*)y, ld_y, gamma, beta,
@@ -321,6 +353,7 @@ int psg_groupnorm_bwd(const void* dy, long long ld_dy, const void* x, long long 
   int threads;
   PSG_CHECK_ARG(make_shape(s, B, HW, C, G, psg_groupnorm_slices(B, HW), &threads) == 0,
                 "psg_groupnorm_bwd: unsupported shape B=%d HW=%d C=%d G=%d", B, HW, C, G);
+  PSG_CHECK_ARG(s.cpg % 2 == 0, "psg_groupnorm_bwd: odd channels per group are forward-only (C=%d G=%d)", C, G);
   PSG_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0, "psg_groupnorm_bwd: pitches must be multiples of 8");
   PSG_CHECK_ARG(B <= 65535, "psg_groupnorm_bwd: B too large");
   dim3 grid(s.S, B);

@@ -142,6 +142,32 @@ class Epilogue:
             e.drop_scale = 1.0
 
 
+def _epi_signature(self) -> str:
+    """what the epilogue fuses, for the per-shape profile (tools/profile_step.py --shapes)"""
+    parts = []
+    if self.bias is not None:
+        parts.append("bias")
+    if getattr(self, "rowbias", None) is not None:
+        parts.append("rowbias")
+    if self.act != L.ACT_NONE:
+        parts.append({L.ACT_GELU: "gelu", L.ACT_SILU: "silu"}.get(self.act, f"act{self.act}"))
+    if self.aux_out is not None:
+        parts.append("aux_out")
+    if self.aux_in is not None:
+        parts.append("aux_in")
+    if self.drop_p > 0.0:
+        parts.append("drop")
+    if self.residual is not None:
+        parts.append("res")
+    if self.accumulate:
+        parts.append("acc")
+    parts.append("f32" if self.out.dtype == torch.float32 else "bf16")
+    return "+".join(parts)
+
+
+Epilogue.signature = _epi_signature
+
+
 def plan(a: Operand, b: Operand, block_n: int = 0, m_tiles: int = 0):
     """Tile shape the tcgen05 engine will use for this problem: (block_n, m_tiles, number of output tiles)."""
     d = L.PsgGemmDesc()
@@ -207,4 +233,4 @@ def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", spl
     if prof is not None:
         ev1.record()
         prof.append((ev0, ev1, float(algo_flops) if algo_flops is not None else 2.0 * a.rows * b.rows * a.k, engine,
-                     (a.mode, b.mode, a.rows, b.rows, a.k, split_k)))
+                     (a.mode, b.mode, a.rows, b.rows, a.k, split_k), epi.signature()))

@@ -15,7 +15,7 @@ from typing import Callable, Optional
 
 import torch
 
-from .scheduler import LinearNoiseScheduler, NoiseScheduler
+from .scheduler import DiffusersNoiseScheduler, GradioLinearSchedule, LinearNoiseScheduler, NoiseScheduler
 
 
 class _GraphedUNet:
@@ -93,3 +93,41 @@ def posterior_sample(unet, scheduler: LinearNoiseScheduler, text_emb: torch.Tens
             lat = lat - eps        # reference :202-204 (dead at 50 steps: t never reaches 0)
     unet.train(was_training)
     return lat
+
+
+@torch.no_grad()
+def gradio_sample(unet, schedule: GradioLinearSchedule, text_emb: torch.Tensor, num_inference_steps: int = 50, latent_dim: int = 8,
+                  initial_latent: Optional[torch.Tensor] = None, noise_fn: Optional[Callable[[tuple], torch.Tensor]] = None) -> torch.Tensor:
+    """The demo app's sampling loop (gradio_app.py:297-361): timesteps linspace(T-1, 0, steps) truncated to integers; per step
+    denoise with (1-alpha_t)/sqrt(1-abar_t), then re-noise to the next timestep while it is > 0."""
+    dev = text_emb.device
+    B = text_emb.shape[0]
+    shape = (B, latent_dim, 27, 27)
+    draw = noise_fn if noise_fn is not None else (lambda s: torch.randn(s, device=dev))
+    was_training = getattr(unet, "training", False)
+    if hasattr(unet, "eval"):
+        unet.eval()
+    lat = draw(shape).to(dev) if initial_latent is None else initial_latent.clone()
+    ts = torch.linspace(schedule.num_timesteps - 1, 0, num_inference_steps, dtype=torch.long).tolist()
+    for i, t in enumerate(ts):
+        eps = unet(lat, torch.full((B,), t, device=dev, dtype=torch.long), text_emb)
+        if i < len(ts) - 1:
+            nxt = ts[i + 1]
+            lat = schedule.step(lat, eps, t, nxt, noise=draw(shape).to(dev) if nxt > 0 else None)
+        else:
+            lat = schedule.step(lat, eps, t, None)
+    if hasattr(unet, "train"):
+        unet.train(was_training)
+    return lat
+
+
+@torch.no_grad()
+def text_to_sprite(unet, vae_decoder, text_emb: torch.Tensor, scheduler: Optional[LinearNoiseScheduler] = None,
+                   num_inference_steps: int = 50, use_cuda_graph: bool = True) -> torch.Tensor:
+    """BASELINE config 5 downstream of the text encoder: 50 posterior DDPM steps of the U-Net (FinalPokemonGenerator.forward,
+    src/training/final_trainer.py:183-204), then the VAE decoder to [B, 3, 215, 215], mapped to [0, 1] as `generate_samples` does
+    (src/training/improved_diffusion_trainer.py:598)."""
+    scheduler = scheduler or LinearNoiseScheduler()
+    lat = posterior_sample(unet, scheduler, text_emb, num_inference_steps, use_cuda_graph=use_cuda_graph)
+    img = vae_decoder(lat, text_emb)
+    return torch.clamp((img + 1.0) / 2.0, 0, 1)

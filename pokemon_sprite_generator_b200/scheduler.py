@@ -154,3 +154,93 @@ class LinearNoiseScheduler:
                L.ptr(self.sqrt_one_minus_alphas_cumprod), L.ptr(self.sqrt_posterior_variance), C.c_int(int(timestep)),
                C.c_int(self.num_timesteps), L.stream_ptr())
         return out
+
+
+def _reverse_step(x_t: torch.Tensor, eps: torch.Tensor, noise, mode: int, coef) -> torch.Tensor:
+    x_t = x_t.float().contiguous()
+    eps = eps.float().contiguous()
+    if noise is not None:
+        noise = noise.float().contiguous()
+    out = torch.empty_like(x_t)
+    arr = (C.c_float * 5)(*[float(c) for c in coef] + [0.0] * (5 - len(coef)))
+    L.call("psg_reverse_step", L.ptr(x_t), L.ptr(eps), L.ptr(noise), L.ptr(out), C.c_longlong(x_t.numel()), C.c_int(mode), arr,
+           L.stream_ptr())
+    return out
+
+
+class DiffusersNoiseScheduler:
+    """The scheduler of the reference's diffusers-U-Net trainer (src/training/diffusers_trainer.py:27-100): the clipped-cosine
+    schedule plus a posterior variance whose first entry is copied from the second, and the x0-prediction reverse step
+    `sample_prev_timestep`.  Tables are built with the reference's torch ops in the reference's order (bit-identical on CPU);
+    the step's scalars are evaluated as 0-dim fp32 tensor ops exactly as the reference evaluates them at step time."""
+
+    def __init__(self, num_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02):
+        self.num_timesteps = num_timesteps
+        self.betas = NoiseScheduler._cosine_beta_schedule(num_timesteps, beta_start, beta_end).float()
+        self.alphas = (1.0 - self.betas).float()
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0).float()
+        self.sqrt_alphas_cumprod = torch.sqrt(self.alphas_cumprod).float()
+        self.sqrt_one_minus_alphas_cumprod = torch.sqrt(1.0 - self.alphas_cumprod).float()
+        self.posterior_variance = self.betas * (1.0 - torch.cat([torch.tensor([1.0]), self.alphas_cumprod[:-1]])) / (
+            1.0 - self.alphas_cumprod)
+        self.posterior_variance[0] = self.posterior_variance[1]
+        self.sqrt_alphas_cumprod = torch.clamp(self.sqrt_alphas_cumprod, min=1e-8)
+        self.sqrt_one_minus_alphas_cumprod = torch.clamp(self.sqrt_one_minus_alphas_cumprod, min=1e-8)
+        self._coef = {}
+
+    def to(self, device):
+        return self          # the tables stay on the host: only five scalars per step reach the kernel
+
+    def add_noise(self, x_0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        """reference :59-74 (the NaN/Inf clamp of the result is the caller's finite check here)."""
+        return self._as_cosine().add_noise(x_0, noise, timesteps)      # same tables: the fused q_sample kernel
+
+    def _as_cosine(self):
+        if not hasattr(self, "_cos"):
+            self._cos = NoiseScheduler(self.num_timesteps)
+        return self._cos
+
+    def step_coefficients(self, timestep: int):
+        """(sqrt(1-abar_t), sqrt(abar_t), sqrt(abar_prev), sqrt(1-abar_prev), sqrt(posterior_variance_t)), reference :84-98."""
+        c = self._coef.get(timestep)
+        if c is None:
+            abar_t = self.alphas_cumprod[timestep]
+            abar_prev = self.alphas_cumprod[timestep - 1] if timestep > 0 else torch.tensor(1.0)
+            c = (float(torch.sqrt(1 - abar_t)), float(torch.sqrt(abar_t)), float(torch.sqrt(abar_prev)),
+                 float(torch.sqrt(1 - abar_prev)), float(torch.sqrt(self.posterior_variance[timestep])))
+            self._coef[timestep] = c
+        return c
+
+    def sample_prev_timestep(self, x_t: torch.Tensor, noise_pred: torch.Tensor, timestep: int,
+                             noise: torch.Tensor | None = None) -> torch.Tensor:
+        """reference :76-100.  `noise` defaults to torch.randn_like(x_t) drawn here when timestep > 0, as the reference does."""
+        timestep = int(timestep)
+        if timestep > 0 and noise is None:
+            noise = torch.randn_like(x_t)
+        if timestep <= 0:
+            noise = None
+        return _reverse_step(x_t, noise_pred, noise, 2, self.step_coefficients(timestep))
+
+
+class GradioLinearSchedule:
+    """The linear schedule and the denoise / re-noise step of the reference's demo app (gradio_app.py:281-284, 342-359)."""
+
+    def __init__(self, num_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02):
+        self.num_timesteps = num_timesteps
+        self.betas = torch.linspace(beta_start, beta_end, num_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+
+    def step(self, latent: torch.Tensor, predicted_noise: torch.Tensor, t: int, next_t: int | None,
+             noise: torch.Tensor | None = None) -> torch.Tensor:
+        """One iteration of the loop: denoise at t; if there is a next step with next_t > 0, re-noise to it (drawing
+        torch.randn_like(latent) unless `noise` is given).  next_t = None: the last step."""
+        a_t = self.alphas[int(t)]
+        c0 = float((1 - a_t) / torch.sqrt(1 - self.alphas_cumprod[int(t)]))
+        c1 = float(torch.sqrt(a_t))
+        if next_t is None or int(next_t) <= 0:
+            return _reverse_step(latent, predicted_noise, None, 3, (c0, c1))
+        a_n = self.alphas[int(next_t)]
+        if noise is None:
+            noise = torch.randn_like(latent)
+        return _reverse_step(latent, predicted_noise, noise, 3, (c0, c1, float(torch.sqrt(a_n)), float(torch.sqrt(1 - a_n))))

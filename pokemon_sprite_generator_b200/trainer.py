@@ -12,7 +12,8 @@ What changes underneath:
     folded into the clip coefficient (non-finite gradients skip the update, as the reference skips the batch);
   * data parallelism: one process per GPU, gradients averaged with one all-reduce over the flat buffer;
   * the frozen VAE encoder / text encoder / dataset are out of scope: they are imported from the
-    reference package when it is importable, or injected (`components=`) -- e.g. synthetic latents for benchmarks.
+    reference package when it is importable, or injected (`components=`) -- e.g. synthetic latents for benchmarks;
+    the VAE decoder that `generate_samples` needs is this package's own drop-in (`vae.VAEDecoder`).
 """
 from __future__ import annotations
 
@@ -278,8 +279,8 @@ class DiffusionTrainer:
                                                                         hidden_dim=mc["text_embedding_dim"]).to(self.device).eval()
         if self.vae_encoder is None and self.vae_checkpoint_path is not None:
             enc = self._reference_component("VAEEncoder")(input_channels=3, latent_dim=mc.get("latent_dim", 8)).to(self.device)
-            dec = self._reference_component("VAEDecoder")(latent_dim=mc.get("latent_dim", 8), text_dim=mc["text_embedding_dim"],
-                                                          output_channels=3).to(self.device)
+            from .vae import VAEDecoder      # the drop-in decoder (same state_dict as the reference's): generate_samples on CUDA kernels
+            dec = VAEDecoder(latent_dim=mc.get("latent_dim", 8), text_dim=mc["text_embedding_dim"], output_channels=3).to(self.device)
             ckpt = torch.load(self.vae_checkpoint_path, map_location=self.device)
             if "vae_state_dict" in ckpt:
                 sd = ckpt["vae_state_dict"]

@@ -1,0 +1,248 @@
+"""VAE decoder of the latent-diffusion pipeline: latent [B, 8, 27, 27] + text embeddings -> sprite
+[B, 3, 215, 215], computed by the same sm_100a kernels as the U-Net (tcgen05 implicit-GEMM convolutions, GroupNorm(+SiLU),
+attention, bilinear resize) through the C ABI.  Inference only -- the reference trains the VAE in stage 1, which is outside
+the hot path; here it closes text -> sprite generation (`DiffusionTrainer.generate_samples`, `sampler.text_to_sprite`).
+
+Drop-in for `src/models/vae_decoder.py:VAEDecoder` (:128-222), `ResNetBlock` (:8-31) and `CrossAttentionBlock` (:33-65) of the
+reference: same constructor arguments, module tree, registration order (so `torch.manual_seed(s); VAEDecoder()` draws the same
+initial weights as the reference) and state_dict keys.  The container modules hold parameters only; `VAEDecoder.forward`
+issues the kernel schedule.
+
+Deliberately reproduced quirk (:54-55): K and V of the decoder's cross-attention are `Linear(text)` outputs [B, L, C] RESHAPED
+(not transposed) to [B, heads, head_dim, L] -- per sample the flat [L*C] buffer is re-read as a [C, L] matrix.  Here that is
+one per-sample transpose kernel (`psg_batched_transpose`) in front of the ordinary attention core.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import gemm as G
+from . import ops as K
+
+
+class _Container(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise L.PsgError(f"{type(self).__name__} holds parameters only; run the enclosing VAEDecoder")
+
+
+class ResNetBlock(_Container):
+    """reference vae_decoder.py:8-31 (norm1, conv1, norm2, conv2, dropout, shortcut)."""
+
+    def __init__(self, in_channels: int, out_channels: int, groups: int = 32, dropout: float = 0.0):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, in_channels)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1)
+        self.norm2 = nn.GroupNorm(groups, out_channels)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.dropout = nn.Dropout(dropout)
+        self.shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1) if in_channels != out_channels else nn.Identity()
+
+
+class CrossAttentionBlock(_Container):
+    """reference vae_decoder.py:33-65 (norm, q, k, v, proj)."""
+
+    def __init__(self, channels: int, text_dim: int, num_heads: int = 8):
+        super().__init__()
+        self.channels, self.text_dim, self.num_heads = channels, text_dim, num_heads
+        self.head_dim = channels // num_heads
+        self.norm = nn.GroupNorm(32, channels)
+        self.q = nn.Conv2d(channels, channels, kernel_size=1)
+        self.k = nn.Linear(text_dim, channels)
+        self.v = nn.Linear(text_dim, channels)
+        self.proj = nn.Conv2d(channels, channels, kernel_size=1)
+
+
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+class _Conv:
+    """Kernel-side copy of one Conv2d: tap-major [Cout_p, kk * Cin_p] in the compute dtype (+ fp32 bias [Cout_p]); bf16 mode
+    pads both channel counts to multiples of 64 with zeros so that every layer runs on the tcgen05 engine."""
+
+    def __init__(self, conv: nn.Conv2d, dtype: torch.dtype, device):
+        self.k, self.pad, self.stride = conv.kernel_size[0], conv.padding[0], conv.stride[0]
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        pad = dtype == torch.bfloat16
+        self.cin_p = _pad64(self.cin) if pad else self.cin
+        self.cout_p = _pad64(self.cout) if pad else self.cout
+        self.w = torch.zeros(self.cout_p, self.k * self.k * self.cin_p, dtype=dtype, device=device)
+        K.pack_conv_weight(conv.weight.data.contiguous(), self.w, None, self.cin_p, self.cout_p)
+        self.bias = torch.zeros(1, self.cout_p, dtype=torch.float32, device=device)
+        self.bias[0, :self.cout].copy_(conv.bias.data)          # (one-time weight preparation, not the compute path)
+
+
+class _Lin:
+    def __init__(self, lin: nn.Linear, dtype: torch.dtype, device):
+        n, k = lin.weight.shape
+        self.n, self.kdim = n, k
+        if dtype == torch.bfloat16:
+            self.w = torch.empty(n, k, dtype=dtype, device=device)
+            K.pack_linear_weight(lin.weight.data.contiguous(), self.w, None)
+        else:
+            self.w = lin.weight.data
+        self.bias = lin.bias.data
+
+
+class VAEDecoder(nn.Module):
+    """Text-conditioned VAE decoder, [B, latent_dim, 27, 27] x [B, L, text_dim] -> [B, 3, 215, 215] in [-1, 1].
+
+    Extra (keyword-only, non-reference) argument: compute_dtype torch.bfloat16 (default: tcgen05 tensor cores, fp32 accumulate)
+    or torch.float32 (parity mode on the fp32 CUDA-core engine)."""
+
+    def __init__(self, latent_dim: int = 8, text_dim: int = 256, output_channels: int = 3, *,
+                 compute_dtype: torch.dtype = torch.bfloat16):
+        super().__init__()
+        self.latent_dim, self.text_dim = latent_dim, text_dim
+        self.compute_dtype = compute_dtype
+        self.latent_proj = nn.Conv2d(latent_dim, 512, kernel_size=3, padding=1)
+        self.block1_resnet1 = ResNetBlock(512, 512)
+        self.block1_attn = CrossAttentionBlock(512, text_dim)
+        self.block1_resnet2 = ResNetBlock(512, 512)
+        self.block2_resnet1 = ResNetBlock(512, 256)
+        self.block2_attn = CrossAttentionBlock(256, text_dim)
+        self.block2_resnet2 = ResNetBlock(256, 256)
+        self.block2_upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
+        self.block3_resnet1 = ResNetBlock(256, 128)
+        self.block3_attn = CrossAttentionBlock(128, text_dim)
+        self.block3_resnet2 = ResNetBlock(128, 128)
+        self.block3_upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
+        self.block4_resnet1 = ResNetBlock(128, 64)
+        self.block4_attn = CrossAttentionBlock(64, text_dim)
+        self.block4_resnet2 = ResNetBlock(64, 64)
+        self.block4_upsample = nn.Upsample(size=(215, 215), mode="bilinear", align_corners=False)
+        self.block5_resnet1 = ResNetBlock(64, 32)
+        self.block5_attn = CrossAttentionBlock(32, text_dim)
+        self.block5_resnet2 = ResNetBlock(32, 32)
+        self.final_conv = nn.Sequential(nn.GroupNorm(8, 32), nn.SiLU(), nn.Conv2d(32, output_channels, kernel_size=3, padding=1),
+                                        nn.Tanh())
+        self._packed: Dict[int, object] = {}
+        self._packed_key = None
+
+    # ---- kernel-side weights (re-packed when a parameter changed or moved) ---------------------------------------------
+    def _pack(self, device):
+        key = (str(device), self.compute_dtype, tuple(p._version for p in self.parameters()), tuple(p.data_ptr() for p in self.parameters()))
+        if key == self._packed_key:
+            return
+        dt = self.compute_dtype
+        self._packed = {}
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                self._packed[id(m)] = _Conv(m, dt, device)
+            elif isinstance(m, nn.Linear):
+                self._packed[id(m)] = _Lin(m, dt, device)
+        self._packed_key = key
+
+    # ---- primitives (token-major activations [B*H*W, C_pitch], channels past C are zero) --------------------------------
+    def _conv(self, x, B, H, W, conv: nn.Conv2d, residual=None):
+        c: _Conv = self._packed[id(conv)]
+        assert x.shape[1] == c.cin_p, (x.shape, c.cin_p)
+        out = torch.empty(B * H * W, c.cout_p, dtype=x.dtype, device=x.device)
+        eng = "umma" if x.dtype == torch.bfloat16 else "simt"
+        epi = G.Epilogue(out=out, bias=c.bias[0], residual=residual)
+        if c.k == 1:
+            G.run_gemm(G.kmajor(x), G.kmajor(c.w), epi, engine=eng)
+        else:
+            ld = x.stride(0)
+            x4 = x.as_strided((B, H, W, x.shape[1]), (H * W * ld, W * ld, ld, 1))
+            G.run_gemm(G.im2col(x4, c.k, c.stride, c.pad), G.kmajor(c.w), epi, engine=eng)
+        return out
+
+    def _norm(self, x, B, gn: nn.GroupNorm, silu: bool):
+        Cr = gn.num_channels
+        # padded channels of the result must be zero (finite): the next conv multiplies them by zero weights
+        y = torch.zeros_like(x) if x.shape[1] != Cr else torch.empty_like(x)
+        stats = torch.empty(B, gn.num_groups, 2, dtype=torch.float32, device=x.device)
+        xr, yr = x[:, :Cr], y[:, :Cr]
+        K.groupnorm_fwd(xr, yr, gn.weight.data, gn.bias.data, stats, B, gn.num_groups, gn.eps, silu)
+        return y
+
+    def _resnet(self, x, B, H, W, rb: ResNetBlock):
+        h = self._norm(x, B, rb.norm1, True)
+        h = self._conv(h, B, H, W, rb.conv1)
+        h = self._norm(h, B, rb.norm2, True)          # (dropout p = 0: identity)
+        sc = x if isinstance(rb.shortcut, nn.Identity) else self._conv(x, B, H, W, rb.shortcut)
+        return self._conv(h, B, H, W, rb.conv2, residual=sc)
+
+    def _attn(self, x, B, H, W, ab: CrossAttentionBlock, text_tok, Lt: int):
+        Cc, heads, hd = ab.channels, ab.num_heads, ab.head_dim
+        n = self._norm(x, B, ab.norm, False)
+        q = self._conv(n, B, H, W, ab.q)                         # [B*HW, C_p]; channel c = head * hd + d
+        kl: _Lin = self._packed[id(ab.k)]
+        vl: _Lin = self._packed[id(ab.v)]
+        eng = "umma" if x.dtype == torch.bfloat16 else "simt"
+        kv = []
+        for lin in (kl, vl):
+            y = torch.empty(B * Lt, Cc, dtype=x.dtype, device=x.device)
+            G.run_gemm(G.kmajor(text_tok), G.kmajor(lin.w), G.Epilogue(out=y, bias=lin.bias), engine=eng)
+            # raw reshape [B, L, C] -> [B, heads, hd, L]: per sample the flat buffer re-read as [C, L]; keys/values per token
+            # are the columns of that matrix, i.e. its transpose [L, C]
+            yt = torch.empty(B * Lt, Cc, dtype=x.dtype, device=x.device)
+            L.call("psg_batched_transpose", L.ptr(y), L.ptr(yt), C.c_int(B), C.c_int(Cc), C.c_int(Lt), C.c_int(L.dt(y)), L.stream_ptr())
+            kv.append(yt)
+        o = torch.zeros_like(q) if q.shape[1] != Cc else torch.empty_like(q)
+        hw = H * W
+        if x.dtype == torch.bfloat16 and K.attn_fused_ok(B, heads, hw, Lt, hd):
+            K.attn_fused_fwd(q[:, :Cc], kv[0], kv[1], o[:, :Cc], None, B, heads, hw, Lt, hd)
+        else:
+            K.attn_fwd(q[:, :Cc], kv[0], kv[1], o[:, :Cc], None, B, heads, hw, Lt, hd)
+        return self._conv(o, B, H, W, ab.proj, residual=x)
+
+    def _upsample(self, x, B, H, W, OH, OW):
+        y = torch.empty(B * OH * OW, x.shape[1], dtype=x.dtype, device=x.device)
+        K.upsample_fwd(x, y, B, H, W, OH, OW)
+        return y
+
+    @torch.no_grad()
+    def forward(self, latent: torch.Tensor, text_emb: torch.Tensor) -> torch.Tensor:
+        if not latent.is_cuda:
+            raise L.PsgError("VAEDecoder runs on CUDA only (there is no CPU fallback)")
+        dev, dt = latent.device, self.compute_dtype
+        self._pack(dev)
+        B, Cl, H, W = latent.shape
+        Lt = text_emb.shape[1]
+        lp: _Conv = self._packed[id(self.latent_proj)]
+        x = torch.zeros(B * H * W, lp.cin_p, dtype=dt, device=dev)
+        K.nchw_to_tokens(latent.float().contiguous(), x[:, :Cl])
+        te = text_emb.float().contiguous().view(B * Lt, self.text_dim)
+        if dt == torch.bfloat16:
+            text_tok = torch.empty(B * Lt, self.text_dim, dtype=dt, device=dev)
+            K.cast_bf16(te.view(-1), text_tok.view(-1))
+        else:
+            text_tok = te
+        x = self._conv(x, B, H, W, self.latent_proj)
+        x = self._resnet(x, B, H, W, self.block1_resnet1)
+        x = self._attn(x, B, H, W, self.block1_attn, text_tok, Lt)
+        x = self._resnet(x, B, H, W, self.block1_resnet2)
+        x = self._resnet(x, B, H, W, self.block2_resnet1)
+        x = self._attn(x, B, H, W, self.block2_attn, text_tok, Lt)
+        x = self._resnet(x, B, H, W, self.block2_resnet2)
+        x = self._upsample(x, B, H, W, 2 * H, 2 * W)
+        H, W = 2 * H, 2 * W
+        x = self._resnet(x, B, H, W, self.block3_resnet1)
+        x = self._attn(x, B, H, W, self.block3_attn, text_tok, Lt)
+        x = self._resnet(x, B, H, W, self.block3_resnet2)
+        x = self._upsample(x, B, H, W, 2 * H, 2 * W)
+        H, W = 2 * H, 2 * W
+        x = self._resnet(x, B, H, W, self.block4_resnet1)
+        x = self._attn(x, B, H, W, self.block4_attn, text_tok, Lt)
+        x = self._resnet(x, B, H, W, self.block4_resnet2)
+        OH, OW = self.block4_upsample.size
+        x = self._upsample(x, B, H, W, OH, OW)
+        H, W = OH, OW
+        x = self._resnet(x, B, H, W, self.block5_resnet1)
+        x = self._attn(x, B, H, W, self.block5_attn, text_tok, Lt)
+        x = self._resnet(x, B, H, W, self.block5_resnet2)
+        x = self._norm(x, B, self.final_conv[0], True)
+        x = self._conv(x, B, H, W, self.final_conv[2])
+        cout = self.final_conv[2].out_channels
+        img = torch.empty(B, cout, H, W, dtype=torch.float32, device=dev)
+        K.tokens_to_nchw(x[:, :cout], img)
+        L.call("psg_tanh", L.ptr(img), L.ptr(img), C.c_longlong(img.numel()), L.stream_ptr())
+        return img

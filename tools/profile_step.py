@@ -48,7 +48,7 @@ for name, a, b in calls:
     agg[name][1] += 1
 MODE = {0: "K", 1: "MN", 2: "im2col", 3: "im2colT", 4: "dgrad", 5: "convwT"}
 gagg = collections.defaultdict(lambda: [0.0, 0, 0.0])
-for a, b, fl, eng, (am, bm, M, N, Kd, sp) in gemms:
+for a, b, fl, eng, (am, bm, M, N, Kd, sp), _sig in gemms:
     key = f"gemm:{eng}:{MODE[am]}x{MODE[bm]}"
     gagg[key][0] += a.elapsed_time(b)
     gagg[key][1] += 1
@@ -61,9 +61,10 @@ for ms, k, n, fl in sorted(rows, reverse=True):
 print(f"sum of measured calls: {sum(r[0] for r in rows):.2f} ms")
 if "--shapes" in sys.argv:
     per = collections.defaultdict(lambda: [0.0, 0, 0.0])
-    for a, b, fl, eng, key in gemms:
-        per[(eng,) + key][0] += a.elapsed_time(b)
-        per[(eng,) + key][1] += 1
-        per[(eng,) + key][2] += fl
-    for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:60]:
+    for a, b, fl, eng, key, sig in gemms:
+        kk = (eng, MODE[key[0]] + "x" + MODE[key[1]]) + key[2:5] + (sig,)
+        per[kk][0] += a.elapsed_time(b)
+        per[kk][1] += 1
+        per[kk][2] += fl
+    for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:70]:
         print(f"{v[0]:8.3f} ms n={v[1]:3d} {v[2] / v[0] / 1e9:8.1f} TF/s  {k}")

@@ -285,6 +285,88 @@ def run_sample_mode(args):
         dist.destroy_process_group()
 
 
+def run_sprite_mode(args):
+    """BASELINE config 5 downstream of the text encoder: every rank turns ITS 64 prompts (512 / 8; weak scaling) into sprites with
+    sampler.text_to_sprite -- 50 posterior DDPM steps of the U-Net (CUDA-graph forward) + the VAE decoder to 215 x 215 -- reading
+    host text embeddings and writing the images back to pinned host memory inside the timed region.  Rank 0 prints one JSON line
+    (sprites/s whole job, and the split between the sampling loop and the decoder)."""
+    import torch
+    import torch.distributed as dist
+    from pokemon_sprite_generator_b200 import _lib as L
+    from pokemon_sprite_generator_b200 import parallel, sampler
+    from pokemon_sprite_generator_b200.scheduler import LinearNoiseScheduler
+    from pokemon_sprite_generator_b200.unet import UNet
+    from pokemon_sprite_generator_b200.vae import VAEDecoder
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    L.check(L.load().psg_check_device(), "psg_check_device")
+    per_gpu = args.sprites // 8
+    torch.manual_seed(0)
+    unet = UNet(num_heads=args.heads, compute_dtype=torch.bfloat16).to(dev).eval()
+    dec = VAEDecoder().to(dev).eval()
+    sched = LinearNoiseScheduler()
+    g = torch.Generator(device="cpu").manual_seed(4321)
+    all_text = torch.randn(world * per_gpu, args.text_len, 256, generator=g)
+    host_text = parallel.shard_prompts(all_text).contiguous().pin_memory()
+    host_img = torch.empty(per_gpu, 3, 215, 215).pin_memory()
+    chunk = args.decode_chunk
+
+    def run(steps):
+        text = host_text.to(dev, non_blocking=True)
+        lat = sampler.posterior_sample(unet, sched, text, steps, use_cuda_graph=True)
+        e_mid = torch.cuda.Event(enable_timing=True)
+        e_mid.record()
+        for i in range(0, per_gpu, chunk):       # the decoder's 215 x 215 activations: a chunk of prompts at a time
+            img = torch.clamp((dec(lat[i:i + chunk], text[i:i + chunk]) + 1.0) / 2.0, 0, 1)
+            host_img[i:i + chunk].copy_(img, non_blocking=True)
+        return e_mid
+
+    torch.manual_seed(1000 + rank)
+    run(2)                                        # warm-up: graph capture, weight packing, workspaces
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib = L.load()
+    lib.psg_launch_count.restype = __import__("ctypes").c_longlong
+    lib.psg_launch_count(1)
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e_mid = run(args.sprite_steps)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    t = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(e_mid)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_sample = t.tolist()
+    if rank == 0:
+        line = {"metric": "text_to_sprite_images_per_s", "value": world * per_gpu / (ms / 1e3), "unit": "sprites/s", "n_gpus": world,
+                "steps": 1, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"text-to-sprite (config 5 downstream of the text encoder): {args.sprite_steps} posterior DDPM steps "
+                                       f"(CUDA-graph U-Net forward) + VAE decoder to 215x215, {per_gpu} prompts/GPU ({world * per_gpu} total), "
+                                       f"{args.text_len}x256 synthetic text emb, heads {args.heads}, decoder chunk {chunk}",
+                           "parallelism": f"prompt-sharded x{world}, no communication"},
+                "e2e": {"value": world * per_gpu / (ms / 1e3), "unit": "sprites/s", "h2d_bytes_per_step": host_text.numel() * 4,
+                        "d2h_bytes_per_step": host_img.numel() * 4},
+                "sampling_ms": ms_sample, "decoder_ms": ms - ms_sample, "finite": bool(torch.isfinite(host_img).all()),
+                "image_mean": float(host_img.mean()), "gpu_launches": int(lib.psg_launch_count(0)), "clocks": clk,
+                "note": "launch count: kernels inside graph replays are counted once at capture, not per replay"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
@@ -301,7 +383,10 @@ def main():
     ap.add_argument("--denoise-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true")
-    ap.add_argument("--mode", default="train", choices=["train", "sample"],
+    ap.add_argument("--sprites", type=int, default=512, help="--mode sprite: global prompt batch at 8 GPUs (64 per GPU, weak scaling)")
+    ap.add_argument("--sprite-steps", type=int, default=50, help="--mode sprite: posterior DDPM steps")
+    ap.add_argument("--decode-chunk", type=int, default=16, help="--mode sprite: prompts per VAE-decoder call")
+    ap.add_argument("--mode", default="train", choices=["train", "sample", "sprite"],
                     help="sample: BASELINE config 4 -- full DDPM sampling, prompts sharded over the GPUs with no communication")
     ap.add_argument("--prompts", type=int, default=1024, help="--mode sample: global prompt batch at 8 GPUs (128 per GPU, weak scaling)")
     ap.add_argument("--sample-steps", type=int, default=1000, help="--mode sample: reverse steps (1000 = fast_sampling=False)")
@@ -310,6 +395,8 @@ def main():
         return run_reference_arm(args)
     if args.mode == "sample":
         return run_sample_mode(args)
+    if args.mode == "sprite":
+        return run_sprite_mode(args)
 
     import torch
     import torch.distributed as dist
@@ -388,6 +475,8 @@ def main():
     prof, G.PROFILE = G.PROFILE, None
     clk = clocks.stop()
     launches = int(lib.psg_launch_count(0))
+    from pokemon_sprite_generator_b200 import ops as _K
+    _K.check_kernel_timeouts()       # a bounded in-kernel wait that expired voids the measurement: fail loudly
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

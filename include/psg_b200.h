@@ -5,8 +5,11 @@
  * (pokemon_sprite_generator_b200/{unet,scheduler,trainer}.py) mirrors that contract and binds THIS header through
  * ctypes.  Each entry point below names the reference op(s) it replaces (paths relative to the reference root).
  *
- * Conventions: every function returns 0 (PSG_OK) or a negative error code and never allocates, synchronises or
- * touches global state beyond a kernel-launch counter; `stream` is a cudaStream_t; all pointers are device pointers
+ * Conventions: every function returns 0 (PSG_OK) or a negative error code and never allocates or synchronises (the test
+ * hooks psg_*_timeout_flag excepted); `stream` is a cudaStream_t.  Host-side state: a process-wide kernel-launch counter; per
+ * DEVICE (the calling thread's current device) the registered stream-K workspace and the SM reservation of the tcgen05 GEMM
+ * engine -- one stream at a time may run stream-K GEMMs on a device; and the process-wide measurement / test hooks named as
+ * such below (psg_umma_pairs, psg_umma_debug, psg_attn_fused_split, psg_attn_umma_enable, psg_groupnorm_* tuning); all pointers are device pointers
  * unless noted; the caller owns all memory (workspaces included); psg_last_error() describes the last failure of the
  * calling thread.  dtype: 0 = fp32, 1 = bf16 (activation storage type).  Token-major tensors are [rows, C] with row
  * pitch `ld` in elements (channel slices of wider buffers are valid operands).

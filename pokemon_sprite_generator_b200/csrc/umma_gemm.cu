@@ -987,7 +987,22 @@ extern "C" {
 // [kMaxCtas] slots of 2*128*256 fp32 partial accumulators.
 static constexpr int kMaxCtas = 160;
 static constexpr size_t kSlotBytes = (size_t)2 * 128 * 256 * sizeof(float);
-static void* g_sk_ws = nullptr;
+// Host-side engine state is kept PER DEVICE (indexed by the calling thread's current device), so two devices driven from one
+// process never share a stream-K workspace or an SM reservation.  Within one device the registered workspace serves ONE
+// stream at a time: a caller that wants stream-K GEMMs in flight on several streams of one device must serialise them (this
+// library's engine issues every GEMM on one stream).  g_debug / g_pairs_on are
+// measurement hooks (tools/, tests/), process-wide on purpose.
+static constexpr int kMaxDevices = 32;
+struct DeviceState {
+  void* sk_ws = nullptr;
+  int reserve_sms = 0;
+};
+static DeviceState g_dev[kMaxDevices];
+static DeviceState& dev_state() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_dev[(dev >= 0 && dev < kMaxDevices) ? dev : 0];
+}
 static int g_debug = 0;
 static int g_pairs_on = 1;
 
@@ -1000,10 +1015,10 @@ int psg_umma_max_pairs() { return umma::max_resident_pairs(); }
 int psg_umma_debug(int flags) { g_debug = flags; return PSG_OK; }
 // SMs the persistent grids leave free (for a concurrently running collective's CTAs: parallel.GradSync).  Returns the
 // previous value.
-static int g_reserve_sms = 0;
 int psg_umma_reserve_sms(int n) {
-  const int prev = g_reserve_sms;
-  if (n >= 0) g_reserve_sms = n;
+  DeviceState& ds = dev_state();
+  const int prev = ds.reserve_sms;
+  if (n >= 0) ds.reserve_sms = n;
   return prev;
 }
 
@@ -1013,7 +1028,7 @@ int psg_umma_set_workspace(void* ws, size_t bytes) {
   PSG_CHECK_ARG(ws == nullptr || bytes >= psg_umma_workspace_bytes(), "psg_umma_set_workspace: need %zu bytes, got %zu",
                 psg_umma_workspace_bytes(), bytes);
   PSG_CHECK_ARG(((uintptr_t)ws % 256) == 0, "psg_umma_set_workspace: workspace must be 256B aligned");
-  g_sk_ws = ws;
+  dev_state().sk_ws = ws;
   return PSG_OK;
 }
 
@@ -1082,7 +1097,8 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   // CTA pairs (cta_group::2).  Measured on this model's shapes (profiles/r01_bench_gemm_modes.txt): a gain of 10-25% for
   // the NT (wgrad) reductions when the 2x taller pair tile does not add much row padding, nothing for TN / TT (equal to a
   // single CTA within noise, slightly worse at short K) -- so only the former use them unless forced (psg_umma_pairs(2)).
-  const int free_sms = psg_num_sms() - g_reserve_sms > 8 ? psg_num_sms() - g_reserve_sms : 8;
+  const DeviceState& ds = dev_state();
+  const int free_sms = psg_num_sms() - ds.reserve_sms > 8 ? psg_num_sms() - ds.reserve_sms : 8;
   int cl = 1, units = free_sms;
   if (g_pairs_on && block_n % 128 == 0 && d->M > (long long)BLOCK_M * m_tiles) {
     const long long rows1 = (d->M + BLOCK_M * m_tiles - 1) / (BLOCK_M * m_tiles) * (BLOCK_M * m_tiles);
@@ -1179,9 +1195,9 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
     kp.sk_ctas = (int)sk_ctas;
     kp.sk_units = sk_units;
     if (sk_ctas != sk_tiles) {     // some tile is shared between CTAs
-      PSG_CHECK_ARG(g_sk_ws != nullptr, "psg_umma_gemm: stream-K workspace not registered (psg_umma_set_workspace)");
-      kp.sk_flags = reinterpret_cast<int*>(g_sk_ws);
-      kp.sk_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(g_sk_ws) + 1024);
+      PSG_CHECK_ARG(ds.sk_ws != nullptr, "psg_umma_gemm: stream-K workspace not registered on this device (psg_umma_set_workspace)");
+      kp.sk_flags = reinterpret_cast<int*>(ds.sk_ws);
+      kp.sk_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(ds.sk_ws) + 1024);
     }
   }
   dim3 grid((unsigned)(ctas * cl));

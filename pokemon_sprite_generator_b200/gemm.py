@@ -193,8 +193,8 @@ def _ensure_umma_workspace(device) -> None:
     lib.psg_umma_workspace_bytes.restype = C.c_size_t
     n = lib.psg_umma_workspace_bytes()
     ws = torch.zeros(n, dtype=torch.uint8, device=device)
-    L.check(lib.psg_umma_set_workspace(C.c_void_p(ws.data_ptr()), C.c_size_t(n)), "psg_umma_set_workspace")
-    _umma_ws.clear()
+    with torch.cuda.device(device):      # the library keys the registration by the calling thread's current device
+        L.check(lib.psg_umma_set_workspace(C.c_void_p(ws.data_ptr()), C.c_size_t(n)), "psg_umma_set_workspace")
     _umma_ws[device] = ws
 
 

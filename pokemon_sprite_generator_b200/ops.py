@@ -305,3 +305,14 @@ def cast_bf16(x: torch.Tensor, y: torch.Tensor) -> None:
 
 def scale_inplace(x: torch.Tensor, state: torch.Tensor | None, extra: float = 1.0) -> None:
     L.call("psg_scale_inplace", L.ptr(x), C.c_longlong(x.numel()), L.ptr(state), C.c_float(extra), L.stream_ptr())
+
+
+def check_kernel_timeouts() -> None:
+    """Raises if a bounded in-kernel wait (tcgen05 pipeline barrier, stream-K flag) expired since the last call: the kernels
+    never hang the GPU on a protocol fault, they raise a device flag and fall through with incomplete results -- which must
+    not go unnoticed.  Synchronises the device: call at log points, not per step."""
+    lib = L.load()
+    gemm, attn = int(lib.psg_umma_timeout_flag()), int(lib.psg_attn_umma_timeout_flag())
+    if gemm or attn:
+        raise L.PsgError(f"a bounded barrier wait expired inside a tcgen05 kernel (gemm={gemm}, attention={attn}): results since the "
+                         "last check are not trustworthy")

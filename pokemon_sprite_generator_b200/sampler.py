@@ -42,6 +42,26 @@ class _GraphedUNet:
         return self.out
 
 
+# One captured forward per (U-Net, batch, text length): capturing costs about a second (two warm-up forwards + the capture), which
+# a 50-step text-to-sprite call would otherwise pay every time.  The graph reads the weights in place, so optimiser updates are
+# seen by later replays; re-flattened / re-packed weights (another store version) or another shape re-capture.
+_graph_cache = {}
+
+
+def _graphed_for(unet, x: torch.Tensor, t: torch.Tensor, text: torch.Tensor) -> _GraphedUNet:
+    eng = unet.engine()
+    eng.prepare(x.device)
+    key = (id(unet), tuple(x.shape), tuple(text.shape), str(x.device))
+    g = _graph_cache.get(key)
+    if g is None or g._version != eng.store.version():
+        g = _GraphedUNet(unet, x, t, text)
+        _graph_cache.clear()                      # one resident graph: its private memory pool is a full forward's activations
+        _graph_cache[key] = g
+    else:
+        g.text.copy_(text)
+    return g
+
+
 @torch.no_grad()
 def ddpm_sample(unet, scheduler: NoiseScheduler, text_emb: torch.Tensor, num_samples: int, fast_sampling: bool = True,
                 latent_dim: int = 8, noise_fn: Optional[Callable[[tuple], torch.Tensor]] = None,
@@ -56,7 +76,7 @@ def ddpm_sample(unet, scheduler: NoiseScheduler, text_emb: torch.Tensor, num_sam
     steps = list(range(0, scheduler.num_timesteps, 50)) if fast_sampling else list(range(scheduler.num_timesteps))
     graphed = None
     if use_cuda_graph:
-        graphed = _GraphedUNet(unet, x, torch.zeros(num_samples, dtype=torch.long, device=dev), text_emb.float().contiguous())
+        graphed = _graphed_for(unet, x, torch.zeros(num_samples, dtype=torch.long, device=dev), text_emb.float().contiguous())
     for t in reversed(steps):
         if graphed is not None:
             eps = graphed(x, t)
@@ -83,7 +103,7 @@ def posterior_sample(unet, scheduler: LinearNoiseScheduler, text_emb: torch.Tens
     step = max(1, scheduler.num_timesteps // num_inference_steps)
     graphed = None
     if use_cuda_graph:
-        graphed = _GraphedUNet(unet, lat, torch.zeros(B, dtype=torch.long, device=dev), text_emb.float().contiguous())
+        graphed = _graphed_for(unet, lat, torch.zeros(B, dtype=torch.long, device=dev), text_emb.float().contiguous())
     for i in range(num_inference_steps):
         ts = max(0, scheduler.num_timesteps - 1 - i * step)
         eps = graphed(lat, ts) if graphed is not None else unet(lat, torch.full((B,), ts, device=dev, dtype=torch.long), text_emb)

@@ -390,6 +390,7 @@ class DiffusionTrainer:
             return {"train_loss": float("inf")}
         stacked = torch.stack(losses)
         finite = torch.isfinite(stacked)
+        K.check_kernel_timeouts()      # (synchronises, like the .item() below) a protocol fault inside a kernel must not pass silently
         if not bool(finite.any()):
             return {"train_loss": float("inf")}
         avg = stacked[finite].mean().item()

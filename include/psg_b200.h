@@ -34,6 +34,7 @@ extern "C" {
 #define PSG_ACT_GELU 1
 #define PSG_ACT_SILU 2
 #define PSG_ACT_MUL 3   /* aux_in only: multiply by the stored value (a derivative saved by the forward epilogue) */
+#define PSG_ACT_RELU 4  /* forward only (VAE encoder stem) */
 #define PSG_OP_KMAJOR 0
 #define PSG_OP_MNMAJOR 1
 #define PSG_OP_IM2COL 2
@@ -107,6 +108,11 @@ int psg_smooth_l1_fwd_bwd(const float* pred, const float* target, float* dpred, 
                           float beta, float grad_scale, void* stream);
 int psg_ddpm_step(const float* x, const float* eps, const float* z, float* out, long long n, int mode, const float* tab0,
                   const float* tab1, const float* tab2, const float* tab3, int t, int num_t, void* stream);
+
+/* VAE reparameterisation out = mu + eps * exp(0.5 * logvar) [clamped to [lo, hi]]: src/models/vae_decoder.py:119-123 followed by the
+ * trainer's clamp (src/training/improved_diffusion_trainer.py:363); the latent cache samples with it every epoch */
+int psg_reparam(const float* mu, const float* logvar, const float* eps, float* out, long long n, int do_clamp, float lo, float hi,
+                void* stream);
 
 /* the reference's two other reverse-step formulas: mode 2 = src/training/diffusers_trainer.py:76-100, mode 3 = gradio_app.py:324-361;
  * coef5 is a HOST array of the per-step scalars evaluated as the reference evaluates them (see csrc/diffusion_ops.cu) */

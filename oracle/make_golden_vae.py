@@ -7,6 +7,8 @@ Outputs:
   tests/golden/vae_decoder.pt     seed-0 initialisation checksums of the reference VAEDecoder, and its output for seeded latents /
                                   text embeddings: the full image for one sample + strided samples and statistics for a batch of 2
                                   at another text length (src/models/vae_decoder.py:128-222)
+  tests/golden/vae_encoder.pt     the same for the reference VAEEncoder (src/models/vae_decoder.py:68-125): (latent, mu, logvar) with the
+                                  reparameterisation noise pinned by a seed
   tests/golden/reverse_steps.npz  src/training/diffusers_trainer.py:76-100 (`sample_prev_timestep`) single steps and a 30-step loop,
                                   gradio_app.py:297-361 (`ddpm_sample`) 20- and 50-step loops with a stub U-Net, and the schedule
                                   tables both use
@@ -47,10 +49,10 @@ def _load_extra():
         m.__dict__.update(Blocks=_Any(), themes=_Any())
         m.__path__ = []
         sys.modules["gradio"] = m
-    from src.models.vae_decoder import VAEDecoder  # type: ignore
+    from src.models.vae_decoder import VAEDecoder, VAEEncoder  # type: ignore
     from src.training import diffusers_trainer  # type: ignore
     import gradio_app  # type: ignore
-    return VAEDecoder, diffusers_trainer.NoiseScheduler, gradio_app.PokemonGradioGenerator
+    return VAEDecoder, diffusers_trainer.NoiseScheduler, gradio_app.PokemonGradioGenerator, VAEEncoder
 
 
 def vae_inputs(batch: int, text_len: int, seed: int):
@@ -83,6 +85,32 @@ def vae_golden(VAEDecoder):
         print(f"vae {name}: b1 |y|max={y.abs().max():.4f} std={y.std():.4f}; b2 std={y2.std():.4f}", flush=True)
     torch.save(golden, OUT / "vae_decoder.pt")
     print("wrote vae_decoder.pt")
+
+
+def encoder_inputs(batch: int, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, 3, 215, 215, generator=g) * 0.5
+
+
+def encoder_golden(VAEEncoder):
+    """src/models/vae_decoder.py:68-125: (latent, mu, logvar) of the seed-0 reference encoder and of an O(1)-gain state; the
+    reparameterisation noise is the first draw after torch.manual_seed(55) (the encoder draws nothing else in eval mode)."""
+    torch.manual_seed(0)
+    enc = VAEEncoder(input_channels=3, latent_dim=8).eval()
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    golden = {"checksums": {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in sd.items()},
+              "shapes": {k: tuple(v.shape) for k, v in sd.items()}, "num_params": sum(p.numel() for p in enc.parameters()),
+              "amp_seed": 12, "noise_seed": 55, "cases": {}}
+    for name, state in (("init", sd), ("amp", amplified_vae_state(sd, 12))):
+        enc.load_state_dict(state)
+        img = encoder_inputs(2, 888)
+        torch.manual_seed(55)
+        with torch.no_grad():
+            lat, mu, lv = enc(img)
+        golden["cases"][name] = {"batch": 2, "seed": 888, "latent": lat.clone(), "mu": mu.clone(), "logvar": lv.clone()}
+        print(f"encoder {name}: mu std {mu.std():.4f} logvar std {lv.std():.4f} latent std {lat.std():.4f}", flush=True)
+    torch.save(golden, OUT / "vae_encoder.pt")
+    print("wrote vae_encoder.pt")
 
 
 def amplified_vae_state(sd, seed: int = 11):
@@ -134,9 +162,11 @@ def reverse_golden(DiffSched, Gradio):
 def main():
     torch.set_num_threads(8)
     OUT.mkdir(parents=True, exist_ok=True)
-    VAEDecoder, DiffSched, Gradio = _load_extra()
-    reverse_golden(DiffSched, Gradio)
-    vae_golden(VAEDecoder)
+    VAEDecoder, DiffSched, Gradio, VAEEncoder = _load_extra()
+    if "--encoder-only" not in sys.argv:
+        reverse_golden(DiffSched, Gradio)
+        vae_golden(VAEDecoder)
+    encoder_golden(VAEEncoder)
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ from pathlib import Path
 import torch
 
 DT_F32, DT_BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_SILU, ACT_MUL = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_SILU, ACT_MUL, ACT_RELU = 0, 1, 2, 3, 4
 OP_KMAJOR, OP_MNMAJOR, OP_IM2COL, OP_IM2COL_T, OP_DGRAD, OP_CONVW_T = 0, 1, 2, 3, 4, 5
 
 _TORCH_DT = {torch.float32: DT_F32, torch.bfloat16: DT_BF16}

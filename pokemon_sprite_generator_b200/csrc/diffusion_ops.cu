@@ -241,6 +241,26 @@ reverse_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, 
   }
 }
 
+__global__ void __launch_bounds__(kThreads)
+reparam_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, const float* __restrict__ eps, float* __restrict__ out,
+               size_t n, int do_clamp, float lo, float hi) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+    const float sd = expf(__fmul_rn(0.5f, logvar[i]));
+    float v = __fadd_rn(mu[i], __fmul_rn(eps[i], sd));
+    if (do_clamp) v = fminf(fmaxf(v, lo), hi);
+    out[i] = v;
+  }
+}
+
+int psg_reparam(const float* mu, const float* logvar, const float* eps, float* out, long long n, int do_clamp, float lo, float hi,
+                void* stream) {
+  if (n <= 0) return PSG_OK;
+  PSG_CHECK_ARG(mu && logvar && eps && out, "psg_reparam: null pointer");
+  reparam_kernel<<<grid_for((size_t)n, psg_num_sms() * 8), kThreads, 0, (cudaStream_t)stream>>>(mu, logvar, eps, out, (size_t)n, do_clamp, lo, hi);
+  PSG_CHECK_LAUNCH("psg_reparam");
+  return PSG_OK;
+}
+
 int psg_reverse_step(const float* x, const float* eps, const float* z, float* out, long long n, int mode, const float* coef5,
                      void* stream) {
   if (n <= 0) return PSG_OK;

@@ -4,7 +4,7 @@
 //   v   = acc + bias[n] + rowbias[(m / rows_per_group) * ld_rowbias + n]
 //   (aux_out[m,n] = v)                       -- optional pre-activation store, activation dtype            [aux_act == NONE]
 //   (aux_out[m,n] = act'(v) * dropmask * keep_scale)  -- or the saved local derivative of act+dropout     [aux_act != NONE]
-//   v   = act(v)                             -- none | gelu(erf) | silu
+//   v   = act(v)                             -- none | gelu(erf) | silu | relu (forward only)
 //   v  *= act'(aux_in[m,n])                  -- optional, backward of a fused activation; aux_act == PSG_ACT_MUL: v *= aux_in
 //   v   = dropout(v; seed, threshold) * keep_scale
 //   v   = alpha * v + residual[m,n]          -- residual in activation dtype, may alias out
@@ -20,6 +20,7 @@
 #define PSG_ACT_GELU 1
 #define PSG_ACT_SILU 2
 #define PSG_ACT_MUL 3      // aux_in only: multiply by the stored value itself (a derivative saved by the forward epilogue)
+#define PSG_ACT_RELU 4     // forward only (the VAE encoder's stem, src/models/vae_decoder.py:77-88); no saved derivative
 
 struct PsgEpilogue {
   void* out;               // [M, ldc]
@@ -67,6 +68,7 @@ __device__ __forceinline__ void psg_epilogue_scalar(const PsgEpilogue& e, float 
   }
   if (e.act == PSG_ACT_GELU) v = psg_gelu(v);
   else if (e.act == PSG_ACT_SILU) v = psg_silu(v);
+  else if (e.act == PSG_ACT_RELU) v = fmaxf(v, 0.f);
   if (e.aux_in) {
     float a = psg_epi_load_act(e.aux_in, e.act_dtype, m * e.ld_aux + n);
     v *= (e.aux_act == PSG_ACT_GELU) ? psg_gelu_grad(a) : (e.aux_act == PSG_ACT_SILU ? psg_silu_grad(a) : (e.aux_act == PSG_ACT_MUL ? a : 1.f));

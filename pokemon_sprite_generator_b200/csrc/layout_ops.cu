@@ -615,10 +615,18 @@ int psg_mean_pool(const float* x, float* out, int B, int L, int D, void* stream)
 int psg_pack_conv_weight(const float* w, void* wp, void* wd, int Cout, int Cin, int kk, int Cin_p, int Cout_p, int dtype,
                          void* stream) {
   PSG_CHECK_ARG(w && (wp || wd) && Cout > 0 && Cin > 0 && kk > 0 && Cin_p >= Cin && Cout_p >= Cout, "psg_pack_conv_weight: bad args");
-  PSG_CHECK_ARG(kk <= 9, "psg_pack_conv_weight: kernel area > 9 unsupported");
+  PSG_CHECK_ARG(kk <= 25, "psg_pack_conv_weight: kernel area > 25 unsupported");
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
   PSG_CHECK_ARG(grid.y <= 65535, "psg_pack_conv_weight: Cout too large");
   const size_t smem = (size_t)32 * (32 * kk + 1) * sizeof(float);
+  if (smem > 48 * 1024) {      // 4x4 / 5x5 kernels (the VAE encoder's stride-2 stem): opt in to the larger tile once
+    static bool done = false;
+    if (!done) {
+      cudaFuncSetAttribute(pack_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (32 * 25 + 1) * 4);
+      cudaFuncSetAttribute(pack_conv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (32 * 25 + 1) * 4);
+      done = true;
+    }
+  }
   DISPATCH_T(dtype, (pack_conv_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (T*)wp, (T*)wd, Cout, Cin, kk, Cin_p, Cout_p)));
   PSG_CHECK_LAUNCH("psg_pack_conv_weight");
   return PSG_OK;

@@ -421,6 +421,9 @@ __device__ __forceinline__ void epilogue_chunk(const PsgEpilogue& e, const uint3
   } else if (e.act == PSG_ACT_SILU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = psg_silu_fast(v[j]);
+  } else if (e.act == PSG_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (e.aux_in) {
     float a[32];

@@ -13,7 +13,9 @@ What changes underneath:
   * data parallelism: one process per GPU, gradients averaged with one all-reduce over the flat buffer;
   * the frozen VAE encoder / text encoder / dataset are out of scope: they are imported from the
     reference package when it is importable, or injected (`components=`) -- e.g. synthetic latents for benchmarks;
-    the VAE decoder that `generate_samples` needs is this package's own drop-in (`vae.VAEDecoder`).
+    the VAE decoder that `generate_samples` needs and the VAE encoder are this package's own drop-ins (`vae.VAEDecoder`,
+    `vae.VAEEncoder`); `config['data']['latent_cache'] = True` encodes the training set once
+    (`vae.LatentCache`) instead of re-encoding every image every epoch.
 """
 from __future__ import annotations
 
@@ -278,8 +280,8 @@ class DiffusionTrainer:
             self.text_encoder = self._reference_component("TextEncoder")(model_name=mc["bert_model"],
                                                                         hidden_dim=mc["text_embedding_dim"]).to(self.device).eval()
         if self.vae_encoder is None and self.vae_checkpoint_path is not None:
-            enc = self._reference_component("VAEEncoder")(input_channels=3, latent_dim=mc.get("latent_dim", 8)).to(self.device)
-            from .vae import VAEDecoder      # the drop-in decoder (same state_dict as the reference's): generate_samples on CUDA kernels
+            from .vae import VAEDecoder, VAEEncoder      # drop-ins (same state_dicts as the reference's), on the CUDA kernels
+            enc = VAEEncoder(input_channels=3, latent_dim=mc.get("latent_dim", 8), compute_dtype=torch.float32).to(self.device)
             dec = VAEDecoder(latent_dim=mc.get("latent_dim", 8), text_dim=mc["text_embedding_dim"], output_channels=3).to(self.device)
             ckpt = torch.load(self.vae_checkpoint_path, map_location=self.device)
             if "vae_state_dict" in ckpt:
@@ -313,6 +315,12 @@ class DiffusionTrainer:
             val_split=dc["val_split"], test_split=dc["test_split"], image_size=dc["image_size"],
             num_workers=uc.get("num_workers", dc["num_workers"]), pin_memory=dc["pin_memory"])
         self.data_loaders = {"train": tr, "val": va, "test": te}
+        if dc.get("latent_cache", False) and self.vae_encoder is not None and self.text_encoder is not None:
+            # encode the training set ONCE; every epoch re-samples latents from the cached (mu, logvar) on the device (vae.LatentCache)
+            from .vae import LatentCache
+            bs = uc.get("batch_size", dc["batch_size"])
+            self.data_loaders["train"] = LatentCache.build(tr, self.vae_encoder, self.text_encoder, self.device, bs, shuffle=True)
+            self.logger.info(f"latent cache: {self.data_loaders['train'].mu.shape[0]} training images encoded once")
 
     def setup_optimization(self):
         uc = self.config.get("unet_optimization", {})

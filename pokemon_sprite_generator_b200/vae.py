@@ -1,7 +1,11 @@
-"""VAE decoder of the latent-diffusion pipeline: latent [B, 8, 27, 27] + text embeddings -> sprite
-[B, 3, 215, 215], computed by the same sm_100a kernels as the U-Net (tcgen05 implicit-GEMM convolutions, GroupNorm(+SiLU),
-attention, bilinear resize) through the C ABI.  Inference only -- the reference trains the VAE in stage 1, which is outside
-the hot path; here it closes text -> sprite generation (`DiffusionTrainer.generate_samples`, `sampler.text_to_sprite`).
+"""The VAE either side of the latent-diffusion hot path, computed by the same sm_100a kernels as the
+U-Net (tcgen05 implicit-GEMM convolutions, GroupNorm(+SiLU), attention, bilinear resize) through the C ABI.  Inference only --
+the reference trains the VAE in stage 1, which is outside the hot path:
+  * VAEDecoder: latent [B, 8, 27, 27] + text embeddings -> sprite [B, 3, 215, 215]; closes text -> sprite generation
+    (`DiffusionTrainer.generate_samples`, `sampler.text_to_sprite`);
+  * VAEEncoder: image [B, 3, 215, 215] -> (latent, mu, logvar); LatentCache encodes a dataset ONCE (mu, logvar stay on the GPU) and
+    re-samples latents on the device every epoch, instead of re-encoding every image every epoch as stage 2 of the reference
+    does (src/training/improved_diffusion_trainer.py:357-363).
 
 Drop-in for `src/models/vae_decoder.py:VAEDecoder` (:128-222), `ResNetBlock` (:8-31) and `CrossAttentionBlock` (:33-65) of the
 reference: same constructor arguments, module tree, registration order (so `torch.manual_seed(s); VAEDecoder()` draws the same
@@ -90,38 +94,12 @@ class _Lin:
         self.bias = lin.bias.data
 
 
-class VAEDecoder(nn.Module):
-    """Text-conditioned VAE decoder, [B, latent_dim, 27, 27] x [B, L, text_dim] -> [B, 3, 215, 215] in [-1, 1].
+class _KernelNet(nn.Module):
+    """Kernel-side weight copies and the token-major primitives shared by the decoder and the encoder."""
 
-    Extra (keyword-only, non-reference) argument: compute_dtype torch.bfloat16 (default: tcgen05 tensor cores, fp32 accumulate)
-    or torch.float32 (parity mode on the fp32 CUDA-core engine)."""
+    compute_dtype = torch.bfloat16
 
-    def __init__(self, latent_dim: int = 8, text_dim: int = 256, output_channels: int = 3, *,
-                 compute_dtype: torch.dtype = torch.bfloat16):
-        super().__init__()
-        self.latent_dim, self.text_dim = latent_dim, text_dim
-        self.compute_dtype = compute_dtype
-        self.latent_proj = nn.Conv2d(latent_dim, 512, kernel_size=3, padding=1)
-        self.block1_resnet1 = ResNetBlock(512, 512)
-        self.block1_attn = CrossAttentionBlock(512, text_dim)
-        self.block1_resnet2 = ResNetBlock(512, 512)
-        self.block2_resnet1 = ResNetBlock(512, 256)
-        self.block2_attn = CrossAttentionBlock(256, text_dim)
-        self.block2_resnet2 = ResNetBlock(256, 256)
-        self.block2_upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
-        self.block3_resnet1 = ResNetBlock(256, 128)
-        self.block3_attn = CrossAttentionBlock(128, text_dim)
-        self.block3_resnet2 = ResNetBlock(128, 128)
-        self.block3_upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
-        self.block4_resnet1 = ResNetBlock(128, 64)
-        self.block4_attn = CrossAttentionBlock(64, text_dim)
-        self.block4_resnet2 = ResNetBlock(64, 64)
-        self.block4_upsample = nn.Upsample(size=(215, 215), mode="bilinear", align_corners=False)
-        self.block5_resnet1 = ResNetBlock(64, 32)
-        self.block5_attn = CrossAttentionBlock(32, text_dim)
-        self.block5_resnet2 = ResNetBlock(32, 32)
-        self.final_conv = nn.Sequential(nn.GroupNorm(8, 32), nn.SiLU(), nn.Conv2d(32, output_channels, kernel_size=3, padding=1),
-                                        nn.Tanh())
+    def _init_packing(self):
         self._packed: Dict[int, object] = {}
         self._packed_key = None
 
@@ -140,12 +118,14 @@ class VAEDecoder(nn.Module):
         self._packed_key = key
 
     # ---- primitives (token-major activations [B*H*W, C_pitch], channels past C are zero) --------------------------------
-    def _conv(self, x, B, H, W, conv: nn.Conv2d, residual=None):
+    def _conv(self, x, B, H, W, conv: nn.Conv2d, residual=None, act=L.ACT_NONE):
         c: _Conv = self._packed[id(conv)]
         assert x.shape[1] == c.cin_p, (x.shape, c.cin_p)
-        out = torch.empty(B * H * W, c.cout_p, dtype=x.dtype, device=x.device)
+        P = (H + 2 * c.pad - c.k) // c.stride + 1
+        Q = (W + 2 * c.pad - c.k) // c.stride + 1
+        out = torch.empty(B * P * Q, c.cout_p, dtype=x.dtype, device=x.device)
         eng = "umma" if x.dtype == torch.bfloat16 else "simt"
-        epi = G.Epilogue(out=out, bias=c.bias[0], residual=residual)
+        epi = G.Epilogue(out=out, bias=c.bias[0], residual=residual, act=act)
         if c.k == 1:
             G.run_gemm(G.kmajor(x), G.kmajor(c.w), epi, engine=eng)
         else:
@@ -199,6 +179,41 @@ class VAEDecoder(nn.Module):
         K.upsample_fwd(x, y, B, H, W, OH, OW)
         return y
 
+
+class VAEDecoder(_KernelNet):
+    """Text-conditioned VAE decoder, [B, latent_dim, 27, 27] x [B, L, text_dim] -> [B, 3, 215, 215] in [-1, 1].
+
+    Extra (keyword-only, non-reference) argument: compute_dtype torch.bfloat16 (default: tcgen05 tensor cores, fp32 accumulate)
+    or torch.float32 (parity mode on the fp32 CUDA-core engine)."""
+
+    def __init__(self, latent_dim: int = 8, text_dim: int = 256, output_channels: int = 3, *,
+                 compute_dtype: torch.dtype = torch.bfloat16):
+        super().__init__()
+        self.latent_dim, self.text_dim = latent_dim, text_dim
+        self.compute_dtype = compute_dtype
+        self.latent_proj = nn.Conv2d(latent_dim, 512, kernel_size=3, padding=1)
+        self.block1_resnet1 = ResNetBlock(512, 512)
+        self.block1_attn = CrossAttentionBlock(512, text_dim)
+        self.block1_resnet2 = ResNetBlock(512, 512)
+        self.block2_resnet1 = ResNetBlock(512, 256)
+        self.block2_attn = CrossAttentionBlock(256, text_dim)
+        self.block2_resnet2 = ResNetBlock(256, 256)
+        self.block2_upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
+        self.block3_resnet1 = ResNetBlock(256, 128)
+        self.block3_attn = CrossAttentionBlock(128, text_dim)
+        self.block3_resnet2 = ResNetBlock(128, 128)
+        self.block3_upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
+        self.block4_resnet1 = ResNetBlock(128, 64)
+        self.block4_attn = CrossAttentionBlock(64, text_dim)
+        self.block4_resnet2 = ResNetBlock(64, 64)
+        self.block4_upsample = nn.Upsample(size=(215, 215), mode="bilinear", align_corners=False)
+        self.block5_resnet1 = ResNetBlock(64, 32)
+        self.block5_attn = CrossAttentionBlock(32, text_dim)
+        self.block5_resnet2 = ResNetBlock(32, 32)
+        self.final_conv = nn.Sequential(nn.GroupNorm(8, 32), nn.SiLU(), nn.Conv2d(32, output_channels, kernel_size=3, padding=1),
+                                        nn.Tanh())
+        self._init_packing()
+
     @torch.no_grad()
     def forward(self, latent: torch.Tensor, text_emb: torch.Tensor) -> torch.Tensor:
         if not latent.is_cuda:
@@ -246,3 +261,117 @@ class VAEDecoder(nn.Module):
         K.tokens_to_nchw(x[:, :cout], img)
         L.call("psg_tanh", L.ptr(img), L.ptr(img), C.c_longlong(img.numel()), L.stream_ptr())
         return img
+
+
+class VAEEncoder(_KernelNet):
+    """Image encoder, [B, 3, 215, 215] -> (latent, mu, logvar) each [B, latent_dim, 27, 27]: drop-in for
+    src/models/vae_decoder.py:VAEEncoder (:68-125) -- same `encoder` Sequential (indices included), `mu_proj`, `logvar_proj`,
+    same registration order / initialisation / state_dict keys.  The reparameterisation noise is drawn with torch.randn_like on the
+    device generator at the point the reference draws it (:121-122); `noise=` overrides it (parity tests)."""
+
+    def __init__(self, input_channels: int = 3, latent_dim: int = 8, *, compute_dtype: torch.dtype = torch.bfloat16):
+        super().__init__()
+        self.latent_dim = latent_dim
+        self.compute_dtype = compute_dtype
+        self.encoder = nn.Sequential(
+            nn.Conv2d(input_channels, 32, kernel_size=4, stride=2, padding=1), nn.ReLU(), ResNetBlock(32, 32),
+            nn.Conv2d(32, 64, kernel_size=4, stride=2, padding=1), nn.ReLU(), ResNetBlock(64, 64),
+            nn.Conv2d(64, 128, kernel_size=4, stride=2, padding=2), nn.ReLU(), ResNetBlock(128, 128),
+            ResNetBlock(128, 256), ResNetBlock(256, 256), ResNetBlock(256, 512), ResNetBlock(512, 512))
+        self.mu_proj = nn.Conv2d(512, latent_dim, kernel_size=3, padding=1)
+        self.logvar_proj = nn.Conv2d(512, latent_dim, kernel_size=3, padding=1)
+        self._init_packing()
+
+    @torch.no_grad()
+    def moments(self, images: torch.Tensor):
+        """(mu, logvar), fp32 NCHW: everything of `forward` up to the reparameterisation."""
+        if not images.is_cuda:
+            raise L.PsgError("VAEEncoder runs on CUDA only (there is no CPU fallback)")
+        dev, dt = images.device, self.compute_dtype
+        self._pack(dev)
+        B, Ci, H, W = images.shape
+        first: _Conv = self._packed[id(self.encoder[0])]
+        x = torch.zeros(B * H * W, first.cin_p, dtype=dt, device=dev)
+        K.nchw_to_tokens(images.float().contiguous(), x[:, :Ci])
+        for m in self.encoder:
+            if isinstance(m, nn.Conv2d):
+                c: _Conv = self._packed[id(m)]
+                x = self._conv(x, B, H, W, m, act=L.ACT_RELU)            # every stem conv is followed by nn.ReLU (:77-88)
+                H = (H + 2 * c.pad - c.k) // c.stride + 1
+                W = (W + 2 * c.pad - c.k) // c.stride + 1
+            elif isinstance(m, ResNetBlock):
+                x = self._resnet(x, B, H, W, m)
+        out = []
+        for proj in (self.mu_proj, self.logvar_proj):
+            y = self._conv(x, B, H, W, proj)
+            t = torch.empty(B, self.latent_dim, H, W, dtype=torch.float32, device=dev)
+            K.tokens_to_nchw(y[:, :self.latent_dim], t)
+            out.append(t)
+        return out[0], out[1]
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        mu, logvar = self.moments(x)
+        eps = torch.randn_like(mu) if noise is None else noise.to(mu.device).float().contiguous()
+        return reparameterize(mu, logvar, eps), mu, logvar
+
+
+def reparameterize(mu: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor, clamp: Optional[float] = None) -> torch.Tensor:
+    """mu + eps * exp(0.5 * logvar) (reference vae_decoder.py:119-123), optionally clamped to [-clamp, clamp] as the stage-2 trainer
+    clamps the latent before noising it (improved_diffusion_trainer.py:363): one kernel."""
+    mu, logvar, eps = mu.float().contiguous(), logvar.float().contiguous(), eps.float().contiguous()
+    out = torch.empty_like(mu)
+    L.call("psg_reparam", L.ptr(mu), L.ptr(logvar), L.ptr(eps), L.ptr(out), C.c_longlong(mu.numel()), C.c_int(int(clamp is not None)),
+           C.c_float(-(clamp or 0.0)), C.c_float(clamp or 0.0), L.stream_ptr())
+    return out
+
+
+class LatentCache:
+    """Pre-encoded training set for stage 2.  The reference re-encodes every image with the frozen VAE encoder
+    (and re-runs the frozen text encoder) every epoch (improved_diffusion_trainer.py:346-363); the encoder's output depends on the
+    image only through (mu, logvar), so those -- and the text embeddings -- are computed ONCE and kept on the GPU, and each epoch's
+    latents are a fresh reparameterisation sample drawn on the device.  Yields the pre-encoded `{'latent', 'text_emb'}` batches
+    `DiffusionTrainer` accepts, so neither encoder nor the image DataLoader sits in the training loop.
+
+    Statistically identical to the reference loop (fresh eps per image per epoch, same clamp is applied by the trainer); the draw
+    ORDER differs (one randn per batch here, one inside each encoder call there), which no test of the reference pins."""
+
+    def __init__(self, mu: torch.Tensor, logvar: torch.Tensor, text_emb: torch.Tensor, batch_size: int, shuffle: bool = True,
+                 drop_last: bool = False, generator: Optional[torch.Generator] = None):
+        assert mu.shape == logvar.shape and mu.shape[0] == text_emb.shape[0]
+        self.mu, self.logvar, self.text_emb = mu.float().contiguous(), logvar.float().contiguous(), text_emb.float().contiguous()
+        self.batch_size, self.shuffle, self.drop_last, self.generator = batch_size, shuffle, drop_last, generator
+
+    @classmethod
+    @torch.no_grad()
+    def build(cls, loader, vae_encoder, text_encoder, device, batch_size: int, **kw) -> "LatentCache":
+        """One pass over an image loader of the reference's format ({'image', 'full_description'} batches).  It runs once per
+        dataset: prefer an fp32-mode encoder here (`VAEEncoder(compute_dtype=torch.float32)`: (mu, logvar) within 2e-5 of the
+        reference; bf16 mode is within ~1 % of their spread)."""
+        mus, lvs, txts = [], [], []
+        for batch in loader:
+            img = batch["image"].to(device)
+            if hasattr(vae_encoder, "moments"):
+                mu, lv = vae_encoder.moments(img)
+            else:                                   # a reference-style encoder: (latent, mu, logvar)
+                _, mu, lv = vae_encoder(img)
+            mus.append(mu.float())
+            lvs.append(lv.float())
+            txts.append(text_encoder(batch["full_description"]).float().to(device))
+        width = max(t.shape[1] for t in txts)      # descriptions are padded per batch: pad the cache to the longest
+        txts = [torch.nn.functional.pad(t, (0, 0, 0, width - t.shape[1])) for t in txts]
+        return cls(torch.cat(mus), torch.cat(lvs), torch.cat(txts), batch_size, **kw)
+
+    def __len__(self) -> int:
+        n = self.mu.shape[0]
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = self.mu.shape[0]
+        dev = self.mu.device
+        order = torch.randperm(n, generator=self.generator).to(dev) if self.shuffle else torch.arange(n, device=dev)
+        for i in range(len(self)):
+            idx = order[i * self.batch_size:(i + 1) * self.batch_size]
+            mu, lv = self.mu[idx], self.logvar[idx]
+            eps = torch.randn_like(mu)
+            yield {"latent": reparameterize(mu, lv, eps), "text_emb": self.text_emb[idx]}

@@ -145,6 +145,16 @@ int psg_attn_umma_bwd(const void* q, long long ldq, const void* k, long long ldk
                       void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Lq, int Lk, int hd, float scale,
                       unsigned long long drop_seed, float drop_p, void* stream);
 
+/* ---- text encoder pieces (src/models/text_encoder.py:137-163: BertModel -> projection -> LayerNorm) ----------------------------- */
+int psg_layernorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta, long long rows, int D,
+                  float eps, int in_dtype, int out_dtype, void* stream);
+int psg_bert_embed(const long long* ids, const long long* type_ids, const float* word, const float* pos, const float* type, float* out,
+                   long long rows, int L, int D, int vocab, void* stream);
+/* psg_attn_fwd with a per-sample number of valid keys (BERT's padding mask); key_len: device int32 [B], nullable */
+int psg_attn_fwd_keylen(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                        long long ldo, float* lse, const int* key_len, int B, int H, int Lq, int Lk, int hd, float scale, int dtype,
+                        unsigned long long drop_seed, float drop_p, void* stream);
+
 /* ---- GroupNorm (+SiLU)  nn.GroupNorm + F.silu, src/models/unet.py:79,89,115,127,156-157,214,231,397-398 ---------- */
 int psg_groupnorm_slices(int B, int HW);
 int psg_groupnorm_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,

@@ -49,6 +49,7 @@ struct Params {
   float* dsum;             // [B, H, Lq]  D_i = dO_i . O_i
   void *dq, *dk, *dv;
   long long lddq, lddk, lddv;
+  const int* key_len;      // forward only, nullable: [B] number of valid keys per sample (a padding mask that is a suffix)
 };
 
 __device__ __forceinline__ bool keep(const Params& p, int b, int h, int i, int j) {
@@ -128,8 +129,9 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(Params p) {
 #pragma unroll
       for (int e = 0; e < EPW; ++e) acc[w][e] = 0.f;
 
-    for (int c0 = 0; c0 < p.Lk; c0 += p.kc) {
-      const int nk = min(p.kc, p.Lk - c0);
+    const int Lk_eff = p.key_len ? max(1, min(p.Lk, p.key_len[b])) : p.Lk;      // keys past a sample's length are masked out
+    for (int c0 = 0; c0 < Lk_eff; c0 += p.kc) {
+      const int nk = min(p.kc, Lk_eff - c0);
       __syncthreads();  // previous chunk fully consumed
       load_rows<T>(sK, K, p.ldk, c0, nk, p.hd, p.pitch);
       load_rows<T>(sV, V, p.ldv, c0, nk, p.hd, p.pitch);
@@ -429,15 +431,28 @@ static int check_common(const char* name, int B, int H, int Lq, int Lk, int hd, 
 
 extern "C" {
 
+int psg_attn_fwd_keylen(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                        long long ldo, float* lse, const int* key_len, int B, int H, int Lq, int Lk, int hd, float scale, int dtype,
+                        unsigned long long drop_seed, float drop_p, void* stream);
+
 // o[b, i, h*hd:(h+1)*hd] = softmax_j(q_i . k_j * scale) v_j ; lse saved for backward (may be null for inference).
 int psg_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
                  long long ldo, float* lse, int B, int H, int Lq, int Lk, int hd, float scale, int dtype,
                  unsigned long long drop_seed, float drop_p, void* stream) {
+  return psg_attn_fwd_keylen(q, ldq, k, ldk, v, ldv, o, ldo, lse, nullptr, B, H, Lq, Lk, hd, scale, dtype, drop_seed, drop_p, stream);
+}
+
+// The same with a per-sample number of valid keys key_len[b] <= Lk (device array, nullable): keys j >= key_len[b] get zero weight --
+// BERT's padding mask (src/models/text_encoder.py:152-156: tokenizer padding=True -> attention_mask, a suffix of zeros).
+int psg_attn_fwd_keylen(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                        long long ldo, float* lse, const int* key_len, int B, int H, int Lq, int Lk, int hd, float scale, int dtype,
+                        unsigned long long drop_seed, float drop_p, void* stream) {
   using namespace attn;
   int rc = check_common("psg_attn_fwd", B, H, Lq, Lk, hd, dtype);
   if (rc) return rc;
   PSG_CHECK_ARG(q && k && v && o, "psg_attn_fwd: null pointer");
   Params p = {};
+  p.key_len = key_len;
   p.q = q; p.k = k; p.v = v; p.o = o; p.lse = lse;
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.hd = hd; p.scale = scale;

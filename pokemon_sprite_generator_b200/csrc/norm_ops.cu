@@ -297,9 +297,89 @@ int make_shape(GNShape& s, int B, int HW, int C, int G, int slices, int* threads
   return 0;
 }
 
+// ---- LayerNorm over the last dimension, one warp per row (text encoder: src/models/text_encoder.py:158-163 and the
+// BertModel layers inside it); statistics in fp32, two passes over a row held in registers (D <= 1024) ----
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x, long long ldx, TO* __restrict__ y, long long ldy,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
+                                                        int D, float eps) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[32];                      // D <= 1024: element lane + 32 * i
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < D ? psg_ld(x + row * ldx + c) : 0.f;
+    sum += v[i];
+  }
+  const float mean = psg_warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    const float d = c < D ? v[i] - mean : 0.f;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(psg_warp_sum(sq) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < D) psg_st(y + row * ldy + c, (v[i] - mean) * rstd * gamma[c] + beta[c]);
+  }
+}
+
+// out[row, :] = word[ids[row], :] + pos[row % L, :] + type[type_ids ? type_ids[row] : 0, :]   (BertEmbeddings before its LayerNorm)
+__global__ void __launch_bounds__(256) bert_embed_kernel(const long long* __restrict__ ids, const long long* __restrict__ type_ids,
+                                                         const float* __restrict__ word, const float* __restrict__ pos,
+                                                         const float* __restrict__ type, float* __restrict__ out, long long rows, int L,
+                                                         int D, int vocab) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const long long tt = type_ids ? type_ids[row] : 0;
+  const float* w = word + id * D;
+  const float* pp = pos + (row % L) * D;
+  const float* t = type + tt * D;
+  for (int c = lane; c < D; c += 32) out[row * D + c] = w[c] + pp[c] + t[c];
+}
+
 }  // namespace
 
 extern "C" {
+
+// y = LayerNorm(x) * gamma + beta over the last dimension (D <= 1024); in / out dtypes independent (PSG_DTYPE_*)
+int psg_layernorm(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta, long long rows, int D,
+                  float eps, int in_dtype, int out_dtype, void* stream) {
+  if (rows <= 0) return PSG_OK;
+  PSG_CHECK_ARG(x && y && gamma && beta && D > 0 && D <= 1024, "psg_layernorm: bad arguments (D=%d, need 1..1024)", D);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == PSG_DTYPE_F32 && out_dtype == PSG_DTYPE_F32)
+    layernorm_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, ldx, (float*)y, ldy, gamma, beta, rows, D, eps);
+  else if (in_dtype == PSG_DTYPE_F32 && out_dtype == PSG_DTYPE_BF16)
+    layernorm_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, ldx, (__nv_bfloat16*)y, ldy, gamma, beta, rows, D, eps);
+  else if (in_dtype == PSG_DTYPE_BF16 && out_dtype == PSG_DTYPE_BF16)
+    layernorm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, gamma, beta, rows, D, eps);
+  else if (in_dtype == PSG_DTYPE_BF16 && out_dtype == PSG_DTYPE_F32)
+    layernorm_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (float*)y, ldy, gamma, beta, rows, D, eps);
+  else { psg_set_error("psg_layernorm: bad dtype"); return PSG_ERR_INVALID; }
+  PSG_CHECK_LAUNCH("psg_layernorm");
+  return PSG_OK;
+}
+
+// BertEmbeddings sum (before its LayerNorm): ids / type_ids int64 [rows = B * L] (type_ids nullable), tables fp32, out fp32 [rows, D]
+int psg_bert_embed(const long long* ids, const long long* type_ids, const float* word, const float* pos, const float* type, float* out,
+                   long long rows, int L, int D, int vocab, void* stream) {
+  if (rows <= 0) return PSG_OK;
+  PSG_CHECK_ARG(ids && word && pos && type && out && L > 0 && D > 0 && vocab > 0, "psg_bert_embed: bad arguments");
+  bert_embed_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(ids, type_ids, word, pos, type, out, rows, L, D, vocab);
+  PSG_CHECK_LAUNCH("psg_bert_embed");
+  return PSG_OK;
+}
 
 // Number of slices per sample psg_groupnorm_* will use for (B, HW); workspace sizes derive from it:
 //   forward  workspace floats >= B * S * G * 2 ; backward workspace floats >= B * S * C * 2

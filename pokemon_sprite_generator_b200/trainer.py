@@ -277,8 +277,8 @@ class DiffusionTrainer:
         self.vae_encoder = self.components.get("vae_encoder")
         self.vae_decoder = self.components.get("vae_decoder")
         if self.text_encoder is None and "data_loaders" not in self.components:
-            self.text_encoder = self._reference_component("TextEncoder")(model_name=mc["bert_model"],
-                                                                        hidden_dim=mc["text_embedding_dim"]).to(self.device).eval()
+            from .text_encoder import TextEncoder      # drop-in; needs the BERT files like the reference's
+            self.text_encoder = TextEncoder(model_name=mc["bert_model"], hidden_dim=mc["text_embedding_dim"]).to(self.device).eval()
         if self.vae_encoder is None and self.vae_checkpoint_path is not None:
             from .vae import VAEDecoder, VAEEncoder      # drop-ins (same state_dicts as the reference's), on the CUDA kernels
             enc = VAEEncoder(input_channels=3, latent_dim=mc.get("latent_dim", 8), compute_dtype=torch.float32).to(self.device)

@@ -286,17 +286,20 @@ def run_sample_mode(args):
 
 
 def run_sprite_mode(args):
-    """BASELINE config 5 downstream of the text encoder: every rank turns ITS 64 prompts (512 / 8; weak scaling) into sprites with
-    sampler.text_to_sprite -- 50 posterior DDPM steps of the U-Net (CUDA-graph forward) + the VAE decoder to 215 x 215 -- reading
-    host text embeddings and writing the images back to pinned host memory inside the timed region.  Rank 0 prints one JSON line
-    (sprites/s whole job, and the split between the sampling loop and the decoder)."""
+    """BASELINE config 5 from token ids on: every rank turns ITS 64 prompts (512 / 8; weak scaling) into sprites -- BERT-mini-shaped
+    text encoder (random weights: there is no network for the checkpoint; tokenisation, a CPU string operation, is outside) -> 50
+    posterior DDPM steps of the U-Net (CUDA-graph forward) -> VAE decoder to 215 x 215 -- reading host token ids and writing the
+    images back to pinned host memory inside the timed region.  Rank 0 prints one JSON line (sprites/s whole job, and the split
+    between text encoding, the sampling loop and the decoder)."""
     import torch
     import torch.distributed as dist
     from pokemon_sprite_generator_b200 import _lib as L
     from pokemon_sprite_generator_b200 import parallel, sampler
     from pokemon_sprite_generator_b200.scheduler import LinearNoiseScheduler
     from pokemon_sprite_generator_b200.unet import UNet
+    from pokemon_sprite_generator_b200.text_encoder import TextEncoder
     from pokemon_sprite_generator_b200.vae import VAEDecoder
+    from transformers import BertConfig, BertModel
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -310,15 +313,19 @@ def run_sprite_mode(args):
     torch.manual_seed(0)
     unet = UNet(num_heads=args.heads, compute_dtype=torch.bfloat16).to(dev).eval()
     dec = VAEDecoder().to(dev).eval()
+    bert = BertModel(BertConfig(hidden_size=256, num_hidden_layers=4, num_attention_heads=4, intermediate_size=1024))     # BERT-mini shape
+    tenc = TextEncoder(hidden_dim=256, bert=bert).to(dev).eval()
     sched = LinearNoiseScheduler()
     g = torch.Generator(device="cpu").manual_seed(4321)
-    all_text = torch.randn(world * per_gpu, args.text_len, 256, generator=g)
-    host_text = parallel.shard_prompts(all_text).contiguous().pin_memory()
+    all_ids = torch.randint(1000, 30000, (world * per_gpu, args.text_len), generator=g)
+    host_ids = parallel.shard_prompts(all_ids).contiguous().pin_memory()
     host_img = torch.empty(per_gpu, 3, 215, 215).pin_memory()
     chunk = args.decode_chunk
+    e_txt = torch.cuda.Event(enable_timing=True)
 
     def run(steps):
-        text = host_text.to(dev, non_blocking=True)
+        text = tenc.encode_ids(host_ids.to(dev, non_blocking=True))
+        e_txt.record()
         lat = sampler.posterior_sample(unet, sched, text, steps, use_cuda_graph=True)
         e_mid = torch.cuda.Event(enable_timing=True)
         e_mid.record()
@@ -345,21 +352,22 @@ def run_sprite_mode(args):
     if world > 1:
         dist.barrier()
     clk = clocks.stop()
-    t = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(e_mid)], device=dev)
+    t = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(e_mid), e0.elapsed_time(e_txt)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_sample = t.tolist()
+    ms, ms_sample, ms_text = t.tolist()
     if rank == 0:
         line = {"metric": "text_to_sprite_images_per_s", "value": world * per_gpu / (ms / 1e3), "unit": "sprites/s", "n_gpus": world,
                 "steps": 1, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"text-to-sprite (config 5 downstream of the text encoder): {args.sprite_steps} posterior DDPM steps "
-                                       f"(CUDA-graph U-Net forward) + VAE decoder to 215x215, {per_gpu} prompts/GPU ({world * per_gpu} total), "
-                                       f"{args.text_len}x256 synthetic text emb, heads {args.heads}, decoder chunk {chunk}",
+                "config": {"workload": f"text-to-sprite (config 5): BERT-mini-shaped text encoder on {args.text_len} synthetic token ids -> "
+                                       f"{args.sprite_steps} posterior DDPM steps (CUDA-graph U-Net forward) -> VAE decoder to 215x215, "
+                                       f"{per_gpu} prompts/GPU ({world * per_gpu} total), heads {args.heads}, decoder chunk {chunk}, "
+                                       "random-init weights",
                            "parallelism": f"prompt-sharded x{world}, no communication"},
-                "e2e": {"value": world * per_gpu / (ms / 1e3), "unit": "sprites/s", "h2d_bytes_per_step": host_text.numel() * 4,
+                "e2e": {"value": world * per_gpu / (ms / 1e3), "unit": "sprites/s", "h2d_bytes_per_step": host_ids.numel() * 8,
                         "d2h_bytes_per_step": host_img.numel() * 4},
-                "sampling_ms": ms_sample, "decoder_ms": ms - ms_sample, "finite": bool(torch.isfinite(host_img).all()),
+                "text_encoder_ms": ms_text, "sampling_ms": ms_sample - ms_text, "decoder_ms": ms - ms_sample, "finite": bool(torch.isfinite(host_img).all()),
                 "image_mean": float(host_img.mean()), "gpu_launches": int(lib.psg_launch_count(0)), "clocks": clk,
                 "note": "launch count: kernels inside graph replays are counted once at capture, not per replay"}
         print(json.dumps(line), flush=True)

@@ -219,6 +219,35 @@ __device__ __forceinline__ uint64_t mnmajor_desc(const Geo& g, uint32_t base, ui
   return make_desc(base + row0 * g.rowb, box_bytes, 8 * g.rowb, g.swz);
 }
 
+// MMA issue loops with the descriptors advanced incrementally.  Building both 64-bit descriptors from scratch cost the single issuing
+// thread ~100 cycles per MMA -- more than a narrow MMA takes to execute -- and that issue time sat on the MMA -> elementwise -> MMA
+// chain of every block (profiles/r02_attention_umma_role_cycles.txt: "mma: issue ...").  The start-address field is the low 14 bits
+// (address >> 4) and shared memory is < 256 KB, so advancing a descriptor is one 64-bit add of (byte offset >> 4).
+//   D (+)= A[128 rows, K-major boxes] x B[N rows from row_b, K-major boxes]^T over `ksteps` 16-wide K steps
+__device__ __forceinline__ void mma_ss_loop(const Geo& g, uint32_t tmem_d, uint32_t base_a, uint32_t box_a, uint32_t base_b, uint32_t box_b,
+                                            uint32_t row_b, int ksteps, uint32_t idesc) {
+  uint64_t da = make_desc(base_a, 16, 8 * g.rowb, g.swz), db = make_desc(base_b + row_b * g.rowb, 16, 8 * g.rowb, g.swz);
+  const int kpb = 1 << g.kshift;                       // K steps per box row
+  const uint32_t jump_a = (box_a >> 4) - 2u * (kpb - 1), jump_b = (box_b >> 4) - 2u * (kpb - 1);
+  int kin = 0;
+  for (int k = 0; k < ksteps; ++k) {
+    umma_ss(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
+    if (++kin == kpb) { kin = 0; da += jump_a; db += jump_b; }
+    else { da += 2; db += 2; }
+  }
+}
+//   D (+)= A[TMEM, one K step every `a_step` columns] x B[rows row_b + 16 k of an MN-major box stack] over `ksteps` K steps
+__device__ __forceinline__ void mma_ts_loop(const Geo& g, uint32_t tmem_d, uint32_t tmem_a, uint32_t a_step, uint32_t base_b, uint32_t box_b,
+                                            uint32_t row_b, int ksteps, uint32_t idesc, bool accumulate_first) {
+  uint64_t db = make_desc(base_b + row_b * g.rowb, box_b, 8 * g.rowb, g.swz);
+  const uint32_t step_b = (16u * g.rowb) >> 4;
+  for (int k = 0; k < ksteps; ++k) {
+    umma_ts(tmem_d, tmem_a, db, idesc, (accumulate_first || k > 0) ? 1u : 0u);
+    tmem_a += a_step;
+    db += step_b;
+  }
+}
+
 // The (unit, tile) walk every role performs identically: units blockIdx.x, + gridDim.x, ...; tiles 0 .. n_t - 1 of each.
 struct Walk {
   int u, t, n_t, units, step;
@@ -438,8 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
         if (first) mbar_wait(FBAR(F_V_FULL), unit_ctr & 1);
         mbar_wait(FBAR(F_O_EMPTY), (j & 1) ^ 1);
         tc_fence_after();
-        for (int k = 0; k < ksteps_pv; ++k)
-          umma_ts(tmem_base + p.col_o, tmem_base + p.col_p + 8 * k, mnmajor_desc(g, sV, kvbox, 16 * k), idesc_o, k > 0 ? 1u : 0u);
+        mma_ts_loop(g, tmem_base + p.col_o, tmem_base + p.col_p, 8, sV, kvbox, 0, ksteps_pv, idesc_o, false);
         umma_commit(FBAR(F_P_EMPTY));
         if (last) umma_commit(FBAR(F_V_EMPTY));
         umma_commit(FBAR(F_O_FULL));
@@ -451,8 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
         if (it > 0) mbar_wait(FBAR(F_P_FULL), (it - 1) & 1);      // softmax(i-1) has read S and written P
         PROF_LAP(1);
         tc_fence_after();
-        for (int k = 0; k < ksteps_qk; ++k)
-          umma_ss(tmem_base, kmajor_desc(g, sQ, qbox, k, 0), kmajor_desc(g, sK, kvbox, k, 0), idesc_s, k > 0 ? 1u : 0u);
+        mma_ss_loop(g, tmem_base, sQ, qbox, sK, kvbox, 0, ksteps_qk, idesc_s);
         umma_commit(FBAR(F_Q_EMPTY));
         if (w.last()) umma_commit(FBAR(F_K_EMPTY));
         umma_commit(FBAR(F_S_FULL));
@@ -638,19 +665,19 @@ __device__ __forceinline__ void dq_pieces(uint32_t ts, uint32_t tdp, int c0, con
   tmem_wait_ld();
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
-    const int cc = c0 + 16 * i;
+    const int cc = c0 + 16 * i, gk = cc;
     float dpd[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) dpd[j] = __uint_as_float(d[i][j]) * p.ks;
-    if (p.drop.thr) drop_mask<16>(dpd, p.drop, idx0 + (uint64_t)cc);
-    const bool masked = cc + 16 > p.Lk;
+    if (p.drop.thr) drop_mask<16>(dpd, p.drop, idx0 + (uint64_t)gk);
+    const bool masked = gk + 16 > p.Lk;
     uint32_t pk[8];
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
       float p0 = psg_ex2_approx(fmaf(__uint_as_float(s[i][j]), p.scale_l2, -lse2));
       float p1 = psg_ex2_approx(fmaf(__uint_as_float(s[i][j + 1]), p.scale_l2, -lse2));
-      if (masked && cc + j >= p.Lk) p0 = 0.f;
-      if (masked && cc + j + 1 >= p.Lk) p1 = 0.f;
+      if (masked && gk + j >= p.Lk) p0 = 0.f;
+      if (masked && gk + j + 1 >= p.Lk) p1 = 0.f;
       pk[j >> 1] = pack_bf16(p0 * (dpd[j] - delta), p1 * (dpd[j + 1] - delta));
     }
     tmem_st8(ts + cc, pk);
@@ -717,22 +744,19 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_kernel(const __grid_consta
         mbar_wait(QBAR(Q_QD_FULL), it & 1);
         PROF_LAP(0);
         tc_fence_after();
-        for (int k = 0; k < ksteps_hd; ++k)       // (queued behind the previous tile's dQ MMAs, which read dS out of these columns)
-          umma_ss(tmem_base, kmajor_desc(g, sQ, qbox, k, 0), kmajor_desc(g, sK, kvbox, k, 0), idesc_s, k > 0 ? 1u : 0u);
+        mma_ss_loop(g, tmem_base, sQ, qbox, sK, kvbox, 0, ksteps_hd, idesc_s);       // (queued behind the previous tile's dQ MMAs, which read dS out of these columns)
         PROF_LAP(2);
         mbar_wait(QBAR(Q_T_EMPTY), (it & 1) ^ 1);                  // the previous tile's dQ (in dP's columns) has been drained
         PROF_LAP(1);
         tc_fence_after();
-        for (int k = 0; k < ksteps_hd; ++k)
-          umma_ss(tmem_base + p.col_a, kmajor_desc(g, sdO, qbox, k, 0), kmajor_desc(g, sV, kvbox, k, 0), idesc_s, k > 0 ? 1u : 0u);
+        mma_ss_loop(g, tmem_base + p.col_a, sdO, qbox, sV, kvbox, 0, ksteps_hd, idesc_s);
         umma_commit(QBAR(Q_QD_EMPTY));
         umma_commit(QBAR(Q_SD_FULL));
         PROF_LAP(2);
         mbar_wait(QBAR(Q_DS_FULL), it & 1);
         PROF_LAP(3);
         tc_fence_after();
-        for (int k = 0; k < ksteps_lk; ++k)
-          umma_ts(tmem_base + p.col_b, tmem_base + 16 * k, mnmajor_desc(g, sK, kvbox, 16 * k), idesc_q, k > 0 ? 1u : 0u);
+        mma_ts_loop(g, tmem_base + p.col_b, tmem_base, 16, sK, kvbox, 0, ksteps_lk, idesc_q, false);
         if (w.last()) { umma_commit(QBAR(Q_KV_EMPTY)); ++un; }
         umma_commit(QBAR(Q_DQ_FULL));
         PROF_LAP(4);
@@ -944,10 +968,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_kernel(const __grid_const
           const int q0 = jb * kQBlk, nq = min(kQBlk, p.Lq16 - q0);
           const uint32_t idesc_st = make_idesc(nq, 0, 0);
           // S^T = K_t Q_blk^T, dP^T = V_t dO_blk^T (queued behind the previous block's dV / dK MMAs, which read these columns)
-          for (int k = 0; k < ksteps_hd; ++k)
-            umma_ss(tmem_base, kmajor_desc(g, sK, kbox, k, 0), kmajor_desc(g, sQ, qabox, k, q0), idesc_st, k > 0 ? 1u : 0u);
-          for (int k = 0; k < ksteps_hd; ++k)
-            umma_ss(tmem_base + p.col_a, kmajor_desc(g, sV, kbox, k, 0), kmajor_desc(g, sdO, qabox, k, q0), idesc_st, k > 0 ? 1u : 0u);
+          mma_ss_loop(g, tmem_base, sK, kbox, sQ, qabox, q0, ksteps_hd, idesc_st);
+          mma_ss_loop(g, tmem_base + p.col_a, sV, kbox, sdO, qabox, q0, ksteps_hd, idesc_st);
           if (jb == nblk - 1) umma_commit(DBAR(D_KV_EMPTY));        // the K / V tile is free once these have run
           umma_commit(DBAR(D_ST_FULL));
           PROF_LAP(1);
@@ -955,10 +977,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_kernel(const __grid_const
           if (jb == 0) mbar_wait(DBAR(D_ACC_EMPTY), (it & 1) ^ 1);  // the previous tile's dV / dK have been drained
           PROF_LAP(2);
           tc_fence_after();
-          for (int k = 0; k < nq / 16; ++k)
-            umma_ts(tmem_base + p.col_dv, tmem_base + 16 * k, mnmajor_desc(g, sdO, qabox, q0 + 16 * k), idesc_acc, (jb > 0 || k > 0) ? 1u : 0u);
-          for (int k = 0; k < nq / 16; ++k)
-            umma_ts(tmem_base + p.col_dk, tmem_base + p.col_a + 16 * k, mnmajor_desc(g, sQ, qabox, q0 + 16 * k), idesc_acc, (jb > 0 || k > 0) ? 1u : 0u);
+          mma_ts_loop(g, tmem_base + p.col_dv, tmem_base, 16, sdO, qabox, q0, nq / 16, idesc_acc, jb > 0);
+          mma_ts_loop(g, tmem_base + p.col_dk, tmem_base + p.col_a, 16, sQ, qabox, q0, nq / 16, idesc_acc, jb > 0);
           PROF_LAP(3);
         }
         if (w.last()) { umma_commit(DBAR(D_QD_EMPTY)); ++un; }
@@ -1040,6 +1060,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkv_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
+
 
 // ---------------------------------------------------------------------------------------------------------------------
 // host side

@@ -747,7 +747,7 @@ class UNetEngine:
         self.linear(x, d["skip"], into=y)
         return y
 
-    def _attn_block(self, d, x: Act, text_tok: Act, lt: int, site: int) -> Act:
+    def _attn_block(self, d, x: Act, text_tok: Act, lt: int, site: int, out: Act = None) -> Act:
         c, B, HW = d["c"], x.B, x.H * x.W
         train_drop = self.training and self.dropout_enabled
         n1 = self.groupnorm(x, d["norm1"], silu=False)
@@ -762,17 +762,13 @@ class UNetEngine:
         x2 = self.linear(o2, d["co"], alpha=0.8, residual=x1)
         pf = d["p_ffn"]
         f = self.linear(x2, d["f1"], act=L.ACT_GELU, drop=(self._seed(site + 2), pf) if train_drop else None)
-        return self.linear(f, d["f2"], alpha=0.6, residual=x2, drop=(self._seed(site + 3), pf) if train_drop else None)
+        return self.linear(f, d["f2"], alpha=0.6, residual=x2, drop=(self._seed(site + 3), pf) if train_drop else None, out=out)
 
     def _block(self, d, x: Act, cond_all, text_tok, lt, site, out: Act = None) -> Act:
         if d["attn"] is None:
             return self._res_block(d["res"], x, cond_all, out=out)
         h = self._res_block(d["res"], x, cond_all)
-        y = self._attn_block(d["attn"], h, text_tok, lt, site)
-        if out is not None:   # attention output must land in a concat buffer: one strided copy
-            self.copy_into(y, out)
-            return out
-        return y
+        return self._attn_block(d["attn"], h, text_tok, lt, site, out=out)     # `out`: the FFN down-projection writes the concat half itself
 
     # ------------------------------------------------------------------------------------------------------------
     # whole network
@@ -832,22 +828,33 @@ class UNetEngine:
                 x = self._block(blk, x, cond_all, text_tok, lt, site)
                 site += 4
             skips.append(x)
-        x = self._block(self.d_mid, x, cond_all, text_tok, lt, site)
+        # ---- decoder: cat([x, skip]) is one [M, 2C] buffer.  Its x half is written by x's PRODUCER (the middle block, the
+        # previous decoder block or the up-sampling conv write straight into it, and read their gradient out of the concat
+        # gradient's slice: no strided copy either way); the skip half is one strided copy per block ----
+        def new_cat(lvl):
+            ch, size, _ = LEVELS[lvl]
+            return self._new(B * size * size, 2 * ch, B, size, size)
+
+        cat = new_cat(3)
+        self._block(self.d_mid, x, cond_all, text_tok, lt, site, out=cat.slice(0, LEVELS[3][0]))
         site += 4
-        # ---- decoder: cat([x, skip]) is one [M, 2C] buffer filled by two strided copies ----
         for lvl in (3, 2, 1, 0):
             ch, size, _ = LEVELS[lvl]
             skip = skips.pop()
-            M = B * size * size
-            for i, blk in enumerate(self.d_dec[lvl]):
-                cat = self._new(M, 2 * ch, B, size, size)
-                self.copy_into(x, cat.slice(0, ch))
+            blocks = self.d_dec[lvl]
+            for i, blk in enumerate(blocks):
                 self.copy_into(skip, cat.slice(ch, ch))
-                x = self._block(blk, cat, cond_all, text_tok, lt, site)
+                if i + 1 < len(blocks):
+                    nxt = new_cat(lvl)
+                    self._block(blk, cat, cond_all, text_tok, lt, site, out=nxt.slice(0, ch))
+                    cat = nxt
+                else:
+                    x = self._block(blk, cat, cond_all, text_tok, lt, site)
                 site += 4
             if lvl > 0:
                 x = self.upsample(x, LEVELS[lvl - 1][1])
-                x = self.conv(x, self.d_up[lvl])
+                cat = new_cat(lvl - 1)
+                self.conv(x, self.d_up[lvl], out=cat.slice(0, LEVELS[lvl - 1][0]))
         a = self.groupnorm(x, self.d_final_norm, silu=True)
         y = self.conv(a, self.d_final)
         out = torch.empty(B, lat_c, s0, s0, dtype=torch.float32, device=dev)

@@ -218,6 +218,11 @@ int psg_upsample_bilinear_fwd(const void* x, long long ldx, void* y, long long l
                               int OW, int dtype, void* stream);
 int psg_upsample_bilinear_bwd(const void* dy, long long lddy, void* dx, long long lddx, int B, int C, int IH, int IW, int OH,
                               int OW, int accumulate, int dtype, void* stream);
+/* stride-2 3x3 dgrad by output parity: four 2x2 / 1x1 stride-1 convolutions over dY (class weights from the dgrad layout
+ * [Cin][9][Cout]), then one interleave of the four [B, P, Q, C] class results into dX [B, H, W, C] */
+int psg_dgrad_s2_weights(const void* wd, void* w00, void* w01, void* w10, void* w11, int Cin, int Cout, int dtype, void* stream);
+int psg_interleave2x2(const void* c00, const void* c01, const void* c10, const void* c11, void* out, long long ldo, int B, int C, int P,
+                      int Q, int H, int W, int accumulate, int dtype, void* stream);
 int psg_dilate2(const void* dy, long long lddy, void* out, long long ldo, int B, int C, int P, int Q, int H, int W, int dtype,
                 void* stream);
 int psg_dropout_scale(const void* x, long long ldx, void* out, long long ldo, long long rows, int C, float alpha,

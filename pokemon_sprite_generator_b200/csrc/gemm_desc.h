@@ -30,7 +30,8 @@ struct PsgOperand {
   int n, h, w, c;
   int p, q;          // spatial size of the "row" index space (IM2COL*: conv output; DGRAD: conv input)
   int stride, pad, ksize;
-  int flip;          // IM2COL only: use tap (ksize-1-r, ksize-1-s) -> stride-1 dgrad
+  int flip;          // IM2COL only: bit 0: use tap (ksize-1-r, ksize-1-s) -> stride-1 dgrad; bits 8..15: 0, or (pad_hi + 1) when the
+                     // bottom / right padding differs from `pad` (tcgen05 engine only)
 };
 
 struct PsgGemmDesc {

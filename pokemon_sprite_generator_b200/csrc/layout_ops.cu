@@ -299,6 +299,56 @@ __global__ void dilate2_kernel(const T* __restrict__ dy, long long lddy, T* __re
   }
 }
 
+// ---- stride-2 dgrad by output parity (3x3, stride 2, pad 1; src/models/unet.py:335-349 downsample convs) --------------------------
+// dX[2a+pi, 2b+pj] only receives the taps whose parity matches: row taps r = 1 for pi = 0 (reading dY[a]), r = 2 and 0 for pi = 1
+// (reading dY[a] and dY[a+1]); likewise for columns.  Each of the four classes is a 2x2 (or 1x1) stride-1 convolution over dY:
+// 13 taps instead of the 36 a zero-inserted stride-1 convolution executes.
+// Class weights from the dgrad layout wd [Cin][9][Cout] (tap = 3 r + s):  w00 [Cin][Cout];  w01, w10, w11 [Cin][4][Cout] with
+// window tap (dr, ds) at index 2 dr + ds (unused window taps of the 1x2 / 2x1 classes are zero).
+template <typename T>
+__global__ void dgrad_s2_weights_kernel(const T* __restrict__ wd, T* __restrict__ w00, T* __restrict__ w01, T* __restrict__ w10,
+                                        T* __restrict__ w11, int Cin, int Cout) {
+  const long long n = (long long)Cin * 4 * Cout;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const int co = (int)(i % Cout);
+    const int win = (int)((i / Cout) & 3), dr = win >> 1, ds = win & 1;
+    const long long ci = i / (4LL * Cout);
+    const T* src = wd + ci * 9 * Cout + co;
+    const int r1 = 2 - 2 * dr, s1 = 2 - 2 * ds;             // the tap of an odd output row / column that reads dY[a + dr] / dY[b + ds]
+    const T zero = T(0.f);
+    w11[i] = src[(3 * r1 + s1) * Cout];
+    w01[i] = dr == 0 ? src[(3 * 1 + s1) * Cout] : zero;     // even row (r = 1, reads dY[a] only), odd column
+    w10[i] = ds == 0 ? src[(3 * r1 + 1) * Cout] : zero;     // odd row, even column
+    if (win == 0) w00[ci * Cout + co] = src[4 * Cout];
+  }
+}
+
+// dX[b, 2a+pi, 2b'+pj, :] (+)= class_{pi pj}[b, a, b', :] for the positions inside H x W; classes are [B, P, Q, C] (pixel pitch C)
+template <typename T>
+__global__ void interleave2x2_kernel(const T* __restrict__ c00, const T* __restrict__ c01, const T* __restrict__ c10, const T* __restrict__ c11,
+                                     T* __restrict__ out, long long ldo, int B, int C, int P, int Q, int H, int W, int accumulate) {
+  const int vpp = C / 8;
+  const long long n = (long long)B * H * W * vpp;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const int v = (int)(i % vpp);
+    long long t = i / vpp;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    const T* src = (h & 1) ? ((w & 1) ? c11 : c10) : ((w & 1) ? c01 : c00);
+    Vec8<T> r;
+    r.load(src + ((((long long)b * P + (h >> 1)) * Q + (w >> 1)) * C) + v * 8);
+    T* dst = out + (((long long)b * H + h) * W + w) * ldo + v * 8;
+    if (accumulate) {
+      Vec8<T> o;
+      o.load(dst);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] += o.v[j];
+    }
+    r.store(dst);
+  }
+}
+
 // out = alpha * dropout(x; seed, threshold) -- backward of an epilogue dropout applied before a GEMM operand
 template <typename T>
 __global__ void dropout_scale_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo, long long rows, int C,
@@ -580,6 +630,23 @@ int psg_dilate2(const void* dy, long long lddy, void* out, long long ldo, int B,
   PSG_CHECK_ARG(dy && out && B > 0 && C % 8 == 0 && lddy % 8 == 0 && ldo % 8 == 0, "psg_dilate2: bad args");
   DISPATCH_T(dtype, (dilate2_kernel<T><<<blocks_for((long long)B * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const T*)dy, lddy, (T*)out, ldo, B, C, P, Q, H, W)));
   PSG_CHECK_LAUNCH("psg_dilate2");
+  return PSG_OK;
+}
+
+int psg_dgrad_s2_weights(const void* wd, void* w00, void* w01, void* w10, void* w11, int Cin, int Cout, int dtype, void* stream) {
+  PSG_CHECK_ARG(wd && w00 && w01 && w10 && w11 && Cin > 0 && Cout > 0, "psg_dgrad_s2_weights: bad args");
+  DISPATCH_T(dtype, (dgrad_s2_weights_kernel<T><<<blocks_for((long long)Cin * 4 * Cout), kThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)wd, (T*)w00, (T*)w01, (T*)w10, (T*)w11, Cin, Cout)));
+  PSG_CHECK_LAUNCH("psg_dgrad_s2_weights");
+  return PSG_OK;
+}
+
+int psg_interleave2x2(const void* c00, const void* c01, const void* c10, const void* c11, void* out, long long ldo, int B, int C, int P,
+                      int Q, int H, int W, int accumulate, int dtype, void* stream) {
+  PSG_CHECK_ARG(c00 && c01 && c10 && c11 && out && B > 0 && C % 8 == 0 && ldo % 8 == 0 && 2 * P >= H && 2 * Q >= W, "psg_interleave2x2: bad args");
+  DISPATCH_T(dtype, (interleave2x2_kernel<T><<<blocks_for((long long)B * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)c00, (const T*)c01, (const T*)c10, (const T*)c11, (T*)out, ldo, B, C, P, Q, H, W, accumulate)));
+  PSG_CHECK_LAUNCH("psg_interleave2x2");
   return PSG_OK;
 }
 

@@ -895,8 +895,11 @@ static int make_im2col_map(CUtensorMap* tm, const PsgOperand& o, int channels_pe
   cuuint64_t dims[4] = {(cuuint64_t)o.c, (cuuint64_t)o.w, (cuuint64_t)o.h, (cuuint64_t)o.n};
   cuuint64_t strides[3] = {(cuuint64_t)o.ld * 2, (cuuint64_t)o.ld * 2 * o.w, (cuuint64_t)o.ld * 2 * o.w * o.h};
   // bounding box of filter-window base positions: [-pad, dim - 1 + upper], upper = pad - (ksize-1)
+  // flip bits 8..15 (when non-zero): pad_hi + 1, the padding of the bottom / right border when it differs from `pad` (the
+  // parity-class convolutions of the stride-2 dgrad need windows that run one row / column past the end only)
+  const int pad_hi = ((o.flip >> 8) & 0xFF) ? ((o.flip >> 8) & 0xFF) - 1 : o.pad;
   int lower[2] = {-o.pad, -o.pad};
-  int upper[2] = {o.pad - (o.ksize - 1), o.pad - (o.ksize - 1)};
+  int upper[2] = {pad_hi - (o.ksize - 1), pad_hi - (o.ksize - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)o.stride, (cuuint32_t)o.stride, 1};
   CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(o.ptr), dims, strides, lower, upper,
                                (cuuint32_t)channels_per_pixel, (cuuint32_t)pixels_per_column, estr,
@@ -1123,7 +1126,7 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
       PSG_CHECK_ARG(d->M == (long long)a.n * a.p * a.q, "psg_umma_gemm: M != n*p*q");
       rc = make_im2col_map(&kp.tm_a, a, 64, BLOCK_M);
       if (rc) return rc;
-      kp.a_im2col = 1; kp.cblks = a.c / 64; kp.ksize = a.ksize; kp.conv_stride = a.stride; kp.pad = a.pad; kp.flip = a.flip;
+      kp.a_im2col = 1; kp.cblks = a.c / 64; kp.ksize = a.ksize; kp.conv_stride = a.stride; kp.pad = a.pad; kp.flip = a.flip & 1;
       kp.P = a.p; kp.Q = a.q;
     } else {
       PSG_CHECK_ARG(d->K % 8 == 0, "psg_umma_gemm: K %% 8 != 0");

@@ -12,6 +12,7 @@ No op here is computed by PyTorch: torch provides memory (torch.empty), streams 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -21,6 +22,8 @@ from . import _lib as L
 from . import gemm as G
 from . import ops as K
 from .unet import LEVELS
+
+_DGRAD_S2 = os.environ.get("PSG_DGRAD_S2", "1") != "0"     # A/B switch: 0 = zero-inserted stride-1 dgrad for the downsample convs
 
 NUM_SMS = 148
 ALIGN = 64  # elements; keeps every parameter 256-byte aligned inside the flat buffers
@@ -382,6 +385,12 @@ class UNetEngine:
                 c.wd = self._wd_all[off:off + n].view(c.cin, c.k * c.k * c.cout)
             off += n
         K.conv_weights_transpose(self.store.shadow, self._wd_all, jobs)
+        # stride-2 convs (the three downsample layers): dgrad by output parity needs four small class weights (see _conv_bwd)
+        for c in convs:
+            if c.stride == 2 and c.k == 3 and c.pad == 1:
+                if getattr(c, "wd_s2", None) is None or c.wd_s2[0].device != device:
+                    c.wd_s2 = [torch.empty(c.cin, (1 if i == 0 else 4) * c.cout, dtype=torch.bfloat16, device=device) for i in range(4)]
+                K.dgrad_s2_weights(c.wd, *c.wd_s2, c.cin, c.cout)
         # Linear weights [N, K] likewise: dgrad (dX = dY W) reads a K-major [K, N] copy instead of the MN-major in-place
         # operand (a Linear is a 1-tap conv for the transpose kernel; row slices of a packed in_proj are column slices here)
         weights = {}
@@ -522,6 +531,20 @@ class UNetEngine:
         elif eng == "simt":
             a = G.dgrad_gather(dy4, x.H, x.W, cw.k, cw.stride, cw.pad)
             self._dgrad_gemm(a, G.kmajor(cw.wd), tgt, res, x, eng)
+        elif getattr(cw, "wd_s2", None) is not None and x.pre is None and _DGRAD_S2:
+            # stride-2 dgrad by output parity: dX[2a+pi, 2b+pj] only receives the taps of matching parity, so each of the four classes
+            # is a 2x2 (1x1 for even/even) stride-1 convolution over dY whose window may run one row / column past the end
+            # (pad_hi = 1: zero-filled by TMA); 13 taps over the 14x14 grid instead of the 36 a zero-inserted convolution over the
+            # 27x27 grid executes (2.6x fewer MMA FLOPs), then one interleave pass writes (or accumulates into) dX
+            P, Q = out.H, out.W
+            cls = []
+            for i, wc in enumerate(cw.wd_s2):
+                ci = torch.empty(x.B * P * Q, cw.cin_p, dtype=dy.dtype, device=dy.device)
+                a = G.kmajor(dy) if i == 0 else G.im2col(dy4, 2, 1, 0, pad_hi=1)
+                G.run_gemm(a, G.kmajor(wc), G.Epilogue(out=ci), engine=eng,
+                           algo_flops=(2.0 * dy.shape[0] * cw.cin_p * cw.k * cw.k * cw.cout_p) if i == 0 else 0.0)
+                cls.append(ci)
+            K.interleave2x2(cls[0], cls[1], cls[2], cls[3], tgt, x.B, P, Q, x.H, x.W, acc)
         else:
             # stride-2 dgrad on the tensor-core engine: zero-insert dY to the input grid, then a stride-1 flipped conv
             dil = torch.empty(x.B * x.H * x.W, cw.cout_p, dtype=dy.dtype, device=dy.device)

@@ -50,12 +50,15 @@ def _nhwc_geom(x: torch.Tensor):
     return n, h, w, c, ld
 
 
-def im2col(x: torch.Tensor, ksize: int, stride: int, pad: int, flip: bool = False) -> Operand:
-    """rows = conv output pixels (n,p,q); K = ksize^2 * C over NHWC `x`."""
+def im2col(x: torch.Tensor, ksize: int, stride: int, pad: int, flip: bool = False, pad_hi: Optional[int] = None) -> Operand:
+    """rows = conv output pixels (n,p,q); K = ksize^2 * C over NHWC `x`.  pad_hi: padding of the bottom / right border when it
+    differs from `pad` (tcgen05 engine only; carried in bits 8..15 of the operand's `flip` field, see csrc/gemm_desc.h)."""
     n, h, w, c, ld = _nhwc_geom(x)
-    p = (h + 2 * pad - ksize) // stride + 1
-    q = (w + 2 * pad - ksize) // stride + 1
-    return Operand(x, L.OP_IM2COL, ld, n * p * q, ksize * ksize * c, (n, h, w, c, p, q, stride, pad, ksize, int(flip)))
+    hi = pad if pad_hi is None else pad_hi
+    p = (h + pad + hi - ksize) // stride + 1
+    q = (w + pad + hi - ksize) // stride + 1
+    fl = int(flip) | ((hi + 1) << 8 if pad_hi is not None else 0)
+    return Operand(x, L.OP_IM2COL, ld, n * p * q, ksize * ksize * c, (n, h, w, c, p, q, stride, pad, ksize, fl))
 
 
 def im2col_t(x: torch.Tensor, ksize: int, stride: int, pad: int) -> Operand:

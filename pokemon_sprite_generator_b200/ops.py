@@ -79,6 +79,17 @@ def dilate2(dy: torch.Tensor, out: torch.Tensor, b: int, p: int, q: int, h: int,
            C.c_int(p), C.c_int(q), C.c_int(h), C.c_int(w), C.c_int(L.dt(dy)), L.stream_ptr())
 
 
+def dgrad_s2_weights(wd: torch.Tensor, w00: torch.Tensor, w01: torch.Tensor, w10: torch.Tensor, w11: torch.Tensor, cin: int, cout: int) -> None:
+    """wd [Cin, 9*Cout] (dgrad layout) -> the four parity-class weights of a 3x3 stride-2 pad-1 conv's dgrad."""
+    L.call("psg_dgrad_s2_weights", L.ptr(wd), L.ptr(w00), L.ptr(w01), L.ptr(w10), L.ptr(w11), C.c_int(cin), C.c_int(cout), C.c_int(L.dt(wd)),
+           L.stream_ptr())
+
+
+def interleave2x2(c00, c01, c10, c11, out: torch.Tensor, b: int, p: int, q: int, h: int, w: int, accumulate: bool) -> None:
+    L.call("psg_interleave2x2", L.ptr(c00), L.ptr(c01), L.ptr(c10), L.ptr(c11), L.ptr(out), C.c_longlong(_ld(out)), C.c_int(b),
+           C.c_int(out.shape[1]), C.c_int(p), C.c_int(q), C.c_int(h), C.c_int(w), C.c_int(int(accumulate)), C.c_int(L.dt(out)), L.stream_ptr())
+
+
 def dropout_scale(x: torch.Tensor, out: torch.Tensor, alpha: float, seed: int, drop_p: float) -> None:
     L.call("psg_dropout_scale", L.ptr(x), C.c_longlong(_ld(x)), L.ptr(out), C.c_longlong(_ld(out)), C.c_longlong(x.shape[0]),
            C.c_int(x.shape[1]), C.c_float(alpha), C.c_ulonglong(seed), C.c_float(drop_p), C.c_int(L.dt(x)), L.stream_ptr())

@@ -236,6 +236,39 @@ def test_layout_and_reductions(cuda_device, dtype):
     assert torch.equal(dil.view(2, 27, 27, 64), ref)
 
 
+@pytest.mark.parametrize("B,H,cin,cout", [(2, 27, 64, 128), (3, 14, 128, 64), (2, 7, 64, 64)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_stride2_dgrad_by_output_parity(cuda_device, B, H, cin, cout, accumulate):
+    """3x3 / stride 2 / pad 1 dgrad as four class convolutions over dY (1x1 for the even/even positions, 2x2 windows that may run one
+    row / column past the end for the rest: im2col pad_hi=1) + the interleave pass, against torch.nn.grad.conv2d_input, on odd and even
+    input sizes."""
+    K = _ops()
+    from pokemon_sprite_generator_b200 import gemm as G
+    torch.manual_seed(H)
+    P = (H + 2 - 3) // 2 + 1
+    bf = torch.bfloat16
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") * 0.1).to(bf).float()
+    dy = torch.randn(B, cout, P, P, device="cuda").to(bf).float()
+    wd = torch.empty(cin, 9 * cout, device="cuda", dtype=bf)
+    K.pack_conv_weight(w, torch.empty(cout, 9 * cin, device="cuda", dtype=bf), wd)
+    cls_w = [torch.empty(cin, n * cout, device="cuda", dtype=bf) for n in (1, 4, 4, 4)]
+    K.dgrad_s2_weights(wd, *cls_w, cin, cout)
+    dy_rows = dy.permute(0, 2, 3, 1).contiguous().to(bf).view(B * P * P, cout)
+    cls = []
+    for i, wc in enumerate(cls_w):
+        ci = torch.empty(B * P * P, cin, device="cuda", dtype=bf)
+        a = G.kmajor(dy_rows) if i == 0 else G.im2col(dy_rows.view(B, P, P, cout), 2, 1, 0, pad_hi=1)
+        G.run_gemm(a, G.kmajor(wc), G.Epilogue(out=ci), engine="umma")
+        cls.append(ci)
+    base = torch.randn(B * H * H, cin, device="cuda").to(bf)
+    dx = base.clone()
+    K.interleave2x2(*cls, dx, B, P, P, H, H, accumulate)
+    ref = torch.nn.grad.conv2d_input((B, cin, H, H), w, dy, stride=2, padding=1).permute(0, 2, 3, 1).reshape(B * H * H, cin)
+    if accumulate:
+        ref = ref + base.float()
+    _cmp(dx, ref, bf, f"s2 dgrad H={H} acc={accumulate}")
+
+
 def test_cond_inputs_and_weight_packing(cuda_device):
     K = _ops()
     t = torch.tensor([0, 1, 500, 999], device="cuda")

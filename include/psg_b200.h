@@ -84,6 +84,9 @@ typedef struct PsgGemmDesc {
  * m_tiles: 0 = auto, 1 or 2 (CTA tile = 128*m_tiles rows).  psg_umma_plan reports the automatic choice. */
 int psg_umma_gemm(const PsgGemmDesc* desc, int block_n, void* stream);
 int psg_umma_gemm_ex(const PsgGemmDesc* desc, int block_n, int m_tiles, void* stream);
+/* As psg_umma_gemm_ex, naming the stream-K workspace lane (0 or 1): launches that may be in flight together on different streams
+ * of one device must use different lanes (psg_umma_gemm / _ex use lane 0). */
+int psg_umma_gemm_lane(const PsgGemmDesc* desc, int block_n, int m_tiles, int lane, void* stream);
 int psg_umma_plan(const PsgGemmDesc* desc, int* block_n, int* m_tiles);
 /* Stream-K scheduling: tiles whose k-range is shared between CTAs exchange fp32 partial accumulators through a
  * caller-owned workspace (psg_umma_workspace_bytes() bytes, 256B aligned, first 1 KiB zeroed), registered once. */

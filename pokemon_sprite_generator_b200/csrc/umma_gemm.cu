@@ -504,10 +504,9 @@ struct Segment {          // a maximal run of one CTA's k-blocks inside one tile
 struct SegmentIter {
   long long cur, end;
   int num_kb, dp_tile, num_tiles, stride;
-  __device__ __forceinline__ SegmentIter(const long long sk_units, int sk_ctas, int sk_split, int sk_tiles, int num_tiles_, int num_kb_,
-                                         int c, int ctas)
-      : cur(sk_begin(sk_units, c, sk_ctas, sk_split, num_kb_)), end(sk_begin(sk_units, c + 1, sk_ctas, sk_split, num_kb_)),
-        num_kb(num_kb_), dp_tile(sk_tiles + c), num_tiles(num_tiles_), stride(ctas) {}
+  __device__ __forceinline__ SegmentIter(const KernelParams& p, int c, int ctas)
+      : cur(sk_begin(p.sk_units, c, p.sk_ctas, p.sk_split, p.num_kb)), end(sk_begin(p.sk_units, c + 1, p.sk_ctas, p.sk_split, p.num_kb)),
+        num_kb(p.num_kb), dp_tile(p.sk_tiles + c), num_tiles(p.num_tiles), stride(ctas) {}
   __device__ __forceinline__ bool next(Segment& s) {
     if (cur < end) {
       s.tile = (int)(cur / num_kb);
@@ -527,7 +526,7 @@ struct SegmentIter {
     return false;
   }
 };
-#define PSG_SEGMENTS(p) SegmentIter segs((p).sk_units, (p).sk_ctas, (p).sk_split, (p).sk_tiles, (p).num_tiles, (p).num_kb, vcta, vctas)
+#define PSG_SEGMENTS(p) SegmentIter segs((p), vcta, vctas)
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }   // the epilogue warps
 
@@ -545,6 +544,15 @@ __device__ __forceinline__ void wait_flag(const int* flag) {
 // ---------------------------------------------------------------------------------------------
 // the kernel: persistent CTAs, one contiguous stream-K range of (tile, k-block) units each
 // ---------------------------------------------------------------------------------------------
+// Sub-tiles (128 rows per CTA, 128 * kCl per scheduling unit) of row tile `tile_m` that hold at least one row < M.  With kMT = 2 the
+// last row tile of e.g. M = 640 (pairs: 512-row tiles) or 1280 keeps only its lower half: the upper one is neither loaded, multiplied
+// nor drained (all three roles derive the same count).
+template <int kMT, int kCl>
+__device__ __forceinline__ int live_subtiles(int tile_m, int M) {
+  if (kMT == 1) return 1;
+  return (long long)tile_m * (BLOCK_M * kMT * kCl) + BLOCK_M * kCl >= M ? 1 : kMT;
+}
+
 template <int kBlockN, int kStages, int kMode, int kMT, int kCl>
 __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_constant__ KernelParams p) {
   using L = SmemLayout<kBlockN, kStages, kMT, kCl>;
@@ -597,6 +605,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
         constexpr int kRowStep = BLOCK_M * kCl;
         const int m0 = tile_m * (BM * kCl) + (int)cta_rank * BLOCK_M;
         const int kb0 = sg.kb0, kb1 = sg.kb1;
+        const int live = live_subtiles<kMT, kCl>(tile_m, p.M);      // 1: the upper 128-row sub-tile(s) are past M -- not loaded / issued
+        const uint32_t stage_tx = kCl * (L::STAGE_BYTES - (uint32_t)(kMT - live) * A_BYTES);
         int w0[kMT], h0[kMT], img0[kMT];
         if (!kAMn && p.a_im2col) {
           const int pq = p.P * p.Q;
@@ -616,7 +626,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           // in a pair both CTAs' loads are counted on the LEADER's full barrier (the leader issues the MMAs)
           const uint32_t full = (kCl == 2) ? leader_addr(bar_full + 8 * s) : bar_full + 8 * s;
-          if (kCl == 1 || cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, kCl * L::STAGE_BYTES);
+          if (kCl == 1 || cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, stage_tx);
           const uint32_t sa = smem + s * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_TILE_BYTES;
           if (!kAMn) {
@@ -626,14 +636,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
               if (p.flip) { r = p.ksize - 1 - r; ss = p.ksize - 1 - ss; }
 #pragma unroll
               for (int t = 0; t < kMT; ++t)
-                tma_im2col<kCl>(sa + t * A_BYTES, &p.tm_a, full, cb * BLOCK_K, w0[t], h0[t], img0[t], (uint16_t)ss, (uint16_t)r);
+                if (t < live) tma_im2col<kCl>(sa + t * A_BYTES, &p.tm_a, full, cb * BLOCK_K, w0[t], h0[t], img0[t], (uint16_t)ss, (uint16_t)r);
             } else {
 #pragma unroll
-              for (int t = 0; t < kMT; ++t) tma_2d<kCl>(sa + t * A_BYTES, &p.tm_a, full, kb * BLOCK_K, m0 + t * kRowStep);
+              for (int t = 0; t < kMT; ++t)
+                if (t < live) tma_2d<kCl>(sa + t * A_BYTES, &p.tm_a, full, kb * BLOCK_K, m0 + t * kRowStep);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_2d<kCl>(sa + j * 8192, &p.tm_a, full, m0 + (j >> 1) * kRowStep + 64 * (j & 1), kb * BLOCK_K);
+            for (int j = 0; j < BM / 64; ++j)
+              if ((j >> 1) < live) tma_2d<kCl>(sa + j * 8192, &p.tm_a, full, m0 + (j >> 1) * kRowStep + 64 * (j & 1), kb * BLOCK_K);
           }
           // B: alone, the whole tile; in a pair, this CTA's half of it (the MMA reads the other half from the peer's smem)
           constexpr int kMyBoxes = kBlockN / 64 / kCl;
@@ -688,6 +700,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       Segment sg;
       for (; segs.next(sg); ++wi) {
         const int kb0 = sg.kb0, kb1 = sg.kb1;
+        const int live = live_subtiles<kMT, kCl>(sg.tile / p.num_n_tiles, p.M);
         const int acc = wi % kAcc;
         const uint32_t aph = (wi / kAcc) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1);       // the epilogue (of both CTAs) has drained this accumulator
@@ -711,6 +724,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
               else       bd = make_desc(sbh + k * (UMMA_K * 128), 8192, 1024);
 #pragma unroll
               for (int t = 0; t < kMT; ++t) {
+                if (t >= live) break;
                 uint64_t ad;
                 if (!kAMn) ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 2), 16, 1024);
                 else       ad = make_desc(sa + t * A_BYTES + k * (UMMA_K * 128), 8192, 1024);
@@ -745,6 +759,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       const long long tile_row0 = (long long)tile_m * (BM * kCl) + (long long)cta_rank * BLOCK_M;   // + t * BLOCK_M * kCl per sub-tile
       const int acc = wi % kAcc;
       const uint32_t aph = (wi / kAcc) & 1;
+      const int live = live_subtiles<kMT, kCl>(tile_m, p.M);
       const bool contributor = sg.kb0 > 0;                      // someone else owns this tile: park the partial sums
       const bool shared_owner = sg.kb0 == 0 && sg.kb1 < p.num_kb;
       // scheduling units vcta+1 .. last_contrib hold the rest of this tile (their ranges start inside it); in a pair each
@@ -780,7 +795,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * (kMT * kBlockN);
 #pragma unroll 1
-      for (int t = 0; t < kMT; ++t) {
+      for (int t = 0; t < live; ++t) {
         const long long m_base = tile_row0 + (long long)t * (BLOCK_M * kCl) + q * 32;
 #pragma unroll 1
         for (int ch = cslot; ch < kChunks; ch += kEpiWarps / 4) {
@@ -830,7 +845,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) umma_gemm_kernel(const __grid_
       } else if (shared_owner) {
         epi_bar_sync();                      // every epilogue thread has read the slots: hand them back
         if (warp == 2 && lane == 0)
-          for (int c = vcta + 1; c <= last_contrib; ++c) p.sk_flags[c * kCl + cta_rank] = 0;
+          for (int c = vcta + 1; c <= last_contrib; ++c) {
+            int zero = 0;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + c * kCl + cta_rank), "r"(zero) : "memory");
+          }
       }
     }
   }
@@ -995,9 +1013,10 @@ static constexpr int kMaxCtas = 160;
 static constexpr size_t kSlotBytes = (size_t)2 * 128 * 256 * sizeof(float);
 // Host-side engine state is kept PER DEVICE (indexed by the calling thread's current device), so two devices driven from one
 // process never share a stream-K workspace or an SM reservation.  Within one device the registered workspace serves ONE
-// stream at a time: a caller that wants stream-K GEMMs in flight on several streams of one device must serialise them (this
-// library's engine issues every GEMM on one stream).  g_debug / g_pairs_on are
-// measurement hooks (tools/, tests/), process-wide on purpose.
+// stream at a time PER LANE: the workspace holds kLanes independent copies (flags + slots), and launches that may be in flight at
+// the same time on different streams of one device must name different lanes (psg_umma_gemm_lane; the engine's backward pass runs
+// its weight-gradient GEMMs on a second stream with lane 1).  g_debug / g_pairs_on are measurement hooks (tools/, tests/),
+// process-wide on purpose.
 static constexpr int kMaxDevices = 32;
 struct DeviceState {
   void* sk_ws = nullptr;
@@ -1028,7 +1047,9 @@ int psg_umma_reserve_sms(int n) {
   return prev;
 }
 
-size_t psg_umma_workspace_bytes() { return 1024 + (size_t)kMaxCtas * kSlotBytes; }
+static constexpr int kLanes = 2;
+static constexpr size_t kLaneBytes = 1024 + (size_t)kMaxCtas * kSlotBytes;
+size_t psg_umma_workspace_bytes() { return kLanes * kLaneBytes; }
 
 int psg_umma_set_workspace(void* ws, size_t bytes) {
   PSG_CHECK_ARG(ws == nullptr || bytes >= psg_umma_workspace_bytes(), "psg_umma_set_workspace: need %zu bytes, got %zu",
@@ -1075,8 +1096,9 @@ int psg_umma_plan(const PsgGemmDesc* d, int* block_n, int* m_tiles) {
 }
 
 // block_n: 0 = auto, else 64/128/160/256 (160 only for K-major B).  m_tiles: 0 = auto, 1 or 2 (CTA tile = 128*m_tiles rows).
-int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* stream) {
+int psg_umma_gemm_lane(const PsgGemmDesc* d, int block_n, int m_tiles, int lane, void* stream) {
   using namespace umma;
+  PSG_CHECK_ARG(lane >= 0 && lane < kLanes, "psg_umma_gemm: workspace lane %d out of range [0, %d)", lane, kLanes);
   PSG_CHECK_ARG(d != nullptr, "psg_umma_gemm: null desc");
   PSG_CHECK_ARG(d->in_dtype == PSG_DTYPE_BF16, "psg_umma_gemm: operands must be bf16");
   PSG_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "psg_umma_gemm: empty problem M=%lld N=%lld K=%lld", d->M, d->N, d->K);
@@ -1202,8 +1224,9 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
     kp.sk_units = sk_units;
     if (sk_ctas != sk_tiles) {     // some tile is shared between CTAs
       PSG_CHECK_ARG(ds.sk_ws != nullptr, "psg_umma_gemm: stream-K workspace not registered on this device (psg_umma_set_workspace)");
-      kp.sk_flags = reinterpret_cast<int*>(ds.sk_ws);
-      kp.sk_slots = reinterpret_cast<float*>(reinterpret_cast<char*>(ds.sk_ws) + 1024);
+      char* ws = reinterpret_cast<char*>(ds.sk_ws) + (size_t)lane * kLaneBytes;
+      kp.sk_flags = reinterpret_cast<int*>(ws);
+      kp.sk_slots = reinterpret_cast<float*>(ws + 1024);
     }
   }
   dim3 grid((unsigned)(ctas * cl));
@@ -1238,7 +1261,8 @@ int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* strea
   return PSG_ERR_UNSUPPORTED;
 }
 
-int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) { return psg_umma_gemm_ex(d, block_n, 0, stream); }
+int psg_umma_gemm_ex(const PsgGemmDesc* d, int block_n, int m_tiles, void* stream) { return psg_umma_gemm_lane(d, block_n, m_tiles, 0, stream); }
+int psg_umma_gemm(const PsgGemmDesc* d, int block_n, void* stream) { return psg_umma_gemm_lane(d, block_n, 0, 0, stream); }
 
 // Test hook: 1 if any mbarrier wait timed out since the last call (synchronises the device).
 int psg_umma_timeout_flag() {

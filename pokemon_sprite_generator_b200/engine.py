@@ -11,6 +11,7 @@ No op here is computed by PyTorch: torch provides memory (torch.empty), streams 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from typing import Callable, List, Optional
@@ -23,6 +24,7 @@ from . import gemm as G
 from . import ops as K
 from .unet import LEVELS
 
+_WGRAD_STREAM = os.environ.get("PSG_WGRAD_STREAM", "1") != "0"  # A/B switch: 0 = weight gradients on the main stream
 _DGRAD_S2 = os.environ.get("PSG_DGRAD_S2", "1") != "0"     # A/B switch: 0 = zero-inserted stride-1 dgrad for the downsample convs
 
 NUM_SMS = 148
@@ -255,6 +257,11 @@ class UNetEngine:
         # `global_step` by DiffusionTrainer.load_checkpoint, so a resumed run continues the sequence instead of replaying it.
         self.seed = None
         self.launches = 0
+        # backward: weight / bias gradients run on a second stream (see _weight_stream)
+        self.weight_stream_enabled = _WGRAD_STREAM     # bench.py turns it off for its per-kernel (serialised) timing pass
+        self.wstream = None               # the stream in use during the current backward (None: everything on the main stream)
+        self._wstream_obj = None
+        self._wbusy = {}                  # data_ptr of a gradient tensor the second stream reads -> event after that read
 
     # ------------------------------------------------------------------------------------------------------------
     # descriptors
@@ -439,7 +446,44 @@ class UNetEngine:
         if a.grad is None:
             a.grad = torch.empty(a.M, a.C, dtype=a.t.dtype, device=a.t.device)
             return a.grad, False
+        if self._wbusy:
+            # a residual's gradient may BE the dY buffer of a layer whose weight gradient is still being formed on the second
+            # stream (_pass_grad hands the buffer over): the in-place accumulation that follows waits for that read
+            ev = self._wbusy.pop(a.grad.data_ptr(), None)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
         return a.grad, True
+
+    @contextlib.contextmanager
+    def _weight_stream(self, dy: torch.Tensor, *reads: torch.Tensor):
+        """Backward's weight / bias gradients (wgrad GEMMs, bias column sums) are needed only by the optimizer (or the gradient
+        all-reduce), not by the dX chain, so they are enqueued on a second stream: their CTAs fill the SMs the critical-path
+        kernels leave idle (persistent-grid tails, stream-K imbalance, the small 4x4-level GEMMs) and the column sums co-reside
+        with the GEMM CTAs.  The block runs after everything enqueued so far on the main stream; `dy` and `reads` are the
+        tensors it reads (kept alive for the second stream; an in-place accumulation into `dy` later on the main stream waits
+        for the read: _grad_target).  backward() joins the streams at the end, GradSync before each bucket goes out."""
+        side = self.wstream
+        if side is None:
+            yield
+            return
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        for t in (dy,) + reads:
+            t.record_stream(side)
+        G.LANE = 1                      # the second stream-K workspace: these GEMMs overlap the main stream's
+        try:
+            with torch.cuda.stream(side):
+                yield
+        finally:
+            G.LANE = 0
+        ev = torch.cuda.Event()
+        ev.record(side)
+        self._wbusy[dy.data_ptr()] = ev
+
+    def _join_weight_stream(self) -> None:
+        if self.wstream is not None:
+            torch.cuda.current_stream().wait_stream(self.wstream)
+            self._wbusy.clear()
 
     def _pass_grad(self, dy: torch.Tensor, a: Act) -> None:
         """grad(a) += dy for a residual connection (out = f(..) + a).  The first contribution to a stand-alone activation
@@ -497,27 +541,32 @@ class UNetEngine:
         dy = out.g()
         gb = self.store.grad_of(cw.mod.bias)
         dy_real = dy[:, :cw.cout] if cw.cout_p != cw.cout else dy
+        plain_colsum = False
         if out.colsum_done:
             pass        # bias / conditioning gradients came out of the consumer GroupNorm's backward
         elif rowbias is not None:
             tgt, acc = self._rowbias_target(rowbias)
             K.colsum(dy_real, x.B, tgt, gb, acc_groups=acc)
         else:
-            K.colsum(dy_real, 1, None, gb)
+            plain_colsum = True
         if residual is not None:
             self._pass_grad(dy, residual)
         # wgrad: dW[co][tap][ci] = sum_pix dY[pix, co] * im2col(X)[pix, (tap, ci)]
         gw = self.store.grad_of(cw.mod.weight)
         kk = cw.k * cw.k
         ncols = kk * cw.cin_p
-        a_op, b_op = G.mnmajor(dy), G.im2col_t(x.nhwc(), cw.k, cw.stride, cw.pad)
-        if cw.in_place:     # the gradient buffer IS the [Cout, taps*Cin] matrix the GEMM produces (stream-K: no split pass)
-            G.run_gemm(a_op, b_op, G.Epilogue(out=self.store.matrix(self.store.grads, cw.mod.weight)), engine=eng)
-        else:
-            nel = cw.cout_p * ncols
-            part = K.workspace(self.device, nel, "wgrad").narrow(0, 0, nel).view(1, cw.cout_p, ncols)
-            G.run_gemm(a_op, b_op, G.Epilogue(out=part[0]), engine=eng)
-            K.wgrad_finalize(part, 1, nel, gw, cin_p=cw.cin_p)
+        with self._weight_stream(dy, x.t) if eng == "umma" else contextlib.nullcontext():
+            if plain_colsum:
+                K.colsum(dy_real, 1, None, gb)
+            a_op, b_op = G.mnmajor(dy), G.im2col_t(x.nhwc(), cw.k, cw.stride, cw.pad)
+            if cw.in_place:     # the gradient buffer IS the [Cout, taps*Cin] matrix the GEMM produces (stream-K: no split pass)
+                G.run_gemm(a_op, b_op, G.Epilogue(out=self.store.matrix(self.store.grads, cw.mod.weight)), engine=eng)
+            else:
+                nel = cw.cout_p * ncols
+                tag = "wgrad2" if G.LANE else "wgrad"      # the second stream's own scratch
+                part = K.workspace(self.device, nel, tag).narrow(0, 0, nel).view(1, cw.cout_p, ncols)
+                G.run_gemm(a_op, b_op, G.Epilogue(out=part[0]), engine=eng)
+                K.wgrad_finalize(part, 1, nel, gw, cin_p=cw.cin_p)
         if not x_needs_grad:
             return
         # dgrad
@@ -603,10 +652,11 @@ class UNetEngine:
             dpre = torch.empty(dy.shape, dtype=dy.dtype, device=dy.device)
             K.dropout_scale(dy, dpre, alpha, drop[0], drop[1])
             dy, scale = dpre, 1.0
-        if gb is not None:
-            K.colsum(dy, 1, None, gb, scale=scale)
-        # wgrad: dW[n][k] = scale * sum_m dY[m, n] X[m, k]
-        G.run_gemm(G.mnmajor(dy), G.mnmajor(x.t), G.Epilogue(out=gw2, alpha=scale), engine=eng)
+        with self._weight_stream(dy, x.t) if eng == "umma" else contextlib.nullcontext():
+            if gb is not None:
+                K.colsum(dy, 1, None, gb, scale=scale)
+            # wgrad: dW[n][k] = scale * sum_m dY[m, n] X[m, k]
+            G.run_gemm(G.mnmajor(dy), G.mnmajor(x.t), G.Epilogue(out=gw2, alpha=scale), engine=eng)
         if not x_needs_grad:
             return
         tgt, acc = self._grad_target(x) if x.parent is None else (x.g(), False)
@@ -892,14 +942,24 @@ class UNetEngine:
         flat gradient buffer (tail first), overlapped with the rest of the backward pass."""
         tape, y = ctx
         self.taping = False
+        if self.weight_stream_enabled and self.bf16 and dout.is_cuda:
+            if self._wstream_obj is None or self._wstream_obj.device != dout.device:
+                self._wstream_obj = torch.cuda.Stream(device=dout.device)
+            self.wstream = self._wstream_obj
+        else:
+            self.wstream = None
         lat_c = dout.shape[1]
         y.grad = (torch.zeros if y.C != lat_c else torch.empty)(y.M, y.C, dtype=y.t.dtype, device=y.t.device)
         K.nchw_to_tokens(dout.detach().contiguous().float(), y.grad[:, :lat_c])
         if grad_sync is None:
-            while tape:
-                tape.pop()()
+            try:
+                while tape:
+                    tape.pop()()
+            finally:
+                self._join_weight_stream()
             return
         grad_sync.begin(self.store, len(tape))
+        grad_sync.before_issue = self._join_weight_stream      # a bucket's all-reduce is ordered after the main stream only
         try:
             done = 0
             while tape:
@@ -908,6 +968,7 @@ class UNetEngine:
                 grad_sync.after_entry(done)
         finally:
             grad_sync.finish()
+            self._join_weight_stream()
 
     # ------------------------------------------------------------------------------------------------------------
     # autograd glue

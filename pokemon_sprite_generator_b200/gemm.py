@@ -201,6 +201,9 @@ def _ensure_umma_workspace(device) -> None:
     _umma_ws[device] = ws
 
 
+# Stream-K workspace lane of the launches that follow (0 or 1): GEMMs in flight together on two streams use different lanes.
+LANE = 0
+
 # When set to a list, every launch appends (start_event, end_event, algorithmic_flops, engine): bench.py uses it to time
 # the tensor-core kernel on its own stream inside the timed region (roofline numerator and denominator).
 PROFILE = None
@@ -228,7 +231,7 @@ def run_gemm(a: Operand, b: Operand, epi: Epilogue, *, engine: str = "auto", spl
         ev0.record()
     if engine == "umma":
         _ensure_umma_workspace(a.t.device)
-        L.check(lib.psg_umma_gemm_ex(C.byref(d), C.c_int(block_n), C.c_int(m_tiles), L.stream_ptr()), "psg_umma_gemm")
+        L.check(lib.psg_umma_gemm_lane(C.byref(d), C.c_int(block_n), C.c_int(m_tiles), C.c_int(LANE), L.stream_ptr()), "psg_umma_gemm")
     elif engine == "simt":
         L.check(lib.psg_simt_gemm(C.byref(d), L.stream_ptr()), "psg_simt_gemm")
     else:

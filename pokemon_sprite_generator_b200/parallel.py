@@ -89,6 +89,7 @@ class GradSync:
         self.bounds: List[Tuple[int, int]] = []
         self.stats = {"calibrations": 0, "overlapped_buckets": 0, "tail_buckets": 0}
         self._reserved = 0
+        self.before_issue: Optional[Callable[[], None]] = None     # the engine joins its weight-gradient stream here
 
     def _reserve(self, n: int) -> None:
         if self.reserve_hook is not None and n != self._reserved:
@@ -151,6 +152,8 @@ class GradSync:
         s, e = self.bounds[b]
         self.issued[b] = True
         if self.world > 1 and e > s:
+            if self.before_issue is not None:
+                self.before_issue()
             self.works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def after_entry(self, done: int) -> None:

@@ -265,6 +265,27 @@ def test_conv_wgrad(cuda_device, engine, dtype, n, h, cin, cout, stride, split):
     _close(dw, ref, 1e-4, f"wgrad {engine} h{h} {cin}->{cout} s{stride} split{split}")
 
 
+@pytest.mark.parametrize("n,h,cin,cout", [(2, 14, 640, 640), (24, 14, 640, 640), (4, 8, 1280, 1280), (40, 8, 1280, 1280), (16, 27, 320, 320)])
+def test_conv_wgrad_half_row_tiles(cuda_device, n, h, cin, cout):
+    """Conv weight gradients whose last 256-row CTA tile keeps only its lower 128-row sub-tile (Cout = 640, 1280: the upper one is
+    neither loaded, multiplied nor drained -- umma_gemm.cu live_subtiles), with and without shared (stream-K) tiles; bit-identical
+    across repeats."""
+    L, G = _mods()
+    x, wt = _conv_inputs(n, h, h, cin, cout, 7 + h + cin, torch.bfloat16)
+    dy = torch.randn(n * h * h, cout, device="cuda").bfloat16()
+    outs = []
+    for _ in range(2):
+        dw = torch.full((cout, 9 * cin), float("nan"), device="cuda")
+        G.run_gemm(G.mnmajor(dy), G.im2col_t(x, 3, 1, 1), G.Epilogue(out=dw), engine="umma")
+        torch.cuda.synchronize()
+        _check_timeout(L)
+        outs.append(dw)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3),
+                                      dy.float().reshape(n, h, h, cout).permute(0, 3, 1, 2), stride=1, padding=1)
+    _close(outs[0].reshape(cout, 3, 3, cin).permute(0, 3, 1, 2), ref, 1e-4, f"wgrad half row tile h{h} {cin}->{cout}")
+    assert torch.equal(outs[0], outs[1]), "wgrad is not run-to-run deterministic"
+
+
 @pytest.mark.parametrize("M,N,K,bn,mt", [(392, 640, 1280, 0, 0), (12544, 1280, 2560, 256, 2), (1000, 320, 640, 0, 0), (300, 96, 128, 0, 0)])
 def test_gemm_tt_weight_in_place(cuda_device, M, N, K, bn, mt):
     """dgrad of a Linear with the [N_w, K_w] weight read transposed in place (A K-major, B MN-major)."""

@@ -54,3 +54,34 @@ if which in ("all", "wgrad"):
     for mt in (1, 2):
         wgrad(B, 27, 320, 320, 3, 128, mt); wgrad(B, 27, 320, 320, 2, 256, mt); wgrad(B, 14, 640, 640, 1, 256, mt); wgrad(B, 14, 640, 640, 1, 128, mt)
         wgrad(B, 7, 1280, 1280, 1, 256, mt); wgrad(B, 4, 1280, 1280, 1, 256, mt); wgrad(B, 4, 1280, 1280, 2, 256, mt)
+if which == "wgrad_sweep":
+    # the conv weight-gradient shapes of a batch-256 step: (H, cin, cout); tile shape x pairing sweep
+    from pokemon_sprite_generator_b200 import _lib as L
+    shapes = [(14, 640, 640), (27, 320, 320), (14, 1280, 640), (27, 640, 320), (7, 1280, 1280), (4, 1280, 1280), (7, 2560, 1280)]
+    for (H, cin, cout) in shapes:
+        for pairs in (0, 1, 2):
+            L.load().psg_umma_pairs(pairs)
+            for bn, mt in ((256, 1), (256, 2), (128, 1), (128, 2)) if pairs != 1 else ((0, 0),):
+                print(f"pairs={pairs} ", end="")
+                wgrad(B, H, cin, cout, 1, bn, mt)
+    L.load().psg_umma_pairs(1)
+if which == "modes":
+    # same L2-resident problem, same tile shape, through the three operand-layout modes: what does an MN-major operand cost?
+    from pokemon_sprite_generator_b200 import _lib as L
+    for (M, N, K) in ((3072, 3072, 4096), (3072, 3072, 16384), (1280, 11520, 12544)):
+        a = torch.randn(M, K, device=dev).bfloat16(); b = torch.randn(N, K, device=dev).bfloat16()
+        at, bt = a.t().contiguous(), b.t().contiguous()
+        out = torch.empty(M, N, device=dev)
+        for pairs in (0, 2):
+            L.load().psg_umma_pairs(pairs)
+            for bn, mt in ((256, 1), (256, 2)):
+                fl = 2.0 * M * N * K
+                timeit(lambda: G.run_gemm(G.kmajor(a), G.kmajor(b), G.Epilogue(out=out), engine="umma", block_n=bn, m_tiles=mt), fl, f"TN pairs={pairs} M={M} N={N} K={K} bn={bn} mt={mt}")
+                timeit(lambda: G.run_gemm(G.kmajor(a), G.mnmajor(bt), G.Epilogue(out=out), engine="umma", block_n=bn, m_tiles=mt), fl, f"TT pairs={pairs} M={M} N={N} K={K} bn={bn} mt={mt}")
+                timeit(lambda: G.run_gemm(G.mnmajor(at), G.mnmajor(bt), G.Epilogue(out=out), engine="umma", block_n=bn, m_tiles=mt), fl, f"NT pairs={pairs} M={M} N={N} K={K} bn={bn} mt={mt}")
+    L.load().psg_umma_pairs(1)
+if which == "wgrad_auto":
+    # conv weight gradients of a batch-256 step, automatic tile shape
+    for (H, cin, cout) in [(14, 640, 640), (27, 320, 320), (14, 1280, 640), (27, 640, 320), (7, 1280, 1280), (4, 1280, 1280), (7, 2560, 1280),
+                           (4, 2560, 1280), (14, 320, 640), (7, 640, 1280), (14, 1920, 640), (27, 960, 320)]:
+        wgrad(B, H, cin, cout, 1, 0, 0)

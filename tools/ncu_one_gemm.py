@@ -22,7 +22,10 @@ elif variant == "wgrad":
     Bn, H, cin, cout = 256, 14, 640, 640
     x = torch.randn(Bn, H, H, cin, device=dev).bfloat16(); dy = torch.randn(Bn * H * H, cout, device=dev).bfloat16()
     out = torch.empty(cout, 9 * cin, device=dev)
-    fn = lambda: G.run_gemm(G.mnmajor(dy), G.im2col_t(x, 3, 1, 1), G.Epilogue(out=out), engine="umma")
+    import os
+    L.load().psg_umma_pairs(int(os.environ.get("PSG_PAIRS", "1")))         # tile-shape overrides for A/B captures
+    bn, mt = int(os.environ.get("PSG_BN", "0")), int(os.environ.get("PSG_MT", "0"))
+    fn = lambda: G.run_gemm(G.mnmajor(dy), G.im2col_t(x, 3, 1, 1), G.Epilogue(out=out), engine="umma", block_n=bn, m_tiles=mt)
 else:
     Bn, H, cin, cout = 256, 14, 640, 640
     x = torch.randn(Bn, H, H, cin, device=dev).bfloat16(); w = torch.randn(cout, 9 * cin, device=dev).bfloat16()

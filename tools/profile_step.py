@@ -27,6 +27,7 @@ torch.cuda.synchronize()
 import os
 NCU = os.environ.get("PSG_NCU") == "1"      # under ncu: --profile-from-start off, one step between start/stop
 if not NCU:
+    unet.engine().weight_stream_enabled = False     # per-call events need serialised kernels (see engine._weight_stream)
     L.CALL_PROFILE, G.PROFILE = [], []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 if NCU:

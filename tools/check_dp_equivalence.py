@@ -14,6 +14,8 @@ from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
 from pokemon_sprite_generator_b200.trainer import FusedAdamW, TrainStep
 from pokemon_sprite_generator_b200.unet import UNet
 
+import faulthandler
+faulthandler.dump_traceback_later(int(os.environ.get("PSG_DUMP_AFTER", "240")), exit=True)      # a hang prints where, and ends the run
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -52,10 +54,11 @@ for t, n in zip(ts, noises):
     losses.append(loss.item() / world)
 torch.cuda.synchronize()
 stats = dict(step.grad_sync.stats)
+# (constructed on every rank: TrainStep's constructor broadcasts rank 0's replica, a collective; only rank 0 then trains it)
+ref = make()
+rstep = TrainStep(ref, NoiseScheduler().to(dev), FusedAdamW(ref, max_grad_norm=0.7))
+rstep.world, rstep.grad_sync = 1, None              # one process, whole batch
 if rank == 0:
-    ref = make()
-    rstep = TrainStep(ref, NoiseScheduler().to(dev), FusedAdamW(ref, max_grad_norm=0.7))
-    rstep.world, rstep.grad_sync = 1, None              # one process, whole batch
     rl = [rstep(latent, text, timesteps=t, noise=n).item() for t, n in zip(ts, noises)]
     num = den = 0.0
     for (k, a), (_, b) in zip(unet.named_parameters(), ref.named_parameters()):

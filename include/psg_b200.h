@@ -177,7 +177,7 @@ int psg_groupnorm_fused_plan(int B, int HW, int C, int G, int* out8);
  * previous mode.  psg_groupnorm_cluster_plan: out8 = {CC, cluster size, rows per CTA, R, TU, U, iters, smem bytes}.     */
 int psg_groupnorm_fused_mode(int mode);
 int psg_groupnorm_cluster_plan(int B, int HW, int C, int G, int bwd, int* out8);
-int psg_groupnorm_cluster_tune(int which, int value); /* measurement hook: 0 fwd threads, 1 bwd threads, 2 fwd slab bytes per CTA, 3 max cluster, 4 vectors per unit row, 5 bwd slab bytes */
+int psg_groupnorm_cluster_tune(int which, int value); /* measurement hook: 0 fwd threads, 1 bwd threads, 2 fwd slab bytes per CTA, 3 max cluster, 4 vectors per unit row, 5 bwd slab bytes, 6 L2 prefetch one residency ahead (0 off / 1 auto / resident CTAs) */
 int psg_groupnorm_fused_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float* gamma, const float* beta,
                             float* stats, int B, int HW, int C, int G, float eps, int act, void* stream);
 int psg_groupnorm_fused_bwd(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,

@@ -18,6 +18,8 @@
 // Every reduction is fixed-order: results are run-to-run bit-identical.  Other shapes fall back to norm_fused.cu.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "norm_cluster.h"
 #include "psg_common.cuh"
 
@@ -31,8 +33,11 @@ constexpr size_t kSmemLimit = 200 * 1024;
 
 // tunables (psg_groupnorm_cluster_tune): {fwd threads, bwd threads, fwd bytes of x per CTA, largest cluster, 16-byte
 // vectors per pixel row of a unit (20: 160 channels = 320 B rows; 10: 80 channels = 160 B rows; 0: by shape), bwd bytes
-// of x per CTA (0: by shape)}.  Defaults from tools/sweep_gn.py on B200 (profiles/r01_bench_groupnorm_v2.txt).
-static int g_tune[6] = {160, 160, 32 * 1024, 8, 0, 0};
+// of x per CTA (0: by shape), L2 prefetch of the rows of the CTA that will run one residency later (0: off, 1: distance
+// from the occupancy estimate below, > 1: that many resident CTAs)}.  Defaults from tools/sweep_gn.py on B200
+// (profiles/r01_bench_groupnorm_v2.txt); the environment variable PSG_GN_PREFETCH overrides entry 6 (A/B runs).
+static int g_tune[7] = {160, 160, 32 * 1024, 8, 0, 0, 296};
+static bool g_tune_env_read = false;
 
 struct Shape {
   int B, HW, C, G, cpg;
@@ -40,6 +45,8 @@ struct Shape {
   int S, rp;                   // cluster size, pixel rows per CTA
   int R, TU, U, iters;         // rows in flight per unit, threads per unit, units per block, pixel iterations
   int threads;
+  int pf;                      // L2 prefetch distance in units (the same rank of the cluster `pf` units ahead); 0 = none
+  int strict;                  // 1: every thread arrives with .release (A/B switch, env PSG_GN_STRICT_BARRIER=1)
 };
 
 static int plan(Shape& s, int B, int HW, int C, int G, int bwd) {
@@ -72,7 +79,39 @@ static int plan(Shape& s, int B, int HW, int C, int G, int bwd) {
     }
     if (r >= s.rp) break;
   }
+  s.pf = 0;
   return best < 0.0 ? -1 : 0;
+}
+
+static size_t fwd_smem(const Shape& s);
+static size_t bwd_smem(const Shape& s);
+// The CTAs of a grid start in blockIdx order, so the CTA that takes over a slot of this SM generation is (about) one
+// residency ahead: resident CTAs = 148 SMs x min(shared-memory, register, warp limits).  Each CTA asks L2 for that
+// CTA's rows right after it has requested its own, so the later CTA's load phase is an L2 hit and DRAM keeps
+// streaming while the resident CTAs reduce and store (the kernels are latency bound, profiles/r01_ncu_groupnorm_v3.md).
+static void plan_prefetch(Shape& s, int bwd) {
+  if (!g_tune_env_read) {
+    g_tune_env_read = true;
+    if (const char* e = getenv("PSG_GN_PREFETCH")) g_tune[6] = atoi(e);
+  }
+  s.pf = 0;
+  static const int strict = getenv("PSG_GN_STRICT_BARRIER") ? atoi(getenv("PSG_GN_STRICT_BARRIER")) : 0;
+  s.strict = strict;
+  if (g_tune[6] <= 0) return;
+  int resident = g_tune[6];
+  if (resident == 1) {
+    const size_t smem = (bwd ? bwd_smem(s) : fwd_smem(s)) + 1024;
+    int per_sm = (int)((size_t)227 * 1024 / smem);
+    const int by_regs = 65536 / ((bwd ? 96 : 64) * ((s.threads + 31) / 32 * 32));
+    if (per_sm > by_regs) per_sm = by_regs;
+    if (per_sm > 2048 / s.threads) per_sm = 2048 / s.threads;
+    if (per_sm < 1) per_sm = 1;
+    resident = 148 * per_sm;
+  }
+  const int per_cta_units = s.S > 1 ? 1 : s.U;
+  int pf = resident / (s.S * per_cta_units);           // units one residency ahead
+  if (pf < 1) pf = 1;
+  s.pf = pf * per_cta_units;                           // whole CTAs ahead (U units per CTA when S == 1)
 }
 
 static size_t fwd_smem(const Shape& s) {
@@ -121,12 +160,26 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_s
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float tanh_approx(float x) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
   return t;
 }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// Cluster barrier, arrive side.  `barrier.cluster.arrive.release` costs every thread a MEMBAR.ALL.GPU (SASS; 10 % of a
+// CTA's lifetime in the ncu stall samples, profiles/r01_ncu_groupnorm_v3.md).  The data handed over is the CTA's
+// shared-memory partial sums, already ordered before thread 0 by the __syncthreads() that precedes every call, so ONE
+// cluster-scope fence by thread 0 followed by relaxed arrivals publishes them (release cumulativity through the CTA
+// barrier).  The second barrier of a kernel only says "I have finished reading your shared memory": no fence at all.
+__device__ __forceinline__ void cluster_arrive_publish(bool leader, int strict) {
+  if (strict) { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); return; }
+  if (leader) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_arrive_done(int strict) {
+  if (strict) { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); return; }
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void load8(const float* p, float2 (&v)[4]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
@@ -169,6 +222,13 @@ __global__ void __launch_bounds__(kMaxThreads, 2) gn_cluster_fwd_kernel(const __
     for (int k = 0, p = row; k < s.iters; ++k, p += s.R, src += step, dst += (uint32_t)T * 16) {
       const bool ok = p < nrows;
       cp_async16(dst, ok ? src : x, ok ? 16 : 0);
+    }
+    // the same rows of the unit that runs one residency later: one request per 128-byte line of a row piece
+    const int unit_pf = unit + s.pf;
+    if (s.pf > 0 && (v & 7) == 0 && unit_pf < s.B * s.chunks) {
+      const int b2 = unit_pf / s.chunks, ch2 = unit_pf - b2 * s.chunks;
+      const __nv_bfloat16* px = x + ((long long)b2 * s.HW + row0 + row) * ld + ch2 * kCC + v * 8;
+      for (int p = row; p < nrows; p += s.R, px += step) prefetch_l2(px);
     }
   }
   float2 ga[4], be[4];      // affine parameters: fetched while the slab is in flight
@@ -218,7 +278,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) gn_cluster_fwd_kernel(const __
   __syncthreads();
   const float inv_m = 1.f / ((float)CPG * (float)s.HW);
   if (s.S > 1) {
-    cluster_arrive();
+    cluster_arrive_publish(tid == 0, s.strict);
     cluster_wait();                                    // every CTA's part[] is visible cluster-wide
     if (tid < NG) {
       cg::cluster_group cluster = cg::this_cluster();
@@ -242,7 +302,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) gn_cluster_fwd_kernel(const __
     if (active) *reinterpret_cast<float2*>(stats + ((long long)b * s.G + ch * NG + tu) * 2) = make_float2(mean, rstd);
   }
   __syncthreads();
-  if (s.S > 1) cluster_arrive();                       // done reading the peers' shared memory (waited on before exit)
+  if (s.S > 1) cluster_arrive_done(s.strict);                  // done reading the peers' shared memory (waited on before exit)
   if (active) {
     float2 sc[4], sh[4];      // n = x * sc + sh;  with SiLU: h = n / 2 and y = h + h * tanh(h)
     {
@@ -336,6 +396,17 @@ __global__ void __launch_bounds__(kMaxThreads / 2 + 64, 2) gn_cluster_bwd_kernel
       cp_async16(dst, ok ? sx : x, ok ? 16 : 0);
       cp_async16(dst + off_d, ok ? sd : dy, ok ? 16 : 0);
     }
+    // the same rows of the unit that runs one residency later: one request per 128-byte line of a row piece
+    const int unit_pf = unit + s.pf;
+    if (s.pf > 0 && (v & 7) == 0 && unit_pf < s.B * s.chunks) {
+      const int b2 = unit_pf / s.chunks, ch2 = unit_pf - b2 * s.chunks;
+      const __nv_bfloat16* px = x + ((long long)b2 * s.HW + row0 + row) * ld + ch2 * kCC + v * 8;
+      const __nv_bfloat16* pd = dy + ((long long)b2 * s.HW + row0 + row) * lddy + ch2 * kCC + v * 8;
+      for (int p = row; p < nrows; p += s.R, px += stepx, pd += stepd) {
+        prefetch_l2(px);
+        prefetch_l2(pd);
+      }
+    }
   }
   // per-channel constants while the slab is in flight:  rs, nmr = -mean*rs,  h = x*ah + bh (= n/2)
   float gam = 0.f;
@@ -410,7 +481,7 @@ __global__ void __launch_bounds__(kMaxThreads / 2 + 64, 2) gn_cluster_bwd_kernel
   // totals over the cluster (rank order: identical bits in every CTA), converted to the centred sums s1, s2, s3
   float s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (s.S > 1) {
-    cluster_arrive();
+    cluster_arrive_publish(tid == 0, s.strict);
     cluster_wait();                                       // every CTA's chan[] is visible cluster-wide
     if (tid < kCC) {
       cg::cluster_group cluster = cg::this_cluster();
@@ -439,7 +510,7 @@ __global__ void __launch_bounds__(kMaxThreads / 2 + 64, 2) gn_cluster_bwd_kernel
     tot[(u * 3 + 1) * kCC + tu] = gam * s2;
   }
   __syncthreads();
-  if (s.S > 1) cluster_arrive();                          // done reading the peers' shared memory (waited on before exit)
+  if (s.S > 1) cluster_arrive_done(s.strict);                     // done reading the peers' shared memory (waited on before exit)
   if (tu < 2 * NG) {
     const int stat = tu & 1, g = tu >> 1;
     const float* sv = tot + (u * 3 + stat) * kCC + g * CPG;
@@ -580,9 +651,10 @@ static int run_bwd(const Shape& s, const void* dy, long long ld_dy, const void* 
   }
 
 int gnc_tune(int which, int value) {
-  if (which < 0 || which > 5) return -1;
+  if (which < 0 || which > 6) return -1;
   if (which == 4 && value > 0 && value != 10 && value != 20) return -1;
   const int prev = gnc::g_tune[which];
+  if (which == 6 && value >= 0) gnc::g_tune_env_read = true;   // an explicit setting wins over the environment
   if (value > 0 || (value == 0 && which >= 4)) gnc::g_tune[which] = value;
   return prev;
 }
@@ -605,6 +677,7 @@ int gnc_fwd(const void* x, long long ld_x, void* y, long long ld_y, const float*
             int HW, int C, int G, float eps, int act, cudaStream_t stream) {
   gnc::Shape s;
   if (gnc::plan(s, B, HW, C, G, 0) != 0 || gnc::fwd_smem(s) > gnc::kSmemLimit) return PSG_ERR_UNSUPPORTED;
+  gnc::plan_prefetch(s, 0);
 #define FN run_fwd
   GNC_DISPATCH(s, x, ld_x, y, ld_y, gamma, beta, stats, eps, stream)
 #undef FN
@@ -615,6 +688,7 @@ int gnc_bwd(const void* dy, long long ld_dy, const void* x, long long ld_x, void
             int act, int accumulate_dx, cudaStream_t stream) {
   gnc::Shape s;
   if (gnc::plan(s, B, HW, C, G, 1) != 0 || gnc::bwd_smem(s) > gnc::kSmemLimit) return PSG_ERR_UNSUPPORTED;
+  gnc::plan_prefetch(s, 1);
 #define FN run_bwd
   GNC_DISPATCH(s, dy, ld_dy, x, ld_x, dx, ld_dx, gamma, beta, stats, partial, dx_colsum, ld_colsum, accumulate_dx, stream)
 #undef FN

@@ -5,7 +5,8 @@
 #include <cuda_runtime.h>
 
 // tunables: which = 0 fwd threads, 1 bwd threads, 2 fwd bytes of x per CTA, 3 largest cluster, 4 vectors per unit row
-// (10 / 20 / 0 = by shape), 5 bwd bytes of x per CTA (0 = by shape); value < 0 only reads
+// (10 / 20 / 0 = by shape), 5 bwd bytes of x per CTA (0 = by shape), 6 L2 prefetch one residency ahead (0 off, 1 auto,
+// > 1 resident CTAs assumed; env PSG_GN_PREFETCH sets the start value); value < 0 only reads
 int gnc_tune(int which, int value);
 int gnc_supported(int B, int HW, int C, int G, int bwd);
 // out = {CC, S (cluster size), rows per CTA, R, TU, U, iters, smem bytes}

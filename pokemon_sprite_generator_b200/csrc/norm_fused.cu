@@ -374,8 +374,20 @@ __global__ void __launch_bounds__(512) gn_fused_param_grad_kernel(const float* _
   const int c = blockIdx.x * 32 + tx;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f;
   if (c < C) {
-    for (int r = ty; r < B; r += 16) {
-      const float* p = partial + ((long long)r * C + c) * 3;
+    const float* p = partial + ((long long)ty * C + c) * 3;
+    const long long step = (long long)16 * C * 3;
+    int r = ty;
+    for (; r + 48 < B; r += 64, p += 4 * step) {       // four rows' loads in flight per thread (the fold is latency bound)
+      const float a0 = p[0], a1 = p[1], a2 = p[2];
+      const float b0 = p[step], b1 = p[step + 1], b2 = p[step + 2];
+      const float c0 = p[2 * step], c1 = p[2 * step + 1], c2 = p[2 * step + 2];
+      const float d0 = p[3 * step], d1 = p[3 * step + 1], d2 = p[3 * step + 2];
+      t0 += a0; t1 += a1; t2 += a2;
+      t0 += b0; t1 += b1; t2 += b2;
+      t0 += c0; t1 += c1; t2 += c2;
+      t0 += d0; t1 += d1; t2 += d2;
+    }
+    for (; r < B; r += 16, p += step) {
       t0 += p[0];
       t1 += p[1];
       t2 += p[2];

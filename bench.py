@@ -534,7 +534,7 @@ def main():
         for name, s0, s1 in calls:
             tot[name] = tot.get(name, 0.0) + s0.elapsed_time(s1)
         n_act, n_par = 6403520 * B, sum(p.numel() for p in unet.parameters())
-        fams = {"groupnorm_fwd": ("psg_groupnorm_fused_fwd", 2 * n_act * 2), "groupnorm_bwd": ("psg_groupnorm_fused_bwd", 3 * n_act * 2),
+        fams = {"groupnorm_fwd": ("psg_groupnorm_fused_fwd", 2 * n_act * 2), "groupnorm_bwd": ("psg_groupnorm_fused_bwd_ws", 3 * n_act * 2),
                 "adamw": ("psg_adam_step", 30 * n_par), "grad_sumsq": ("psg_sumsq", 4 * n_par)}
         hbm_kernels = {"peak_gbs": peaks["hbm_gbs"], "peak_source": f"{peaks['src']} copy bandwidth"}
         for fam, (cname, nbytes) in fams.items():

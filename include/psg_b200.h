@@ -174,7 +174,7 @@ int psg_groupnorm_fused_plan(int B, int HW, int C, int G, int* out8);
 /* The fused entry points run the cluster-split kernels (norm_cluster.cu: pixels of a (sample, 160-channel) unit split over
  * the CTAs of a thread-block cluster, partial sums exchanged through distributed shared memory) where their plan applies
  * and the slab kernels otherwise.  psg_groupnorm_fused_mode(1) forces the slab kernels (A/B measurements); returns the
- * previous mode.  psg_groupnorm_cluster_plan: out8 = {CC, cluster size, rows per CTA, R, TU, U, iters, smem bytes}.     */
+ * previous mode (modes 2 / 3: see psg_groupnorm_fused_bwd_ws).  psg_groupnorm_cluster_plan: out8 = {CC, cluster size, rows per CTA, R, TU, U, iters, smem bytes}.     */
 int psg_groupnorm_fused_mode(int mode);
 int psg_groupnorm_cluster_plan(int B, int HW, int C, int G, int bwd, int* out8);
 int psg_groupnorm_cluster_tune(int which, int value); /* measurement hook: 0 fwd threads, 1 bwd threads, 2 fwd slab bytes per CTA, 3 max cluster, 4 vectors per unit row, 5 bwd slab bytes, 6 L2 prefetch one residency ahead (0 off / 1 auto / resident CTAs) */
@@ -184,6 +184,20 @@ int psg_groupnorm_fused_bwd(const void* dy, long long ld_dy, const void* x, long
                             const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta,
                             float* workspace, float* dx_colsum, long long ld_colsum, float* bias_total, int B, int HW, int C, int G,
                             int act, int accumulate_dx, int accumulate_params, void* stream);
+/* The same with the workspace size stated: >= psg_groupnorm_bwd_workspace_floats(...) floats lets the backward of tensors beyond
+ * the L2 (27x27 / 14x14 levels at batch 256) run as the streaming two-phase kernel (norm_stream.cu: per-chunk raw moments,
+ * then dx out of an L2-resident sample group, one launch); psg_groupnorm_fused_bwd == this with B*C*3 floats.
+ * psg_groupnorm_fused_mode: 0 auto, 1 slab kernels only, 2 streaming backward whenever its plan applies, 3 auto without it.
+ * psg_groupnorm_stream_tune: 0 bytes of x + dy per L2 group, 1 pixel rows per chunk, 2 smallest tensor (bytes of x) routed
+ * to it.  psg_groupnorm_timeout_flag: test hook, 1 if a bounded in-kernel wait expired since the last call (synchronises). */
+int psg_groupnorm_fused_bwd_ws(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,
+                               const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta,
+                               float* workspace, long long workspace_floats, float* dx_colsum, long long ld_colsum, float* bias_total,
+                               int B, int HW, int C, int G, int act, int accumulate_dx, int accumulate_params, void* stream);
+long long psg_groupnorm_bwd_workspace_floats(int B, int HW, int C, int G);
+long long psg_groupnorm_stream_tune(int which, long long value);
+int psg_groupnorm_stream_plan(int B, int HW, int C, int G, int* out8);
+int psg_groupnorm_timeout_flag(void);
 
 /* ---- attention core  nn.MultiheadAttention(batch_first) softmax(QK^T/sqrt(d))V, src/models/unet.py:160-173,217,235 */
 int psg_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,

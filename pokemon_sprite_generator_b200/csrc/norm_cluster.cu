@@ -98,6 +98,10 @@ static void plan_prefetch(Shape& s, int bwd) {
   static const int strict = getenv("PSG_GN_STRICT_BARRIER") ? atoi(getenv("PSG_GN_STRICT_BARRIER")) : 0;
   s.strict = strict;
   if (g_tune[6] <= 0) return;
+  // forward only by default: the backward is not waiting for DRAM (same time with and without, profiles/
+  // r02_bench_groupnorm_prefetch_sweep.txt) and the requests cost it 7 % more instructions; PSG_GN_PREFETCH_BWD=1 for A/B
+  static const int bwd_too = getenv("PSG_GN_PREFETCH_BWD") ? atoi(getenv("PSG_GN_PREFETCH_BWD")) : 0;
+  if (bwd && !bwd_too) return;
   int resident = g_tune[6];
   if (resident == 1) {
     const size_t smem = (bwd ? bwd_smem(s) : fwd_smem(s)) + 1024;

@@ -18,9 +18,13 @@
 // reductions): that is the gradient of the conv bias / broadcast conditioning that produced x (unet.py:116-124), which
 // saves a separate column-sum pass over dx.
 #include "norm_cluster.h"
+#include "norm_stream.h"
 #include "psg_common.cuh"
 
-static int g_gn_mode = 0;   // 0: cluster-split kernels where their plan applies, else the slab kernels; 1: slab kernels only
+// 0: backward of tensors beyond the L2 by the streaming two-phase kernel (norm_stream.cu), cluster-split kernels where their plan
+// applies, else the slab kernels; 1: slab kernels only; 2: streaming backward whenever its plan applies (tests); 3: as 0
+// without the streaming backward (A/B)
+static int g_gn_mode = 0;
 
 namespace gnf {
 
@@ -365,47 +369,48 @@ __global__ void __launch_bounds__(kMaxThreads) gn_fused_bwd_kernel(const __nv_bf
 }
 
 // dbeta[c] = sum_b partial[b][c][0]; dgamma[c] = sum_b partial[b][c][1]; bias_total[c] = sum_b partial[b][c][2].
-// 32 channels x 16 sample-lanes per block, fixed-order fold.
-__global__ void __launch_bounds__(512) gn_fused_param_grad_kernel(const float* __restrict__ partial, int B, int C,
-                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                  float* __restrict__ bias_total, int accumulate) {
-  __shared__ float sh[16][32][3];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-  if (c < C) {
-    const float* p = partial + ((long long)ty * C + c) * 3;
-    const long long step = (long long)16 * C * 3;
+// 8 channels x 64 sample-lanes per block (C / 8 blocks: the 10-block grid of the earlier 32 x 16 shape took 7 us per norm
+// at C = 320, latency bound: profiles/r02_ncu_groupnorm_stream_bwd.md), every lane's rows in flight together, fixed-order fold.
+constexpr int kPgCh = 8, kPgLanes = 64;
+__global__ void __launch_bounds__(kPgCh * kPgLanes) gn_fused_param_grad_kernel(const float* __restrict__ partial, int B, int C,
+                                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                               float* __restrict__ bias_total, int accumulate) {
+  __shared__ float sh[kPgLanes][kPgCh * 3];
+  const int tx = threadIdx.x % (kPgCh * 3), ty = threadIdx.x / (kPgCh * 3);     // 24 consecutive floats of a row x 21 row lanes
+  constexpr int kRowLanes = kPgCh * kPgLanes / (kPgCh * 3);                       // 21 (8 threads idle)
+  const int c0 = blockIdx.x * kPgCh;
+  const int ncol = min(kPgCh, C - c0) * 3;
+  float t = 0.f;
+  if (ty < kRowLanes && tx < ncol) {
+    const float* p = partial + ((long long)ty * C + c0) * 3 + tx;
+    const long long step = (long long)kRowLanes * C * 3;
     int r = ty;
-    for (; r + 48 < B; r += 64, p += 4 * step) {       // four rows' loads in flight per thread (the fold is latency bound)
-      const float a0 = p[0], a1 = p[1], a2 = p[2];
-      const float b0 = p[step], b1 = p[step + 1], b2 = p[step + 2];
-      const float c0 = p[2 * step], c1 = p[2 * step + 1], c2 = p[2 * step + 2];
-      const float d0 = p[3 * step], d1 = p[3 * step + 1], d2 = p[3 * step + 2];
-      t0 += a0; t1 += a1; t2 += a2;
-      t0 += b0; t1 += b1; t2 += b2;
-      t0 += c0; t1 += c1; t2 += c2;
-      t0 += d0; t1 += d1; t2 += d2;
-    }
-    for (; r < B; r += 16, p += step) {
-      t0 += p[0];
-      t1 += p[1];
-      t2 += p[2];
-    }
-  }
-  sh[ty][tx][0] = t0;
-  sh[ty][tx][1] = t1;
-  sh[ty][tx][2] = t2;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+    for (; r + 7 * kRowLanes < B; r += 8 * kRowLanes, p += 8 * step) {      // eight rows' loads in flight per thread (latency bound)
+      float a[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { u0 += sh[k][tx][0]; u1 += sh[k][tx][1]; u2 += sh[k][tx][2]; }
-    dbeta[c] = accumulate ? dbeta[c] + u0 : u0;
-    dgamma[c] = accumulate ? dgamma[c] + u1 : u1;
-    if (bias_total) bias_total[c] = u2;
+      for (int k = 0; k < 8; ++k) a[k] = p[k * step];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += a[k];
+    }
+    for (; r + 3 * kRowLanes < B; r += 4 * kRowLanes, p += 4 * step) {
+      const float a = p[0], b = p[step], c = p[2 * step], d = p[3 * step];
+      t += a; t += b; t += c; t += d;
+    }
+    for (; r < B; r += kRowLanes, p += step) t += p[0];
+  }
+  if (ty < kRowLanes) sh[ty][tx] = t;
+  __syncthreads();
+  if (threadIdx.x < ncol) {
+    float u = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRowLanes; ++k) u += sh[k][threadIdx.x];
+    const int c = c0 + threadIdx.x / 3, stat = threadIdx.x % 3;
+    if (stat == 0) dbeta[c] = accumulate ? dbeta[c] + u : u;
+    else if (stat == 1) dgamma[c] = accumulate ? dgamma[c] + u : u;
+    else if (bias_total) bias_total[c] = u;
   }
 }
+#define PSG_GN_PARAM_GRAD_GRID(C) (((C) + gnf::kPgCh - 1) / gnf::kPgCh), (gnf::kPgCh * gnf::kPgLanes)
 
 static size_t fwd_smem(const FShape& s) {
   return (size_t)s.iters * s.threads * 16 + ((size_t)s.threads * kPS + (size_t)s.U * s.NG * 2) * sizeof(float);
@@ -423,7 +428,7 @@ extern "C" {
 // 1 if the single-pass kernels handle this problem (bf16, slab fits in shared memory); else the two-pass kernels run.
 int psg_groupnorm_fused_mode(int mode) {
   const int prev = g_gn_mode;
-  if (mode == 0 || mode == 1) g_gn_mode = mode;
+  if (mode >= 0 && mode <= 3) g_gn_mode = mode;
   return prev;
 }
 
@@ -439,7 +444,7 @@ int psg_groupnorm_cluster_plan(int B, int HW, int C, int G, int bwd, int* out) {
 
 int psg_groupnorm_fused_ok(int B, int HW, int C, int G, int dtype) {
   if (dtype != PSG_DTYPE_BF16) return 0;
-  if (g_gn_mode == 0 && gnc_supported(B, HW, C, G, 0) && gnc_supported(B, HW, C, G, 1)) return 1;
+  if (g_gn_mode != 1 && gnc_supported(B, HW, C, G, 0) && gnc_supported(B, HW, C, G, 1)) return 1;
   gnf::FShape s;
   if (gnf::plan(s, B, HW, C, G) != 0) return 0;
   return gnf::bwd_smem(s) <= gnf::kSmemLimit ? 1 : 0;
@@ -461,7 +466,7 @@ int psg_groupnorm_fused_fwd(const void* x, long long ld_x, void* y, long long ld
   PSG_CHECK_ARG(ld_x % 8 == 0 && ld_y % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
                     ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0),
                 "psg_groupnorm_fused_fwd: pitches/pointers must be 16B aligned");
-  if (g_gn_mode == 0) {
+  if (g_gn_mode != 1) {
     const int rc = gnc_fwd(x, ld_x, y, ld_y, gamma, beta, stats, B, HW, C, G, eps, act, (cudaStream_t)stream);
     if (rc != PSG_ERR_UNSUPPORTED) return rc;
   }
@@ -484,21 +489,34 @@ int psg_groupnorm_fused_fwd(const void* x, long long ld_x, void* y, long long ld
 
 // workspace floats >= B*C*3.  dx_colsum [B, ld_colsum] and bias_total [C] are optional (null): the per-(sample, channel)
 // and per-channel sums over pixels of dx (written, not accumulated; valid only when accumulate_dx == 0).
-int psg_groupnorm_fused_bwd(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,
-                            const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta,
-                            float* workspace, float* dx_colsum, long long ld_colsum, float* bias_total, int B, int HW, int C, int G,
-                            int act, int accumulate_dx, int accumulate_params, void* stream) {
+// workspace_floats: size of `workspace`; >= psg_groupnorm_bwd_workspace_floats(B, HW, C, G) enables the streaming two-phase
+// backward for tensors beyond the L2 (norm_stream.cu); with B*C*3 floats the single-pass kernels run.
+int psg_groupnorm_fused_bwd_ws(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,
+                               const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta,
+                               float* workspace, long long workspace_floats, float* dx_colsum, long long ld_colsum, float* bias_total,
+                               int B, int HW, int C, int G, int act, int accumulate_dx, int accumulate_params, void* stream) {
   using namespace gnf;
+  PSG_CHECK_ARG(workspace_floats >= (long long)B * C * 3, "psg_groupnorm_fused_bwd: workspace of %lld floats < B*C*3", workspace_floats);
   PSG_CHECK_ARG(dy && x && dx && gamma && beta && stats && dgamma && dbeta && workspace, "psg_groupnorm_fused_bwd: null pointer");
   PSG_CHECK_ARG(!(accumulate_dx && (dx_colsum || bias_total)), "psg_groupnorm_fused_bwd: column sums of dx need accumulate_dx == 0");
   PSG_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) &&
                     ((uintptr_t)dx % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0),
                 "psg_groupnorm_fused_bwd: pitches/pointers must be 16B aligned");
-  if (g_gn_mode == 0) {
+  if ((g_gn_mode == 0 && gns_wants(B, HW, C)) || g_gn_mode == 2) {
+    const int rc = gns_bwd(dy, ld_dy, x, ld_x, dx, ld_dx, gamma, beta, stats, workspace, workspace_floats, dx_colsum, ld_colsum, B, HW, C, G,
+                           act, accumulate_dx, (cudaStream_t)stream);
+    if (rc == PSG_OK) {
+      gn_fused_param_grad_kernel<<<PSG_GN_PARAM_GRAD_GRID(C), 0, (cudaStream_t)stream>>>(workspace, B, C, dgamma, dbeta, bias_total, accumulate_params);
+      PSG_CHECK_LAUNCH("psg_groupnorm_fused_bwd");
+      return PSG_OK;
+    }
+    if (rc != PSG_ERR_UNSUPPORTED) return rc;
+  }
+  if (g_gn_mode != 1) {
     const int rc = gnc_bwd(dy, ld_dy, x, ld_x, dx, ld_dx, gamma, beta, stats, workspace, dx_colsum, ld_colsum, B, HW, C, G, act,
                            accumulate_dx, (cudaStream_t)stream);
     if (rc == PSG_OK) {
-      gn_fused_param_grad_kernel<<<(C + 31) / 32, 512, 0, (cudaStream_t)stream>>>(workspace, B, C, dgamma, dbeta, bias_total, accumulate_params);
+      gn_fused_param_grad_kernel<<<PSG_GN_PARAM_GRAD_GRID(C), 0, (cudaStream_t)stream>>>(workspace, B, C, dgamma, dbeta, bias_total, accumulate_params);
       PSG_CHECK_LAUNCH("psg_groupnorm_fused_bwd");
       return PSG_OK;
     }
@@ -519,10 +537,35 @@ int psg_groupnorm_fused_bwd(const void* dy, long long ld_dy, const void* x, long
   gn_fused_bwd_kernel<<<grid, s.threads, bwd_smem(s), st>>>((const __nv_bfloat16*)dy, ld_dy, (const __nv_bfloat16*)x, ld_x,
                                                             (__nv_bfloat16*)dx, ld_dx, gamma, beta, stats, s, workspace, dx_colsum,
                                                             ld_colsum, act, accumulate_dx);
-  gn_fused_param_grad_kernel<<<(C + 31) / 32, 512, 0, st>>>(workspace, B, C, dgamma, dbeta, bias_total, accumulate_params);
+  gn_fused_param_grad_kernel<<<PSG_GN_PARAM_GRAD_GRID(C), 0, st>>>(workspace, B, C, dgamma, dbeta, bias_total, accumulate_params);
   PSG_CHECK_LAUNCH("psg_groupnorm_fused_bwd");
   g_psg_launch_count += 1;  // two kernels
   return PSG_OK;
 }
+
+
+int psg_groupnorm_fused_bwd(const void* dy, long long ld_dy, const void* x, long long ld_x, void* dx, long long ld_dx,
+                            const float* gamma, const float* beta, const float* stats, float* dgamma, float* dbeta,
+                            float* workspace, float* dx_colsum, long long ld_colsum, float* bias_total, int B, int HW, int C, int G,
+                            int act, int accumulate_dx, int accumulate_params, void* stream) {
+  return psg_groupnorm_fused_bwd_ws(dy, ld_dy, x, ld_x, dx, ld_dx, gamma, beta, stats, dgamma, dbeta, workspace, (long long)B * C * 3,
+                                    dx_colsum, ld_colsum, bias_total, B, HW, C, G, act, accumulate_dx, accumulate_params, stream);
+}
+
+// floats of workspace that let psg_groupnorm_fused_bwd_ws pick any of its kernels for this shape (>= B*C*3)
+long long psg_groupnorm_bwd_workspace_floats(int B, int HW, int C, int G) {
+  const long long base = (long long)B * C * 3, st = gns_workspace_floats(B, HW, C, G);
+  return st > base ? st : base;
+}
+// streaming backward: tunables (0 bytes of x + dy per L2-resident sample group, 1 pixel rows per chunk, 2 smallest tensor in bytes
+// of x that the auto mode routes to it; value < 0 only reads; returns the previous value) and plan
+// (out8 = {vectors per row, row lanes, threads, rows per chunk, chunks per sample, samples per group, smem bytes, grid})
+long long psg_groupnorm_stream_tune(int which, long long value) { return gns_tune(which, value); }
+int psg_groupnorm_stream_plan(int B, int HW, int C, int G, int* out) {
+  PSG_CHECK_ARG(out && gns_plan(B, HW, C, G, out) == 0, "psg_groupnorm_stream_plan: unsupported shape B=%d HW=%d C=%d G=%d", B, HW, C, G);
+  return PSG_OK;
+}
+// Test hook: 1 if an apply CTA's bounded wait for its sample's moments expired since the last call (synchronises the device).
+int psg_groupnorm_timeout_flag() { return gns_timeout_flag(); }
 
 }  // extern "C"

@@ -193,9 +193,12 @@ def groupnorm_fused_bwd(dy: torch.Tensor, x: torch.Tensor, dx: torch.Tensor, gam
                         accumulate_dx: bool, dx_colsum: torch.Tensor | None = None, bias_total: torch.Tensor | None = None) -> None:
     """dx_colsum [b, C] (row pitch free) / bias_total [C]: optional sums over pixels of dx per (sample, channel) / per channel."""
     rows, c = x.shape
-    ws = workspace(x.device, b * c * 3, "gn")
-    L.call("psg_groupnorm_fused_bwd", L.ptr(dy), C.c_longlong(_ld(dy)), L.ptr(x), C.c_longlong(_ld(x)), L.ptr(dx), C.c_longlong(_ld(dx)),
-           L.ptr(gamma), L.ptr(beta), L.ptr(stats), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), L.ptr(dx_colsum),
+    lib = L.load()
+    lib.psg_groupnorm_bwd_workspace_floats.restype = C.c_longlong
+    need = int(lib.psg_groupnorm_bwd_workspace_floats(C.c_int(b), C.c_int(rows // b), C.c_int(c), C.c_int(groups)))
+    ws = workspace(x.device, max(need, b * c * 3), "gn")
+    L.call("psg_groupnorm_fused_bwd_ws", L.ptr(dy), C.c_longlong(_ld(dy)), L.ptr(x), C.c_longlong(_ld(x)), L.ptr(dx), C.c_longlong(_ld(dx)),
+           L.ptr(gamma), L.ptr(beta), L.ptr(stats), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), C.c_longlong(ws.numel()), L.ptr(dx_colsum),
            C.c_longlong(dx_colsum.stride(0) if dx_colsum is not None else 0), L.ptr(bias_total), C.c_int(b), C.c_int(rows // b),
            C.c_int(c), C.c_int(groups), C.c_int(int(silu)), C.c_int(int(accumulate_dx)), C.c_int(0), L.stream_ptr())
 
@@ -326,7 +329,7 @@ def check_kernel_timeouts() -> None:
     never hang the GPU on a protocol fault, they raise a device flag and fall through with incomplete results -- which must
     not go unnoticed.  Synchronises the device: call at log points, not per step."""
     lib = L.load()
-    gemm, attn = int(lib.psg_umma_timeout_flag()), int(lib.psg_attn_umma_timeout_flag())
-    if gemm or attn:
-        raise L.PsgError(f"a bounded barrier wait expired inside a tcgen05 kernel (gemm={gemm}, attention={attn}): results since the "
-                         "last check are not trustworthy")
+    gemm, attn, gn = int(lib.psg_umma_timeout_flag()), int(lib.psg_attn_umma_timeout_flag()), int(lib.psg_groupnorm_timeout_flag())
+    if gemm or attn or gn:
+        raise L.PsgError(f"a bounded in-kernel wait expired (tcgen05 gemm={gemm}, attention={attn}, streaming GroupNorm backward={gn}): "
+                         "results since the last check are not trustworthy")

@@ -1,4 +1,5 @@
 """GPU parity tests of the non-GEMM kernels against plain PyTorch fp32 references of the same op."""
+import ctypes
 import math
 
 import pytest
@@ -63,16 +64,42 @@ def test_groupnorm_fwd_bwd(cuda_device, dtype, B, HW, C, G, silu, eps):
                                                (2, 196, 1280, 32, True, 1e-5), (2, 49, 2560, 32, True, 1e-5), (5, 49, 1280, 32, False, 1e-6),
                                                (5, 16, 1280, 32, False, 1e-6), (7, 16, 2560, 32, True, 1e-5), (1, 729, 64, 32, True, 1e-5),
                                                (300, 16, 640, 32, True, 1e-5), (2, 100, 96, 8, True, 1e-5)])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_groupnorm_fused_fwd_bwd(cuda_device, B, HW, C, G, silu, eps, mode):
-    """Single-pass bf16 GroupNorm(+SiLU) forward/backward, including the free column sums of dx, vs torch fp32.
-    mode 0: cluster-split kernels where their plan applies (the U-Net shapes), slab kernels otherwise; mode 1: slab only."""
+    """Fused bf16 GroupNorm(+SiLU) forward/backward, including the free column sums of dx, vs torch fp32.
+    mode 0: as shipped (streaming two-phase backward for tensors beyond the L2, cluster-split kernels where their plan applies
+    (the U-Net shapes), slab kernels otherwise); mode 1: slab only; mode 2: streaming backward on every shape; mode 3: mode 0
+    without the streaming backward."""
     K = _ops()
     prev = K.L.load().psg_groupnorm_fused_mode(mode)
     try:
         _groupnorm_fused_case(K, B, HW, C, G, silu, eps)
+        assert K.L.load().psg_groupnorm_timeout_flag() == 0
     finally:
         K.L.load().psg_groupnorm_fused_mode(prev)
+
+
+@pytest.mark.parametrize("B,HW,C,G,silu,group_bytes,rows", [(5, 196, 640, 32, True, 1100 * 1024, 0), (7, 729, 320, 32, True, 3 << 20, 40),
+                                                            (3, 196, 1280, 32, False, 1 << 20, 7), (9, 49, 2560, 32, True, 1 << 20, 0)])
+def test_groupnorm_stream_bwd_groups_and_chunks(cuda_device, B, HW, C, G, silu, group_bytes, rows):
+    """Streaming backward with several L2 sample groups (ragged last one) and several pixel chunks per sample: the grid order
+    [stats of group g][apply of group g] and the per-sample ready counters, vs torch fp32; the bounded wait never expires."""
+    K = _ops()
+    lib = K.L.load()
+    lib.psg_groupnorm_stream_tune.restype = ctypes.c_longlong
+    prev = lib.psg_groupnorm_fused_mode(2)
+    t0 = lib.psg_groupnorm_stream_tune(0, ctypes.c_longlong(group_bytes))
+    t1 = lib.psg_groupnorm_stream_tune(1, ctypes.c_longlong(rows))
+    try:
+        out = (ctypes.c_int * 8)()
+        assert lib.psg_groupnorm_stream_plan(B, HW, C, G, out) == 0
+        assert out[5] < B and (rows == 0 or out[4] > 1), list(out)          # more than one group / chunk is what is under test
+        _groupnorm_fused_case(K, B, HW, C, G, silu, 1e-5)
+        assert lib.psg_groupnorm_timeout_flag() == 0
+    finally:
+        lib.psg_groupnorm_stream_tune(0, ctypes.c_longlong(t0))
+        lib.psg_groupnorm_stream_tune(1, ctypes.c_longlong(t1))
+        lib.psg_groupnorm_fused_mode(prev)
 
 
 def _groupnorm_fused_case(K, B, HW, C, G, silu, eps):

@@ -28,7 +28,13 @@ def timeit(fn, n=5):
 
 
 lib = K.L.load()
-ONLY = sys.argv[2] if len(sys.argv) > 2 else ""          # "cluster": time only the cluster-split kernels (for ncu)
+import ctypes
+import os
+lib.psg_groupnorm_stream_tune.restype = ctypes.c_longlong
+if os.environ.get("PSG_GNS_TUNE"):          # streaming backward: "group bytes,rows per chunk,min tensor bytes"
+    for i, v in enumerate(os.environ["PSG_GNS_TUNE"].split(",")):
+        lib.psg_groupnorm_stream_tune(i, ctypes.c_longlong(int(v)))
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ""          # "cluster" / "stream": time only that family (for ncu); "fast": both, no slab
 for hw, c in SHAPES:
     x = torch.randn(B * hw, c, device=dev).bfloat16()
     dy = torch.randn(B * hw, c, device=dev).bfloat16()
@@ -38,8 +44,8 @@ for hw, c in SHAPES:
     dg, db = torch.empty(c, device=dev), torch.empty(c, device=dev)
     nbytes = x.numel() * 2
     res = {}
-    for mode, name in ((0, "cluster"), (1, "slab")):
-        if ONLY and name != ONLY:
+    for mode, name in ((3, "cluster"), (2, "stream"), (1, "slab")):
+        if ONLY and name != ONLY and not (ONLY == "fast" and name != "slab"):
             continue
         lib.psg_groupnorm_fused_mode(mode)
         t_f = timeit(lambda: K.groupnorm_fused_fwd(x, y, gamma, beta, stats, B, 32, 1e-5, True))

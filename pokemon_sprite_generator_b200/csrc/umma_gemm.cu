@@ -30,6 +30,7 @@
 //
 // Replaces the ATen calls behind nn.Conv2d / nn.Linear / MHA projections on the reference hot path
 // (src/models/unet.py:80,90,96,160-187,325-399); SURVEY.md §2.1 K1-K3, K6-K9.
+#include <cstdlib>
 #include "gemm_desc.h"
 #include <cuda.h>
 #include <string.h>
@@ -1060,7 +1061,17 @@ int psg_umma_set_workspace(void* ws, size_t bytes) {
 }
 
 // Tile-shape heuristic shared by the auto path and psg_umma_plan.
-static void plan_tiles(int mode, int b_im2col, long long M, long long N, long long K, int* block_n, int* m_tiles) {
+// A plain (K-major, not im2col) TN product with whole 256-row pair tiles and 256-wide column tiles runs as cta_group::2 pairs of
+// 128-row CTAs: each CTA fetches half of the B tile (the operand bytes per FLOP of a 256 x 256 tile) and still keeps two TMEM
+// accumulator stages, so the epilogue overlaps the next tile's mainloop -- measured 3-8 % faster than the single 128 x 256 CTA
+// on the Linear / projection shapes of a batch-256 step and 10-33 % faster than the 256-row single-CTA tile the long-K rule
+// would pick (profiles/r02_bench_linear_tile_sweep.txt); M = 4096 is 2 % slower and keeps the single CTA.
+static bool tn_pairs(int mode, int a_plain, long long M, int block_n) {
+  static const bool enabled = !(getenv("PSG_TN_PAIRS") && atoi(getenv("PSG_TN_PAIRS")) == 0);      // A/B switch
+  return enabled && g_pairs_on >= 1 && mode == 0 && a_plain && block_n == 256 && M >= 8192 && M % (2 * umma::BLOCK_M) == 0;
+}
+
+static void plan_tiles(int mode, int b_im2col, int a_plain, long long M, long long N, long long K, int* block_n, int* m_tiles) {
   int bn = *block_n;
   if (bn == 0) {
     if (mode == 0) {
@@ -1082,6 +1093,7 @@ static void plan_tiles(int mode, int b_im2col, long long M, long long N, long lo
     if (M > 128 && ((mode == 1 && b_im2col && pad2 * 2 <= pad1 * 3) || (mode == 1 && !b_im2col && pad2 == pad1 && N >= 1024) ||
                     (mode != 1 && pad2 == pad1 && K >= 2048)))
       mt = 2;
+    if (tn_pairs(mode, a_plain, M, bn)) mt = 1;
   }
   *block_n = bn;
   *m_tiles = mt;
@@ -1091,7 +1103,7 @@ static void plan_tiles(int mode, int b_im2col, long long M, long long N, long lo
 int psg_umma_plan(const PsgGemmDesc* d, int* block_n, int* m_tiles) {
   PSG_CHECK_ARG(d && block_n && m_tiles, "psg_umma_plan: null pointer");
   const int mode = (d->a.mode == PSG_OP_MNMAJOR) ? 1 : ((d->b.mode == PSG_OP_MNMAJOR || d->b.mode == PSG_OP_CONVW_T) ? 2 : 0);
-  plan_tiles(mode, d->b.mode == PSG_OP_IM2COL_T, d->M, d->N, d->K, block_n, m_tiles);
+  plan_tiles(mode, d->b.mode == PSG_OP_IM2COL_T, d->a.mode == PSG_OP_KMAJOR, d->M, d->N, d->K, block_n, m_tiles);
   return PSG_OK;
 }
 
@@ -1120,18 +1132,19 @@ int psg_umma_gemm_lane(const PsgGemmDesc* d, int block_n, int m_tiles, int lane,
   kp.N = (int)d->N;
   kp.epi = d->epi;
   PSG_CHECK_ARG(d->split_k <= 1, "psg_umma_gemm: split-K is gone (stream-K scheduling balances the k-range itself)");
-  plan_tiles(mode, bm == PSG_OP_IM2COL_T, d->M, d->N, d->K, &block_n, &m_tiles);
+  plan_tiles(mode, bm == PSG_OP_IM2COL_T, am == PSG_OP_KMAJOR, d->M, d->N, d->K, &block_n, &m_tiles);
   // B-multicast pairs: two CTAs on vertically adjacent row tiles share one B tile (each fetches half of it)
   // CTA pairs (cta_group::2).  Measured on this model's shapes (profiles/r01_bench_gemm_modes.txt): a gain of 10-25% for
-  // the NT (wgrad) reductions when the 2x taller pair tile does not add much row padding, nothing for TN / TT (equal to a
-  // single CTA within noise, slightly worse at short K) -- so only the former use them unless forced (psg_umma_pairs(2)).
+  // the NT (wgrad) reductions when the 2x taller pair tile does not add much row padding, nothing for TT and the im2col
+  // products (conv fprop / dgrad: equal to a single CTA within noise); round 2: the plain TN products take them too (tn_pairs).
   const DeviceState& ds = dev_state();
   const int free_sms = psg_num_sms() - ds.reserve_sms > 8 ? psg_num_sms() - ds.reserve_sms : 8;
   int cl = 1, units = free_sms;
   if (g_pairs_on && block_n % 128 == 0 && d->M > (long long)BLOCK_M * m_tiles) {
     const long long rows1 = (d->M + BLOCK_M * m_tiles - 1) / (BLOCK_M * m_tiles) * (BLOCK_M * m_tiles);
     const long long rows2 = (d->M + 2 * BLOCK_M * m_tiles - 1) / (2 * BLOCK_M * m_tiles) * (2 * BLOCK_M * m_tiles);
-    const bool worth = g_pairs_on == 2 || (mode == 1 && rows2 * 4 <= rows1 * 5);
+    const bool worth = g_pairs_on == 2 || (mode == 1 && rows2 * 4 <= rows1 * 5) ||
+                       (m_tiles == 1 && tn_pairs(mode, am == PSG_OP_KMAJOR, d->M, block_n));
     const int pairs = worth ? max_resident_pairs() : 0;
     if (pairs >= 8) { cl = 2; units = pairs < free_sms / 2 ? pairs : free_sms / 2; }
   }

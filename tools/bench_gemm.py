@@ -42,6 +42,11 @@ def wgrad(B, H, cin, cout, split=1, bn=128, mt=0):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+import os
+if os.environ.get("PSG_UMMA_PAIRS"):        # 0 never, 1 the planner's rule, 2 always (where the tile shape allows)
+    from pokemon_sprite_generator_b200 import _lib as _L
+    _L.load().psg_umma_pairs(int(os.environ["PSG_UMMA_PAIRS"]))
+    print("psg_umma_pairs =", os.environ["PSG_UMMA_PAIRS"])
 B = 256
 if which in ("all", "fprop"):
     for mt in (1, 2):
@@ -85,3 +90,22 @@ if which == "wgrad_auto":
     for (H, cin, cout) in [(14, 640, 640), (27, 320, 320), (14, 1280, 640), (27, 640, 320), (7, 1280, 1280), (4, 1280, 1280), (7, 2560, 1280),
                            (4, 2560, 1280), (14, 320, 640), (7, 640, 1280), (14, 1920, 640), (27, 960, 320)]:
         wgrad(B, H, cin, cout, 1, 0, 0)
+if which == "linear_sweep":
+    # the Linear / attention-projection forward + dgrad shapes (TN, short K) of a batch-256 step: tile shape x pairing against the
+    # planner's own choice (bn = mt = 0), plain bf16 epilogue
+    from pokemon_sprite_generator_b200 import _lib as L
+    shapes = [(50176, 640, 640), (50176, 1280, 640), (50176, 640, 1280), (50176, 1920, 640), (50176, 640, 1920), (12544, 1280, 1280),
+              (12544, 2560, 1280), (12544, 1280, 2560), (12544, 3840, 1280), (4096, 1280, 1280), (8192, 1280, 2560), (8192, 2560, 1280)]
+    for (M, N, K) in shapes:
+        for pairs in (1, 2):
+            L.load().psg_umma_pairs(pairs)
+            for bn, mt in ((0, 0),) if pairs == 1 else ((256, 1), (256, 2), (128, 1), (128, 2)):
+                print(f"pairs={pairs} ", end="")
+                tiled(M, N, K, bn, mt)
+        L.load().psg_umma_pairs(0)
+        for bn, mt in ((256, 2), (160, 1), (160, 2), (128, 1), (128, 2)):
+            if bn == 160 and N % 160:
+                continue
+            print("pairs=0 ", end="")
+            tiled(M, N, K, bn, mt)
+    L.load().psg_umma_pairs(1)

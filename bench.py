@@ -60,7 +60,35 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
+    def _nvml(self):
+        """In-process NVML sampling (nvidia_ml_py): no fork of a 40 GB process every 0.2 s next to a timed loop whose host side is
+        only ~1.6x ahead of the GPU.  Returns False when NVML is unusable (the nvidia-smi loop below runs instead)."""
+        if os.environ.get("PSG_CLOCKS") == "smi":
+            return False
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+            get_reasons(h)
+        except Exception:
+            return False
+        while not self._stop_evt.is_set():
+            try:
+                r = get_reasons(h)
+                self.rows.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), str(N.nvmlDeviceGetPowerUsage(h) / 1e3)] +
+                                 ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+        return True
+
     def run(self):
+        if self._nvml():
+            return
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],

@@ -1089,8 +1089,9 @@ static void plan_tiles(int mode, int b_im2col, int a_plain, long long M, long lo
     // 256-row CTA tiles (two MMAs share the B tile) pay off for long reductions with no extra row padding; short-K
     // GEMMs prefer 128-row tiles with double-buffered TMEM (epilogue overlap).  Stream-K balances any tile count.
     // The conv wgrad (NT over im2col pixels) runs ~1.6x faster per MMA row with 256-row tiles, so it takes them even with
-    // padded rows; the plain NT products (Linear wgrad) were measured faster with 128-row tiles unless 256 divides M.
-    if (M > 128 && ((mode == 1 && b_im2col && pad2 * 2 <= pad1 * 3) || (mode == 1 && !b_im2col && pad2 == pad1 && N >= 1024) ||
+    // padded rows; the plain NT products (Linear wgrad) were measured faster with 128-row tiles unless 256 divides M and the
+    // reduction is long (K = 4096, the 4x4 level: 38 vs 54 us at 1280 x 1280, profiles/r02_bench_linear_tile_sweep.txt).
+    if (M > 128 && ((mode == 1 && b_im2col && pad2 * 2 <= pad1 * 3) || (mode == 1 && !b_im2col && pad2 == pad1 && N >= 1024 && K >= 8192) ||
                     (mode != 1 && pad2 == pad1 && K >= 2048)))
       mt = 2;
     if (tn_pairs(mode, a_plain, M, bn)) mt = 1;

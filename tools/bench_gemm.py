@@ -109,3 +109,17 @@ if which == "linear_sweep":
             print("pairs=0 ", end="")
             tiled(M, N, K, bn, mt)
     L.load().psg_umma_pairs(1)
+if which == "lwgrad_sweep":
+    # Linear weight gradients (NT: dW[n_out][k_in] = sum_tokens dY[t, n_out] X[t, k_in]) of a batch-256 step: tile shape x pairing
+    from pokemon_sprite_generator_b200 import _lib as L
+    shapes = [(640, 640, 50176), (1280, 1280, 12544), (1280, 1280, 4096), (2560, 1280, 8192), (640, 1280, 50176), (1280, 2560, 12544),
+              (3840, 1280, 12544), (1920, 640, 50176), (1280, 640, 50176), (2560, 1280, 12544), (2560, 1280, 4096), (1280, 2560, 4096)]
+    for (M, N, K) in shapes:
+        dy = torch.randn(K, M, device=dev).bfloat16(); x = torch.randn(K, N, device=dev).bfloat16()
+        out = torch.empty(M, N, device=dev)
+        for pairs, combos in ((1, ((0, 0),)), (0, ((256, 1), (256, 2), (128, 1), (128, 2))), (2, ((256, 1), (256, 2), (128, 1), (128, 2)))):
+            L.load().psg_umma_pairs(pairs)
+            for bn, mt in combos:
+                timeit(lambda: G.run_gemm(G.mnmajor(dy), G.mnmajor(x), G.Epilogue(out=out), engine="umma", block_n=bn, m_tiles=mt), 2.0 * M * N * K,
+                       f"pairs={pairs} lwgrad M={M} N={N} K={K} bn={bn} mt={mt}")
+    L.load().psg_umma_pairs(1)

@@ -76,8 +76,16 @@ def check(rc: int, what: str = "") -> None:
         raise PsgError(f"{what or 'psg call'} failed (rc={rc}): {msg}")
 
 
+def raw_stream(device=None) -> int:
+    """cudaStream_t of torch's current stream on `device` (default: the current device) as an integer.  The raw accessor, not
+    torch.cuda.current_stream(): that builds a Stream object through several Python layers (device-index resolution, an
+    os.getenv per call) and at ~1350 calls per train step was a fifth of the step's host time (tools/host_profile.py)."""
+    idx = torch.cuda.current_device() if device is None else (device.index if device.index is not None else torch.cuda.current_device())
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
 def stream_ptr() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(raw_stream())
 
 
 def ptr(t) -> C.c_void_p:

@@ -60,7 +60,7 @@ def colsum(x: torch.Tensor, groups: int, out_groups: torch.Tensor | None, out_to
     # zero-initialised: [0] is the fused kernel's counter.  One buffer PER STREAM: backward runs bias column sums on its
     # second stream (engine._weight_stream) next to the main stream's conditioning column sums, and two kernels sharing the
     # counter / partial slots corrupt each other's sums (seen as a wrong init_conv.bias gradient in the batch-256 parity test)
-    ws = workspace(x.device, 32 + groups * s * min(c, 4096), f"colsum@{torch.cuda.current_stream(x.device).cuda_stream}")
+    ws = workspace(x.device, 32 + groups * s * min(c, 4096), f"colsum@{L.raw_stream(x.device)}")
     L.call("psg_colsum", L.ptr(x), C.c_longlong(_ld(x)), C.c_int(groups), C.c_int(rpg), C.c_int(c), L.ptr(out_groups),
            C.c_longlong(out_groups.stride(0) if out_groups is not None else 0), C.c_int(int(acc_groups)), L.ptr(out_total),
            C.c_int(int(acc_total)), C.c_float(scale), L.ptr(ws), C.c_int(L.dt(x)), L.stream_ptr())

@@ -24,6 +24,10 @@ from . import gemm as G
 from . import ops as K
 from .unet import LEVELS
 
+# gradient buckets: "main" (default) joins the weight stream into the main stream before a bucket's all-reduce; "side" issues the
+# all-reduce with the weight stream current instead (no stall of the dX chain).  Measured equal at 2 GPUs (86.2 vs 86.1-86.6 ms,
+# profiles/r02_bench_bucket_issue_ab.txt), so the simpler, longer-validated ordering stays the default.
+_BUCKET_ISSUE_MAIN = os.environ.get("PSG_BUCKET_ISSUE", "main") == "main"
 _WGRAD_STREAM = os.environ.get("PSG_WGRAD_STREAM", "1") != "0"  # A/B switch: 0 = weight gradients on the main stream
 _DGRAD_S2 = os.environ.get("PSG_DGRAD_S2", "1") != "0"     # A/B switch: 0 = zero-inserted stride-1 dgrad for the downsample convs
 
@@ -479,6 +483,18 @@ class UNetEngine:
         ev = torch.cuda.Event()
         ev.record(side)
         self._wbusy[dy.data_ptr()] = ev
+
+    @contextlib.contextmanager
+    def _bucket_issue_ctx(self):
+        """The weight-gradient stream, caught up with the main stream, as the current stream: what is enqueued inside is ordered
+        after everything launched so far on either stream (GradSync issues a bucket's all-reduce here)."""
+        side = self.wstream
+        if side is None:
+            yield
+            return
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            yield
 
     def _join_weight_stream(self) -> None:
         if self.wstream is not None:
@@ -959,7 +975,13 @@ class UNetEngine:
                 self._join_weight_stream()
             return
         grad_sync.begin(self.store, len(tape))
-        grad_sync.before_issue = self._join_weight_stream      # a bucket's all-reduce is ordered after the main stream only
+        # A bucket's all-reduce must follow the kernels of BOTH streams: either the weight stream is joined into the main stream
+        # before every bucket (~20 per backward), or the collective is issued with the weight stream current after that stream has
+        # waited for the main one (PSG_BUCKET_ISSUE=side).
+        if _BUCKET_ISSUE_MAIN:
+            grad_sync.before_issue, grad_sync.issue_ctx = self._join_weight_stream, None
+        else:
+            grad_sync.before_issue, grad_sync.issue_ctx = None, self._bucket_issue_ctx
         try:
             done = 0
             while tape:

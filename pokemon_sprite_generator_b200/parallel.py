@@ -89,7 +89,10 @@ class GradSync:
         self.bounds: List[Tuple[int, int]] = []
         self.stats = {"calibrations": 0, "overlapped_buckets": 0, "tail_buckets": 0}
         self._reserved = 0
-        self.before_issue: Optional[Callable[[], None]] = None     # the engine joins its weight-gradient stream here
+        self.before_issue: Optional[Callable[[], None]] = None     # called before a bucket goes out (e.g. a stream join)
+        # context manager factory entered around the all-reduce call: the engine makes its weight-gradient stream current there, so
+        # that the collective is ordered after BOTH streams without stalling the main (dX) stream at every bucket
+        self.issue_ctx: Optional[Callable[[], object]] = None
 
     def _reserve(self, n: int) -> None:
         if self.reserve_hook is not None and n != self._reserved:
@@ -154,7 +157,11 @@ class GradSync:
         if self.world > 1 and e > s:
             if self.before_issue is not None:
                 self.before_issue()
-            self.works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if self.issue_ctx is not None:
+                with self.issue_ctx():
+                    self.works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                self.works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def after_entry(self, done: int) -> None:
         log = self.store.touch_log

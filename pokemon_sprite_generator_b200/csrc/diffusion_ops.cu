@@ -22,7 +22,7 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fm
 __global__ void __launch_bounds__(kThreads)
 q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
                 const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac, float* __restrict__ out,
-                int n_per, int num_t, int do_clamp, float clo, float chi, int* __restrict__ nonfinite) {
+                int n_per, int num_t, int do_clamp, float clo, float chi, int* __restrict__ nonfinite, int vec_ok) {
   const int b = blockIdx.y;
   long long ti = t[b];
   ti = ti < 0 ? 0 : (ti >= num_t ? num_t - 1 : ti);
@@ -30,7 +30,7 @@ q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, c
   const float s = sqrt_1mac[ti];
   const size_t base = (size_t)b * n_per;
   int bad = 0;
-  if ((n_per & 3) == 0) {
+  if (vec_ok) {             // n_per % 4 == 0 and 16-byte aligned bases (decided by the launcher)
     const int n4 = n_per >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(x0 + base);
     const float4* e4 = reinterpret_cast<const float4*>(noise + base);
@@ -188,8 +188,10 @@ int psg_q_sample(const float* x0, const float* noise, const long long* t, const 
   PSG_CHECK_ARG(batch <= 65535, "psg_q_sample: batch > 65535");
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(grid_for((size_t)(n_per + 3) / 4, 64), batch);
+  // float4 path only for whole vectors at 16-byte aligned addresses (a sliced / offset view takes the scalar path)
+  const int vec_ok = (n_per % 4 == 0) && ((uintptr_t)x0 % 16 == 0) && ((uintptr_t)noise % 16 == 0) && ((uintptr_t)out % 16 == 0);
   q_sample_kernel<<<grid, kThreads, 0, s>>>(x0, noise, t, sqrt_ac, sqrt_1mac, out, n_per, num_t, do_clamp,
-                                            clamp_lo, clamp_hi, nonfinite);
+                                            clamp_lo, clamp_hi, nonfinite, vec_ok);
   PSG_CHECK_LAUNCH("psg_q_sample");
   if (nonfinite != nullptr) {
     size_t n = (size_t)batch * n_per;

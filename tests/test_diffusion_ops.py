@@ -48,6 +48,24 @@ def test_q_sample_bit_exact(cuda_device, gold):
     assert np.array_equal(out.cpu().numpy(), ref)
 
 
+def test_q_sample_offset_views(cuda_device):
+    """Contiguous views that start 4 bytes into their storage (a slice of a flat buffer): per-sample size is a multiple of 4 but the
+    base is not 16-byte aligned, so the launcher must take the scalar path (a float4 access there is a misaligned-address fault).
+    Bit-identical to the aligned call."""
+    from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
+    ns = NoiseScheduler()
+    B, n = 5, 8 * 27 * 27
+    flat_x, flat_e = torch.randn(B * n + 3, device="cuda"), torch.randn(B * n + 3, device="cuda")
+    t = torch.tensor([0, 1, 500, 998, 999], device="cuda")
+    for off in (1, 2, 3):
+        x, e = flat_x[off:off + B * n].view(B, 8, 27, 27), flat_e[off:off + B * n].view(B, 8, 27, 27)
+        assert x.data_ptr() % 16 != 0 and x.is_contiguous()
+        got = ns.add_noise(x, e, t, clamp=3.0)
+        want = ns.add_noise(x.clone(), e.clone(), t, clamp=3.0)
+        assert torch.equal(got, want)
+    torch.cuda.synchronize()
+
+
 def test_q_sample_edge_cases(cuda_device):
     from pokemon_sprite_generator_b200.scheduler import NoiseScheduler
     ns = NoiseScheduler()

@@ -571,6 +571,17 @@ def main():
                 hbm_kernels[fam] = {"ms_per_step": round(tot[cname], 3), "algorithmic_gb": round(nbytes / 1e9, 3), "achieved_gbs": round(gbs, 1),
                                     "frac": round(gbs / peaks["hbm_gbs"], 3) if peaks["hbm_gbs"] else None}
 
+        # 43 of the 61 backward norms ADD into an existing gradient (x also feeds a residual connection: every ResBlock norm1 and
+        # both norms of an attention block; template argument ACCUM = 1 in profiles/r02_launches_summary_v2.md), so they also read
+        # dx: 4 N s instead of 3 N s.  N_accum = 729*1920 + 196*8960 + 49*17920 + 16*21760 = 4,382,080 activations per sample.
+        if "groupnorm_bwd" in hbm_kernels:
+            gb = hbm_kernels["groupnorm_bwd"]
+            nbytes = (3 * n_act + 4382080 * B) * 2
+            gbs = nbytes / (gb["ms_per_step"] / 1e3) / 1e9
+            gb["with_accumulate_reads"] = {"algorithmic_gb": round(nbytes / 1e9, 3), "achieved_gbs": round(gbs, 1),
+                                           "frac": round(gbs / peaks["hbm_gbs"], 3) if peaks["hbm_gbs"] else None,
+                                           "note": "43 of 61 norms accumulate into dx (4 N s bytes); the 3 N s figure above is SURVEY 8d's"}
+
     # q_sample / SmoothL1 / DDPM reverse step at a roofline batch (at batch 256 they are L2-resident 10-20 us
     # launches): batch 8192 => 191 MB per tensor (> the 126 MB L2), each kernel timed alone, 20 launches, CUDA events.
     # algorithmic bytes per sample: q_sample 3 x 5832 x 4, SmoothL1 fwd+bwd 3 x 5832 x 4, DDPM step 4 x 5832 x 4

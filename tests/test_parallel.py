@@ -99,6 +99,18 @@ def _sync_worker(rank, world, port, q):
     order = [[7], [6, 1], [5], [4, 3], [], [2, 1], [0]]
     reserved = []
     sync = GradSync(None, bucket_bytes=4 * 1024, reserve_sms=8, reserve_hook=reserved.append, prescaled=False)
+    # the engine's hooks around a bucket's all-reduce: before_issue (a stream join) and issue_ctx (a stream made current)
+    import contextlib
+    hook_log = []
+
+    @contextlib.contextmanager
+    def issue_ctx():
+        hook_log.append("enter")
+        yield
+        hook_log.append("exit")
+
+    sync.before_issue = lambda: hook_log.append("before")
+    sync.issue_ctx = issue_ctx
     results = []
     for step in range(3):
         values = [float((rank + 1) * (i + 1) + step) for i in range(len(sizes))]
@@ -111,6 +123,9 @@ def _sync_worker(rank, world, port, q):
     ok_plan = st["calibrations"] == 1 and st["overlapped_buckets"] > 0 and store.touch_log is None
     # steps 2 and 3 issue most buckets from inside backward; the SM reservation is raised then and always released
     ok_hook = reserved.count(8) >= 2 and reserved[-1] == 0
+    # every all-reduce went out inside the context, after the before-hook: (before, enter, exit) per issued bucket
+    n_issued = len(hook_log) // 3
+    ok_hook = ok_hook and n_issued >= len(sync.bounds) and hook_log == ["before", "enter", "exit"] * n_issued
     # a tape that writes a bucket after it was reduced must be caught, not silently mis-reduced
     caught = False
     try:

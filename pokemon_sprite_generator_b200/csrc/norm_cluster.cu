@@ -47,6 +47,7 @@ struct Shape {
   int threads;
   int pf;                      // L2 prefetch distance in units (the same rank of the cluster `pf` units ahead); 0 = none
   int strict;                  // 1: every thread arrives with .release (A/B switch, env PSG_GN_STRICT_BARRIER=1)
+  int pf_dx;                   // backward with accumulate: ask L2 for this CTA's own dx rows while x and dy are in flight
 };
 
 static int plan(Shape& s, int B, int HW, int C, int G, int bwd) {
@@ -97,6 +98,10 @@ static void plan_prefetch(Shape& s, int bwd) {
   s.pf = 0;
   static const int strict = getenv("PSG_GN_STRICT_BARRIER") ? atoi(getenv("PSG_GN_STRICT_BARRIER")) : 0;
   s.strict = strict;
+  // accumulate variants (43 of a step's 61 backward norms) re-read dx in the store pass, a dependent global load per row with
+  // nothing to hide it; requesting those lines at kernel start makes them L2 hits (PSG_GN_PREFETCH_DX=0 for A/B)
+  static const int pf_dx = getenv("PSG_GN_PREFETCH_DX") ? atoi(getenv("PSG_GN_PREFETCH_DX")) : 1;
+  s.pf_dx = bwd ? pf_dx : 0;
   if (g_tune[6] <= 0) return;
   // forward only by default: the backward is not waiting for DRAM (same time with and without, profiles/
   // r02_bench_groupnorm_prefetch_sweep.txt) and the requests cost it 7 % more instructions; PSG_GN_PREFETCH_BWD=1 for A/B
@@ -399,6 +404,11 @@ __global__ void __launch_bounds__(kMaxThreads / 2 + 64, 2) gn_cluster_bwd_kernel
       const bool ok = p < nrows;
       cp_async16(dst, ok ? sx : x, ok ? 16 : 0);
       cp_async16(dst + off_d, ok ? sd : dy, ok ? 16 : 0);
+    }
+    if (ACCUM && s.pf_dx && (v & 7) == 0) {      // this CTA's own dx rows (read back in the store pass): one request per 128-byte line
+      const __nv_bfloat16* po = dx + ((long long)b * s.HW + row0 + row) * lddx + c0;
+      const long long stepo = (long long)s.R * lddx;
+      for (int p = row; p < nrows; p += s.R, po += stepo) prefetch_l2(po);
     }
     // the same rows of the unit that runs one residency later: one request per 128-byte line of a row piece
     const int unit_pf = unit + s.pf;

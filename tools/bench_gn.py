@@ -34,6 +34,7 @@ lib.psg_groupnorm_stream_tune.restype = ctypes.c_longlong
 if os.environ.get("PSG_GNS_TUNE"):          # streaming backward: "group bytes,rows per chunk,min tensor bytes"
     for i, v in enumerate(os.environ["PSG_GNS_TUNE"].split(",")):
         lib.psg_groupnorm_stream_tune(i, ctypes.c_longlong(int(v)))
+ACC = os.environ.get("PSG_GN_BENCH_ACC") == "1"          # backward accumulates into dx (4 N bytes; the GB/s printed still count 3 N)
 ONLY = sys.argv[2] if len(sys.argv) > 2 else ""          # "cluster" / "stream": time only that family (for ncu); "fast": both, no slab
 for hw, c in SHAPES:
     x = torch.randn(B * hw, c, device=dev).bfloat16()
@@ -49,7 +50,7 @@ for hw, c in SHAPES:
             continue
         lib.psg_groupnorm_fused_mode(mode)
         t_f = timeit(lambda: K.groupnorm_fused_fwd(x, y, gamma, beta, stats, B, 32, 1e-5, True))
-        t_b = timeit(lambda: K.groupnorm_fused_bwd(dy, x, dx, gamma, beta, stats, dg, db, B, 32, True, False))
+        t_b = timeit(lambda: K.groupnorm_fused_bwd(dy, x, dx, gamma, beta, stats, dg, db, B, 32, True, ACC))
         res[name] = (t_f, t_b)
     lib.psg_groupnorm_fused_mode(0)
     print(f"HW={hw:4d} C={c:5d} {nbytes / 1e6:7.1f} MB | " + " | ".join(
